@@ -1,0 +1,197 @@
+/*
+ * mcan_b200.h -- C ABI of the B200-native MCAN co-attention hot path.
+ *
+ * The reference (Originofamonia/mcan-vqa) is pure Python/PyTorch and has no FFI of its
+ * own; every arithmetic step of its hot path is an ATen call issued from
+ *   core/model/mca.py      (MHAtt 18-78, FFN 85-98, SA 105-127, SGA 134-164, MCA_ED 171-186)
+ *   core/model/net_utils.py (FC 11-34, MLP 37-45, LayerNorm 48-60)
+ *   core/model/net.py      (AttFlat 20-55).
+ * This header is the boundary a maintainer of the reference binds to instead of those
+ * ATen calls (ctypes stub: see INTEGRATION.md).  Each entry point names the reference
+ * lines it replaces.
+ *
+ * Conventions
+ *   - plain C: raw device pointers, sizes, strides in ELEMENTS, POD arg structs.
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated
+ *     here except a process-wide cache of TMA descriptors.
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t passed as void*); it never
+ *     synchronises.  Safe to capture into a CUDA graph.
+ *   - return 0 on success, <0 on error; mcan_last_error() returns a thread-local message.
+ *   - sm_100a only.  There is no CPU path: without a B200 the calls fail with an error.
+ *   - "bf16" pointers are `void*` to __nv_bfloat16 data; activations are row-major
+ *     [rows, features] with rows = batch * sequence.
+ *   - dropout masks are never stored: forward and backward regenerate them from
+ *     (seed, element index) with the hash in csrc/common.cuh.
+ */
+#ifndef MCAN_B200_H_
+#define MCAN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCAN_B200_ABI_VERSION 1
+#define MCAN_MAX_GEMM_SEGMENTS 3
+
+/* -- library ----------------------------------------------------------------------- */
+int mcan_version(void);
+const char* mcan_last_error(void);
+/* number of SMs of the current device (persistent kernels size their grids with it) */
+int mcan_num_sms(void);
+
+/* -- G1/G2/G3: tcgen05 GEMM with fused epilogue --------------------------------------
+ * D[M,N] = epilogue( sum_{s<num_seg} A_s[M,K] * B_s[N,K]^T )         (fp32 accumulate in TMEM)
+ *
+ * Replaces nn.Linear forward (mca.py:33,40,47,61; net_utils.py:26,45; net.py:39,53) and the
+ * autograd dgrad / wgrad GEMMs of the same layers.
+ *
+ *   a_layout 0: A_s is stored [M,K] row-major (lda >= K)     -- activations, forward/dgrad
+ *   a_layout 1: A_s is stored [K,M] row-major (lda >= M)     -- wgrad: A = dY^T, stored as dY
+ *   b_layout 0: B_s is stored [N,K] row-major (ldb >= K)     -- nn.Linear weight (out,in)
+ *   b_layout 1: B_s is stored [K,N] row-major (ldb >= N)     -- dgrad: B = W^T stored as W;
+ *                                                               wgrad: B = X^T stored as X
+ * num_seg > 1 sums several operand pairs into one accumulator (split-precision
+ * "bf16x3": (A_hi,B_hi) + (A_hi,B_lo) + (A_lo,B_hi)).
+ *
+ * Epilogue, applied in this order to v = acc:
+ *   v += bias[n]                         (bias != NULL)
+ *   v  = max(v, 0)                       (relu)
+ *   v  = keep(m*N+n) ? v/(1-p) : 0       (dropout_p > 0)
+ *   v  = gate[m,n] > 0 ? v*gate_scale : 0  (gate != NULL; backward through ReLU+dropout)
+ *   v += resid[m,n]                      (resid != NULL, fp32)
+ *   out_f32[m,n] = v / out_bf16[m,n] = bf16(v) / out_bf16_lo[m,n] = bf16(v - bf16(v))
+ * accumulate != 0: out_f32[m,n] += v with fp32 atomics (required for split_k > 1; only
+ * out_f32 may be set and no other epilogue stage).
+ * Alignment: operand base pointers 16 B, leading dimensions multiples of 8 elements.
+ */
+typedef struct mcan_gemm_args {
+    const void* a[MCAN_MAX_GEMM_SEGMENTS];
+    const void* b[MCAN_MAX_GEMM_SEGMENTS];
+    int32_t num_seg;
+    int32_t a_layout;
+    int32_t b_layout;
+    int64_t m, n, k;
+    int64_t lda, ldb;
+
+    const float* bias;
+    int32_t relu;
+    float dropout_p;
+    uint32_t dropout_seed;
+    const void* gate;
+    int64_t ldg;
+    float gate_scale;
+    const float* resid;
+    int64_t ldr;
+
+    float* out_f32;
+    int64_t ldo_f32;
+    void* out_bf16;
+    void* out_bf16_lo;
+    int64_t ldo_bf16;
+
+    int32_t accumulate;
+    int32_t split_k; /* 0 = choose automatically (only when accumulate != 0) */
+    int32_t block_n; /* 0 = choose automatically, else 128 or 256 */
+    void* stream;
+} mcan_gemm_args;
+
+int mcan_gemm(const mcan_gemm_args* args);
+
+/* -- A1: fused masked-softmax attention, one CTA per (batch, head) -------------------
+ * Replaces MHAtt.att (mca.py:65-78) plus the head split/merge transposes (mca.py:33-59):
+ *   P = softmax(masked_fill(Q K^T * scale, key_mask, -1e9)); P = dropout(P); O = P V
+ * q/k/v/out address row (b*S + s) and columns [h*head_dim, (h+1)*head_dim) of bf16
+ * matrices with leading dimensions ldq/ldk/ldv/ldo, so a fused [rows,3H] QKV buffer or a
+ * cross-layer K/V buffer can be used in place.  key_mask: uint8 [batch, sk], 1 = masked,
+ * may be NULL.  A fully masked row yields the uniform 1/sk distribution, like the
+ * reference.  sq, sk <= 128; head_dim in {64, 128}.
+ */
+typedef struct mcan_attn_args {
+    const void* q;
+    const void* k;
+    const void* v;
+    int64_t ldq, ldk, ldv;
+    const uint8_t* key_mask;
+    void* out;
+    int64_t ldo;
+    int32_t batch, heads, sq, sk, head_dim;
+    float scale;
+    float dropout_p;
+    uint32_t dropout_seed;
+    void* stream;
+} mcan_attn_args;
+
+int mcan_attn_fwd(const mcan_attn_args* args);
+
+/* backward of the above: recomputes P from Q,K (no probabilities are saved) and the
+ * dropout mask from the seed.  dq/dk/dv are bf16 with the same addressing as q/k/v. */
+typedef struct mcan_attn_bwd_args {
+    mcan_attn_args fwd; /* same q,k,v,key_mask,shape,scale,dropout as the forward call; out unused */
+    const void* dout;   /* bf16, [batch*sq, heads*head_dim] */
+    int64_t lddo;
+    void* dq;
+    void* dk;
+    void* dv;
+    int64_t lddq, lddk, lddv;
+} mcan_attn_bwd_args;
+
+int mcan_attn_bwd(const mcan_attn_bwd_args* args);
+
+/* -- L1: MCAN LayerNorm (net_utils.py:48-60) -----------------------------------------
+ * y = a_2 * (x - mean) / (std_unbiased + eps) + b_2 over the last dimension (h).
+ * NOT torch.nn.functional.layer_norm: std uses N-1 and eps is added to std.
+ * Writes y as fp32 and (optionally) bf16 / bf16-lo copies for the next GEMM, and the row
+ * statistics mean[rows], sigma[rows] (sigma = unbiased std, without eps) for backward.
+ */
+int mcan_layernorm_fwd(const float* x, int64_t rows, int64_t h, const float* a2, const float* b2,
+                       float eps, float* y_f32, void* y_bf16, void* y_bf16_lo, float* mean,
+                       float* sigma, void* stream);
+
+/* dx = LayerNorm backward, plus:
+ *   dx_bf16 (optional) = bf16( dropout_mask(seed)[r,c] * dx / (1-p) )  -- the gradient that flows
+ *       into the GEMM whose epilogue produced x = resid + dropout(gemm), ready as a GEMM operand;
+ *   da2[h] += sum_r dy*c/s, db2[h] += sum_r dy, dbias[h] += sum_r dx_bf16 value (optional) -- atomics.
+ */
+int mcan_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* sigma,
+                       const float* a2, float eps, int64_t rows, int64_t h, float* dx_f32,
+                       void* dx_bf16, float dropout_p, uint32_t dropout_seed, float* da2,
+                       float* db2, float* dbias, void* stream);
+
+/* -- F1: AttFlat pooling (net.py:38-55) ----------------------------------------------
+ * Input hmid = dropout(relu(x W1^T + b1)) comes from mcan_gemm (bf16 [batch*s, mlp]).
+ *   logit[b,s,g] = hmid[b,s,:] . w2[g,:] + b2[g];  masked_fill(mask, -1e9)
+ *   att_w = softmax over s;  pooled[b, g*h : (g+1)*h] = sum_s att_w[b,s,g] * x[b,s,:]
+ * pooled is written as fp32 and bf16 (operand of linear_merge).  One CTA per sample.
+ */
+int mcan_attflat_pool_fwd(const void* hmid, const float* w2, const float* b2, const uint8_t* mask,
+                          const float* x, int32_t batch, int32_t s, int32_t h, int32_t mlp,
+                          int32_t glimpses, float* att_w, float* pooled_f32, void* pooled_bf16,
+                          void* stream);
+
+/* backward: dpooled fp32 [batch, g*h] ->
+ *   dx[b,s,:]  = sum_g att_w[b,s,g] * dpooled[b,g,:]                       (fp32, overwritten)
+ *   dlogit     = softmax backward of d att_w[b,s,g] = dpooled[b,g,:] . x[b,s,:]; 0 where masked
+ *   dhmid      = bf16( (hmid > 0) * gate_scale * sum_g dlogit[.,g] * w2[g,:] )  (through ReLU+dropout)
+ *   dw2 += dlogit^T hmid, db2 += sum dlogit                                 (fp32 atomics)
+ */
+int mcan_attflat_pool_bwd(const float* dpooled, const void* hmid, const float* w2,
+                          const uint8_t* mask, const float* x, const float* att_w, int32_t batch,
+                          int32_t s, int32_t h, int32_t mlp, int32_t glimpses, float gate_scale,
+                          float* dx, void* dhmid, float* dw2, float* db2, void* stream);
+
+/* -- small memory-bound helpers -------------------------------------------------------- */
+/* hi = bf16(x); lo (optional) = bf16(x - hi).  n elements. */
+int mcan_cast_bf16(const float* x, int64_t n, void* hi, void* lo, void* stream);
+/* out[c] += sum_r x[r,c]   (x bf16 [rows, cols] with leading dimension ld; fp32 atomics) */
+int mcan_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64_t ld, float* out,
+                     void* stream);
+/* out[c] += sum_r x[r,c]   (x fp32) */
+int mcan_colsum_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCAN_B200_H_ */

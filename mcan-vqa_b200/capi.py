@@ -1,0 +1,144 @@
+"""ctypes binding of the C ABI declared in include/mcan_b200.h.
+
+No torch types cross this boundary: only raw device pointers (ints), sizes and a
+cudaStream_t.  There is no CPU fallback -- if the shared library cannot be loaded every
+entry point raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libmcan_b200.so")
+
+MAX_SEG = 3
+
+c_void_p = ctypes.c_void_p
+c_int32 = ctypes.c_int32
+c_int64 = ctypes.c_int64
+c_uint32 = ctypes.c_uint32
+c_float = ctypes.c_float
+
+
+class GemmArgs(ctypes.Structure):
+    _fields_ = [
+        ("a", c_void_p * MAX_SEG),
+        ("b", c_void_p * MAX_SEG),
+        ("num_seg", c_int32),
+        ("a_layout", c_int32),
+        ("b_layout", c_int32),
+        ("m", c_int64),
+        ("n", c_int64),
+        ("k", c_int64),
+        ("lda", c_int64),
+        ("ldb", c_int64),
+        ("bias", c_void_p),
+        ("relu", c_int32),
+        ("dropout_p", c_float),
+        ("dropout_seed", c_uint32),
+        ("gate", c_void_p),
+        ("ldg", c_int64),
+        ("gate_scale", c_float),
+        ("resid", c_void_p),
+        ("ldr", c_int64),
+        ("out_f32", c_void_p),
+        ("ldo_f32", c_int64),
+        ("out_bf16", c_void_p),
+        ("out_bf16_lo", c_void_p),
+        ("ldo_bf16", c_int64),
+        ("accumulate", c_int32),
+        ("split_k", c_int32),
+        ("block_n", c_int32),
+        ("stream", c_void_p),
+    ]
+
+
+class AttnArgs(ctypes.Structure):
+    _fields_ = [
+        ("q", c_void_p),
+        ("k", c_void_p),
+        ("v", c_void_p),
+        ("ldq", c_int64),
+        ("ldk", c_int64),
+        ("ldv", c_int64),
+        ("key_mask", c_void_p),
+        ("out", c_void_p),
+        ("ldo", c_int64),
+        ("batch", c_int32),
+        ("heads", c_int32),
+        ("sq", c_int32),
+        ("sk", c_int32),
+        ("head_dim", c_int32),
+        ("scale", c_float),
+        ("dropout_p", c_float),
+        ("dropout_seed", c_uint32),
+        ("stream", c_void_p),
+    ]
+
+
+class AttnBwdArgs(ctypes.Structure):
+    _fields_ = [
+        ("fwd", AttnArgs),
+        ("dout", c_void_p),
+        ("lddo", c_int64),
+        ("dq", c_void_p),
+        ("dk", c_void_p),
+        ("dv", c_void_p),
+        ("lddq", c_int64),
+        ("lddk", c_int64),
+        ("lddv", c_int64),
+    ]
+
+
+# every symbol include/mcan_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "mcan_version": (ctypes.c_int, []),
+    "mcan_last_error": (ctypes.c_char_p, []),
+    "mcan_num_sms": (ctypes.c_int, []),
+    "mcan_gemm": (ctypes.c_int, [ctypes.POINTER(GemmArgs)]),
+    "mcan_attn_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs)]),
+    "mcan_attn_bwd": (ctypes.c_int, [ctypes.POINTER(AttnBwdArgs)]),
+    "mcan_layernorm_fwd": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcan_layernorm_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                          c_int64, c_int64, c_void_p, c_void_p, c_float, c_uint32,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcan_attflat_pool_fwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                             c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
+                                             c_void_p, c_void_p]),
+    "mcan_attflat_pool_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                             c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcan_cast_bf16": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mcan_colsum_bf16": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+    "mcan_colsum_f32": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class McanError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads libmcan_b200.so (once).  Raises McanError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise McanError(
+            "libmcan_b200.so not found at %s -- build it with `python mcan-vqa_b200/build.py` "
+            "(there is no CPU or PyTorch fallback for the MCAN hot path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().mcan_last_error()
+        raise McanError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))

@@ -1,0 +1,123 @@
+// Small memory-bound helpers around the GEMMs: fp32 -> bf16 (hi [+ lo]) casts for GEMM
+// operands, and column sums (bias gradients = colsum of the GEMM output gradient).
+#include "../../include/mcan_b200.h"
+#include "common.cuh"
+
+namespace mcan {
+
+int device_num_sms();
+
+__global__ void __launch_bounds__(256)
+cast_bf16_kernel(const float* __restrict__ x, long long n, bf16* __restrict__ hi,
+                 bf16* __restrict__ lo) {
+    const long long nv = n >> 2;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        const float4 v = reinterpret_cast<const float4*>(x)[i];
+        uint2 w;
+        w.x = pack_bf16x2(v.x, v.y);
+        w.y = pack_bf16x2(v.z, v.w);
+        reinterpret_cast<uint2*>(hi)[i] = w;
+        if (lo != nullptr) {
+            uint2 l;
+            l.x = pack_bf16x2(v.x - bf16_lo_to_f(w.x), v.y - bf16_hi_to_f(w.x));
+            l.y = pack_bf16x2(v.z - bf16_lo_to_f(w.y), v.w - bf16_hi_to_f(w.y));
+            reinterpret_cast<uint2*>(lo)[i] = l;
+        }
+    }
+    // tail (n % 4 elements)
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long i = (nv << 2) + threadIdx.x;
+        const bf16 h = __float2bfloat16_rn(x[i]);
+        hi[i] = h;
+        if (lo != nullptr) lo[i] = __float2bfloat16_rn(x[i] - __bfloat162float(h));
+    }
+}
+
+// out[c] += sum_r x[r,c].  Block = 32 column groups x 8 row lanes; grid.y slices the rows.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+colsum_kernel(const T* __restrict__ x, long long rows, long long cols, long long ld,
+              float* __restrict__ out) {
+    __shared__ float s_part[8][32 * VEC + 1];
+    const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const long long c0 = ((long long)blockIdx.x * 32 + cg) * VEC;
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    if (c0 < cols) {
+        for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) {
+            const T* p = x + r * ld + c0;
+            if (c0 + VEC <= cols) {
+                if constexpr (sizeof(T) == 2) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(p);
+                    acc[0] += bf16_lo_to_f(v.x); acc[1] += bf16_hi_to_f(v.x);
+                    acc[2] += bf16_lo_to_f(v.y); acc[3] += bf16_hi_to_f(v.y);
+                    acc[4] += bf16_lo_to_f(v.z); acc[5] += bf16_hi_to_f(v.z);
+                    acc[6] += bf16_lo_to_f(v.w); acc[7] += bf16_hi_to_f(v.w);
+                } else {
+                    const float4 v = *reinterpret_cast<const float4*>(p);
+                    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+                }
+            } else {
+                for (int j = 0; j < VEC; ++j)
+                    if (c0 + j < cols) acc[j] += (float)p[j];
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) s_part[rl][cg * VEC + j] = acc[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * VEC; i += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s += s_part[r][i];
+        const long long c = (long long)blockIdx.x * 32 * VEC + i;
+        if (c < cols) atomicAdd(out + c, s);
+    }
+}
+
+template <typename T, int VEC>
+static int launch_colsum(const T* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream) {
+    MCAN_REQUIRE(x && out && rows > 0 && cols > 0, "mcan_colsum: bad args");
+    MCAN_REQUIRE(ld % VEC == 0 && ((uintptr_t)x & 15) == 0, "mcan_colsum: alignment (ld %% %d)", VEC);
+    const int sms = device_num_sms();
+    MCAN_REQUIRE(sms > 0, "mcan_colsum: no CUDA device");
+    const int gx = (int)((cols + 32 * VEC - 1) / (32 * VEC));
+    long long gy = (2LL * sms + gx - 1) / gx;
+    const long long maxy = (rows + 63) / 64;
+    if (gy > maxy) gy = maxy;
+    if (gy < 1) gy = 1;
+    colsum_kernel<T, VEC><<<dim3(gx, (unsigned)gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, rows, cols, ld, out);
+    MCAN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mcan
+
+using namespace mcan;
+
+extern "C" int mcan_cast_bf16(const float* x, int64_t n, void* hi, void* lo, void* stream) {
+    MCAN_REQUIRE(x && hi && n > 0, "mcan_cast_bf16: bad args");
+    MCAN_REQUIRE(((uintptr_t)x & 15) == 0 && (((uintptr_t)hi | (uintptr_t)lo) & 7) == 0, "mcan_cast_bf16: alignment");
+    const int sms = device_num_sms();
+    MCAN_REQUIRE(sms > 0, "mcan_cast_bf16: no CUDA device");
+    long long blocks = ((n >> 2) + 255) / 256;
+    if (blocks > 8LL * sms) blocks = 8LL * sms;
+    if (blocks < 1) blocks = 1;
+    cast_bf16_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        x, n, reinterpret_cast<bf16*>(hi), reinterpret_cast<bf16*>(lo));
+    MCAN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcan_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64_t ld, float* out,
+                                void* stream) {
+    return launch_colsum<bf16, 8>(reinterpret_cast<const bf16*>(x), rows, cols, ld, out, stream);
+}
+
+extern "C" int mcan_colsum_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out,
+                               void* stream) {
+    return launch_colsum<float, 4>(x, rows, cols, ld, out, stream);
+}

@@ -1,0 +1,239 @@
+"""Per-kernel Python entry points: torch tensors in, C-ABI calls out.
+
+PyTorch is plumbing here (device memory, the current stream); every arithmetic step is a
+kernel of libmcan_b200.so.  All functions enqueue on torch's current CUDA stream and never
+synchronise.  Tensors must be CUDA tensors; 2-D operands may be row-strided views
+(stride(1) == 1).  Nothing here falls back to PyTorch math.
+"""
+import ctypes
+
+import torch
+
+from . import capi
+
+_BF16 = torch.bfloat16
+_F32 = torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t, dtype, name):
+    if not t.is_cuda:
+        raise capi.McanError("%s must be a CUDA tensor (the MCAN hot path has no CPU fallback)" % name)
+    if t.dtype != dtype:
+        raise capi.McanError("%s must be %s, got %s" % (name, dtype, t.dtype))
+
+
+def _req2d(t, dtype, name):
+    _req(t, dtype, name)
+    if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise capi.McanError("%s must be 2-D with unit inner stride" % name)
+
+
+def num_sms():
+    return capi.load().mcan_num_sms()
+
+
+def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, seed=0, gate=None,
+         gate_scale=1.0, resid=None, out_f32=None, out_bf16=None, out_lo=None, accumulate=False,
+         split_k=0, block_n=0):
+    """D[M,N] = epilogue(sum_s A_s B_s^T) on the tcgen05 GEMM (see include/mcan_b200.h).
+
+    a / b: bf16 tensors or equal-length lists of them (segments).  a_layout 0: [M,K], 1: [K,M];
+    b_layout 0: [N,K] (nn.Linear weight), 1: [K,N].
+    """
+    lib = capi.load()
+    a_list = list(a) if isinstance(a, (list, tuple)) else [a]
+    b_list = list(b) if isinstance(b, (list, tuple)) else [b]
+    if len(a_list) != len(b_list) or not 1 <= len(a_list) <= capi.MAX_SEG:
+        raise capi.McanError("gemm: bad segment lists")
+    for t in a_list:
+        _req2d(t, _BF16, "gemm A")
+    for t in b_list:
+        _req2d(t, _BF16, "gemm B")
+    a0, b0 = a_list[0], b_list[0]
+    m, k = (a0.shape[0], a0.shape[1]) if a_layout == 0 else (a0.shape[1], a0.shape[0])
+    n, kb = (b0.shape[0], b0.shape[1]) if b_layout == 0 else (b0.shape[1], b0.shape[0])
+    if k != kb:
+        raise capi.McanError("gemm: contraction mismatch %d vs %d" % (k, kb))
+    args = capi.GemmArgs()
+    for i, (ta, tb) in enumerate(zip(a_list, b_list)):
+        if ta.shape != a0.shape or tb.shape != b0.shape or ta.stride(0) != a0.stride(0) or tb.stride(0) != b0.stride(0):
+            raise capi.McanError("gemm: segments must share shape and leading dimension")
+        args.a[i] = ta.data_ptr()
+        args.b[i] = tb.data_ptr()
+    args.num_seg = len(a_list)
+    args.a_layout, args.b_layout = a_layout, b_layout
+    args.m, args.n, args.k = m, n, k
+    args.lda, args.ldb = a0.stride(0), b0.stride(0)
+    if bias is not None:
+        _req(bias, _F32, "gemm bias")
+        args.bias = bias.data_ptr()
+    args.relu = 1 if relu else 0
+    args.dropout_p = float(dropout_p)
+    args.dropout_seed = int(seed) & 0xFFFFFFFF
+    if gate is not None:
+        _req2d(gate, _BF16, "gemm gate")
+        args.gate, args.ldg = gate.data_ptr(), gate.stride(0)
+    args.gate_scale = float(gate_scale)
+    if resid is not None:
+        _req2d(resid, _F32, "gemm resid")
+        args.resid, args.ldr = resid.data_ptr(), resid.stride(0)
+    if out_f32 is not None:
+        _req2d(out_f32, _F32, "gemm out_f32")
+        args.out_f32, args.ldo_f32 = out_f32.data_ptr(), out_f32.stride(0)
+    if out_bf16 is not None:
+        _req2d(out_bf16, _BF16, "gemm out_bf16")
+        args.out_bf16, args.ldo_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
+    if out_lo is not None:
+        _req2d(out_lo, _BF16, "gemm out_lo")
+        if out_bf16 is None or out_lo.stride(0) != out_bf16.stride(0):
+            raise capi.McanError("gemm: out_lo needs out_bf16 with the same leading dimension")
+        args.out_bf16_lo = out_lo.data_ptr()
+    args.accumulate = 1 if accumulate else 0
+    args.split_k = int(split_k)
+    args.block_n = int(block_n)
+    args.stream = _stream()
+    capi.check(lib.mcan_gemm(ctypes.byref(args)), "mcan_gemm")
+
+
+def _attn_args(q, k, v, key_mask, batch, heads, sq, sk, head_dim, scale, dropout_p, seed):
+    for t, nm in ((q, "q"), (k, "k"), (v, "v")):
+        _req2d(t, _BF16, "attn " + nm)
+    args = capi.AttnArgs()
+    args.q, args.k, args.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    args.ldq, args.ldk, args.ldv = q.stride(0), k.stride(0), v.stride(0)
+    if key_mask is not None:
+        _req(key_mask, torch.uint8, "attn key_mask")
+        if key_mask.numel() != batch * sk or not key_mask.is_contiguous():
+            raise capi.McanError("attn key_mask must be contiguous uint8 [batch, sk]")
+        args.key_mask = key_mask.data_ptr()
+    args.batch, args.heads, args.sq, args.sk, args.head_dim = batch, heads, sq, sk, head_dim
+    args.scale = float(scale)
+    args.dropout_p = float(dropout_p)
+    args.dropout_seed = int(seed) & 0xFFFFFFFF
+    args.stream = _stream()
+    return args
+
+
+def attn_fwd(q, k, v, key_mask, out, *, batch, heads, sq, sk, head_dim, scale, dropout_p=0.0, seed=0):
+    """out[b*sq+s, h*d:(h+1)*d] = softmax(mask(Q K^T scale)) V per (batch, head).  q/k/v/out are
+    bf16 [rows, >=heads*d] views (column offset already applied by slicing)."""
+    lib = capi.load()
+    args = _attn_args(q, k, v, key_mask, batch, heads, sq, sk, head_dim, scale, dropout_p, seed)
+    _req2d(out, _BF16, "attn out")
+    args.out, args.ldo = out.data_ptr(), out.stride(0)
+    capi.check(lib.mcan_attn_fwd(ctypes.byref(args)), "mcan_attn_fwd")
+
+
+def attn_bwd(q, k, v, key_mask, dout, dq, dk, dv, *, batch, heads, sq, sk, head_dim, scale,
+             dropout_p=0.0, seed=0):
+    lib = capi.load()
+    args = capi.AttnBwdArgs()
+    args.fwd = _attn_args(q, k, v, key_mask, batch, heads, sq, sk, head_dim, scale, dropout_p, seed)
+    for t, nm in ((dout, "dout"), (dq, "dq"), (dk, "dk"), (dv, "dv")):
+        _req2d(t, _BF16, "attn " + nm)
+    args.dout, args.lddo = dout.data_ptr(), dout.stride(0)
+    args.dq, args.dk, args.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    args.lddq, args.lddk, args.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
+    capi.check(lib.mcan_attn_bwd(ctypes.byref(args)), "mcan_attn_bwd")
+
+
+def layernorm_fwd(x, a2, b2, eps, *, y_f32=None, y_bf16=None, y_lo=None, mean=None, sigma=None):
+    """MCAN LayerNorm over the last dim of fp32 x [rows, h] (contiguous)."""
+    lib = capi.load()
+    _req(x, _F32, "layernorm x")
+    if not x.is_contiguous():
+        raise capi.McanError("layernorm x must be contiguous")
+    h = x.shape[-1]
+    rows = x.numel() // h
+    capi.check(lib.mcan_layernorm_fwd(x.data_ptr(), rows, h, a2.data_ptr(), b2.data_ptr(), float(eps),
+                                      _ptr(y_f32), _ptr(y_bf16), _ptr(y_lo), _ptr(mean), _ptr(sigma),
+                                      _stream()), "mcan_layernorm_fwd")
+
+
+def layernorm_bwd(dy, x, mean, sigma, a2, eps, *, dx_f32=None, dx_bf16=None, dropout_p=0.0, seed=0,
+                  da2=None, db2=None, dbias=None):
+    lib = capi.load()
+    _req(dy, _F32, "layernorm dy")
+    _req(x, _F32, "layernorm x")
+    if not (dy.is_contiguous() and x.is_contiguous()):
+        raise capi.McanError("layernorm_bwd tensors must be contiguous")
+    h = x.shape[-1]
+    rows = x.numel() // h
+    capi.check(lib.mcan_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), sigma.data_ptr(),
+                                      a2.data_ptr(), float(eps), rows, h, _ptr(dx_f32), _ptr(dx_bf16),
+                                      float(dropout_p), int(seed) & 0xFFFFFFFF, _ptr(da2), _ptr(db2),
+                                      _ptr(dbias), _stream()), "mcan_layernorm_bwd")
+
+
+def attflat_pool_fwd(hmid, w2, b2, mask, x, *, batch, s, h, mlp, glimpses, att_w, pooled_f32=None,
+                     pooled_bf16=None):
+    lib = capi.load()
+    _req(hmid, _BF16, "attflat hmid")
+    _req(x, _F32, "attflat x")
+    _req(w2, _F32, "attflat w2")
+    if mask is not None:
+        _req(mask, torch.uint8, "attflat mask")
+    capi.check(lib.mcan_attflat_pool_fwd(hmid.data_ptr(), w2.data_ptr(), b2.data_ptr(), _ptr(mask),
+                                         x.data_ptr(), batch, s, h, mlp, glimpses, att_w.data_ptr(),
+                                         _ptr(pooled_f32), _ptr(pooled_bf16), _stream()),
+               "mcan_attflat_pool_fwd")
+
+
+def attflat_pool_bwd(dpooled, hmid, w2, mask, x, att_w, *, batch, s, h, mlp, glimpses, gate_scale, dx,
+                     dhmid, dw2=None, db2=None):
+    lib = capi.load()
+    _req(dpooled, _F32, "attflat dpooled")
+    capi.check(lib.mcan_attflat_pool_bwd(dpooled.data_ptr(), hmid.data_ptr(), w2.data_ptr(), _ptr(mask),
+                                         x.data_ptr(), att_w.data_ptr(), batch, s, h, mlp, glimpses,
+                                         float(gate_scale), dx.data_ptr(), dhmid.data_ptr(), _ptr(dw2),
+                                         _ptr(db2), _stream()), "mcan_attflat_pool_bwd")
+
+
+def cast_bf16(x, hi, lo=None):
+    lib = capi.load()
+    _req(x, _F32, "cast x")
+    _req(hi, _BF16, "cast hi")
+    if not (x.is_contiguous() and hi.is_contiguous() and (lo is None or lo.is_contiguous())):
+        raise capi.McanError("cast tensors must be contiguous")
+    capi.check(lib.mcan_cast_bf16(x.data_ptr(), x.numel(), hi.data_ptr(), _ptr(lo), _stream()),
+               "mcan_cast_bf16")
+
+
+def colsum(x, out):
+    """out[c] += sum_r x[r, c]  (x bf16 or fp32 2-D, out fp32)."""
+    lib = capi.load()
+    _req(out, _F32, "colsum out")
+    if x.dtype == _BF16:
+        _req2d(x, _BF16, "colsum x")
+        capi.check(lib.mcan_colsum_bf16(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), out.data_ptr(),
+                                        _stream()), "mcan_colsum_bf16")
+    else:
+        _req2d(x, _F32, "colsum x")
+        capi.check(lib.mcan_colsum_f32(x.data_ptr(), x.shape[0], x.shape[1], x.stride(0), out.data_ptr(),
+                                       _stream()), "mcan_colsum_f32")
+
+
+# ---- host mirror of the device dropout hash (csrc/common.cuh), for tests --------------------
+def dropout_keep_mask(numel, p, seed, device="cpu"):
+    """Boolean keep-mask of the first `numel` linear element indices, identical to the kernels'."""
+    import numpy as np
+    idx = np.arange(numel, dtype=np.uint64)
+    pair = (idx >> np.uint64(1)).astype(np.uint32)
+    with np.errstate(over="ignore"):
+        x = (pair * np.uint32(0x9E3779B9) + np.uint32(seed & 0xFFFFFFFF)).astype(np.uint32)
+        x ^= x >> np.uint32(16)
+        x = (x * np.uint32(0x7FEB352D)).astype(np.uint32)
+        x ^= x >> np.uint32(15)
+        x = (x * np.uint32(0x846CA68B)).astype(np.uint32)
+        x ^= x >> np.uint32(16)
+    u16 = np.where((idx & np.uint64(1)) == 1, x >> np.uint32(16), x & np.uint32(0xFFFF))
+    thr = min(max(int(p * 65536.0 + 0.5), 0), 65535)
+    return torch.from_numpy((u16 >= thr)).to(device)

@@ -1,0 +1,155 @@
+"""tcgen05 GEMM (mcan_gemm through the C ABI) vs torch fp32 matmul on the same bf16 inputs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from mcan_vqa_b200 import ops
+    return ops
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).cuda()
+
+
+def _close(got, ref, tol, what):
+    err = (got.float() - ref).abs().max().item()
+    den = ref.abs().max().item() + 1e-20
+    assert err / den < tol, "%s: max abs err %.4g / max ref %.4g = %.3g" % (what, err, den, err / den)
+
+
+SHAPES_NT = [
+    (128, 128, 64), (128, 256, 128), (256, 128, 192), (896, 512, 512), (6400, 1024, 1024),
+    (100, 512, 512),     # ragged M (TMA zero fill + row guards)
+    (42, 136, 64),       # ragged M and N (scalar tail path)
+    (64, 2048, 1024),    # AttFlat linear_merge shape
+    (300, 1536, 2048),
+]
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES_NT)
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_nt_plain(m, n, k, block_n):
+    ops = _ops()
+    a, w = _rand((m, k), 1), _rand((n, k), 2, 0.05)
+    out = torch.full((m, n), float("nan"), device="cuda")
+    ops.gemm(a, w, out_f32=out, block_n=block_n)
+    torch.cuda.synchronize()
+    _close(out, a.float() @ w.float().t(), 2e-5, "NT plain")
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 512, 512), (6400, 512, 2048), (100, 1024, 512)])
+def test_gemm_dgrad_layout(m, n, k):
+    """dX[M,K'] = dY[M,N'] W[N',K']: B is read MN-major straight from the (out,in) weight."""
+    ops = _ops()
+    dy, w = _rand((m, k), 3), _rand((k, n), 4, 0.05)   # contraction k = N', output n = K'
+    out = torch.full((m, n), float("nan"), device="cuda")
+    ops.gemm(dy, w, b_layout=1, out_f32=out)
+    torch.cuda.synchronize()
+    _close(out, dy.float() @ w.float(), 2e-5, "dgrad layout")
+
+
+@pytest.mark.parametrize("rows,n,k", [(256, 512, 512), (6400, 1024, 512), (896, 512, 2048), (100, 256, 128), (1400, 512, 512)])
+@pytest.mark.parametrize("split_k", [0, 1, 3])
+def test_gemm_wgrad_layout_splitk(rows, n, k, split_k):
+    """dW[N',K'] = dY^T X: both operands MN-major, split-K with fp32 atomics into a zeroed buffer."""
+    ops = _ops()
+    dy, x = _rand((rows, n), 5, 0.1), _rand((rows, k), 6)
+    out = torch.zeros((n, k), device="cuda")
+    ops.gemm(dy, x, a_layout=1, b_layout=1, out_f32=out, accumulate=True, split_k=split_k)
+    torch.cuda.synchronize()
+    _close(out, dy.float().t() @ x.float(), 5e-5, "wgrad")
+
+
+def test_gemm_a_mn_b_k():
+    ops = _ops()
+    at, w = _rand((320, 256), 7), _rand((384, 320), 8, 0.05)   # A stored [K,M], B stored [N,K]
+    out = torch.empty((256, 384), device="cuda")
+    ops.gemm(at, w, a_layout=1, b_layout=0, out_f32=out)
+    torch.cuda.synchronize()
+    _close(out, at.float().t() @ w.float().t(), 2e-5, "A MN-major, B K-major")
+
+
+def test_gemm_epilogue_bias_relu_resid_outputs():
+    ops = _ops()
+    m, n, k = 384, 512, 256
+    a, w = _rand((m, k), 9), _rand((n, k), 10, 0.1)
+    bias = torch.randn(n, device="cuda")
+    resid = torch.randn(m, n, device="cuda")
+    o32 = torch.empty(m, n, device="cuda")
+    obf = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    olo = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, bias=bias, relu=True, resid=resid, out_f32=o32, out_bf16=obf, out_lo=olo)
+    torch.cuda.synchronize()
+    ref = torch.relu(a.float() @ w.float().t() + bias) + resid
+    _close(o32, ref, 2e-5, "bias+relu+resid fp32")
+    assert torch.equal(obf, o32.to(torch.bfloat16))
+    assert torch.equal(olo, (o32 - obf.float()).to(torch.bfloat16))
+    _close(obf.float() + olo.float(), ref, 1e-4, "hi+lo")
+
+
+def test_gemm_epilogue_gate():
+    ops = _ops()
+    m, n, k = 256, 384, 128
+    a, w = _rand((m, k), 11), _rand((k, n), 12, 0.1)
+    gate = _rand((m, n), 13)
+    out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, b_layout=1, gate=gate, gate_scale=1.25, out_bf16=out)
+    torch.cuda.synchronize()
+    ref = torch.where(gate.float() > 0, (a.float() @ w.float()) * 1.25, torch.zeros((), device="cuda"))
+    _close(out, ref, 6e-3, "gate")
+    assert (out.float()[gate.float() <= 0] == 0).all()
+
+
+def test_gemm_epilogue_dropout_matches_host_hash():
+    ops = _ops()
+    m, n, k = 256, 512, 64
+    a, w = _rand((m, k), 14), _rand((n, k), 15, 0.1)
+    p, seed = 0.1, 12345
+    out = torch.empty(m, n, device="cuda")
+    ops.gemm(a, w, dropout_p=p, seed=seed, out_f32=out)
+    torch.cuda.synchronize()
+    keep = ops.dropout_keep_mask(m * n, p, seed).view(m, n).cuda()
+    ref = torch.where(keep, (a.float() @ w.float().t()) / (1 - p), torch.zeros((), device="cuda"))
+    _close(out, ref, 2e-5, "dropout")
+    frac = 1.0 - keep.float().mean().item()
+    assert abs(frac - p) < 0.01, frac
+
+
+def test_gemm_split_precision_segments():
+    """bf16x3: (A_hi,B_hi)+(A_hi,B_lo)+(A_lo,B_hi) reproduces the fp32 product to ~1e-5."""
+    ops = _ops()
+    m, n, k = 256, 256, 512
+    g = torch.Generator().manual_seed(16)
+    a32 = torch.randn(m, k, generator=g).cuda()
+    w32 = (torch.randn(n, k, generator=g) * 0.05).cuda()
+    ah, al = torch.empty_like(a32, dtype=torch.bfloat16), torch.empty_like(a32, dtype=torch.bfloat16)
+    wh, wl = torch.empty_like(w32, dtype=torch.bfloat16), torch.empty_like(w32, dtype=torch.bfloat16)
+    ops.cast_bf16(a32, ah, al)
+    ops.cast_bf16(w32, wh, wl)
+    out = torch.empty(m, n, device="cuda")
+    ops.gemm([ah, ah, al], [wh, wl, wh], out_f32=out)
+    torch.cuda.synchronize()
+    ref = (a32.double() @ w32.double().t()).float()
+    _close(out, ref, 3e-5, "bf16x3")
+    out1 = torch.empty(m, n, device="cuda")
+    ops.gemm(ah, wh, out_f32=out1)
+    torch.cuda.synchronize()
+    assert (out1 - ref).abs().max() > 20 * (out - ref).abs().max()
+
+
+def test_gemm_strided_views_qkv():
+    """Operands / outputs as column slices of wider buffers (fused QKV, cross-layer K/V)."""
+    ops = _ops()
+    m, h = 896, 512
+    x = _rand((m, h), 17)
+    wqkv = _rand((3 * h, h), 18, 0.05)
+    out = torch.zeros(m, 3 * h, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(x, wqkv[h:2 * h], out_bf16=out[:, h:2 * h])
+    torch.cuda.synchronize()
+    ref = x.float() @ wqkv[h:2 * h].float().t()
+    _close(out[:, h:2 * h], ref, 6e-3, "strided out")
+    assert (out[:, :h] == 0).all() and (out[:, 2 * h:] == 0).all()

@@ -1,0 +1,246 @@
+"""LayerNorm / attention / AttFlat-pool / helper kernels through the C ABI vs torch fp32 math."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from mcan_vqa_b200 import ops
+    return ops
+
+
+def _ln_ref(x, a, b, eps=1e-6):
+    mean = x.mean(-1, keepdim=True)
+    std = x.std(-1, keepdim=True)
+    return a * (x - mean) / (std + eps) + b
+
+
+@pytest.mark.parametrize("rows,h", [(896, 512), (6400, 1024), (64, 2048), (37, 512), (5, 64)])
+def test_layernorm_fwd_bwd(rows, h):
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows + h)
+    x = (torch.randn(rows, h, generator=g) * 2 + 0.5).cuda().requires_grad_(True)
+    a = (torch.rand(h, generator=g) + 0.5).cuda().requires_grad_(True)
+    b = torch.randn(h, generator=g).cuda().requires_grad_(True)
+    dy = torch.randn(rows, h, generator=g).cuda()
+    y32 = torch.empty(rows, h, device="cuda")
+    ybf = torch.empty(rows, h, device="cuda", dtype=torch.bfloat16)
+    ylo = torch.empty(rows, h, device="cuda", dtype=torch.bfloat16)
+    mean = torch.empty(rows, device="cuda")
+    sigma = torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(x.detach(), a.detach(), b.detach(), 1e-6, y_f32=y32, y_bf16=ybf, y_lo=ylo, mean=mean, sigma=sigma)
+    ref = _ln_ref(x.double(), a.double(), b.double())
+    ref.backward(dy.double())
+    torch.cuda.synchronize()
+    assert (y32 - ref.float()).abs().max() < 2e-5
+    assert torch.equal(ybf, y32.to(torch.bfloat16))
+    assert torch.equal(ylo, (y32 - ybf.float()).to(torch.bfloat16))
+    assert (sigma - x.detach().std(-1)).abs().max() < 1e-5
+
+    dx = torch.empty(rows, h, device="cuda")
+    dxbf = torch.empty(rows, h, device="cuda", dtype=torch.bfloat16)
+    da, db, dbias = (torch.zeros(h, device="cuda") for _ in range(3))
+    ops.layernorm_bwd(dy, x.detach(), mean, sigma, a.detach(), 1e-6, dx_f32=dx, dx_bf16=dxbf, da2=da, db2=db, dbias=dbias)
+    torch.cuda.synchronize()
+    scale = x.grad.abs().max().item()
+    assert (dx - x.grad.float()).abs().max().item() < 2e-5 * max(scale, 1.0)
+    assert torch.equal(dxbf, dx.to(torch.bfloat16))
+    assert (da - a.grad.float()).abs().max() < 1e-3 * max(1.0, a.grad.abs().max().item())
+    assert (db - b.grad.float()).abs().max() < 1e-3 * max(1.0, b.grad.abs().max().item())
+    assert (dbias - dx.sum(0)).abs().max() < 1e-3 * max(1.0, dx.sum(0).abs().max().item())
+
+
+def test_layernorm_bwd_dropout_gate_matches_gemm_epilogue_indexing():
+    ops = _ops()
+    rows, h, p, seed = 128, 512, 0.1, 777
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(rows, h, generator=g).cuda()
+    dy = torch.randn(rows, h, generator=g).cuda()
+    a = torch.ones(h, device="cuda"); b = torch.zeros(h, device="cuda")
+    mean = torch.empty(rows, device="cuda"); sigma = torch.empty(rows, device="cuda")
+    ops.layernorm_fwd(x, a, b, 1e-6, y_f32=torch.empty_like(x), mean=mean, sigma=sigma)
+    dx = torch.empty_like(x); dxbf = torch.empty(rows, h, device="cuda", dtype=torch.bfloat16)
+    dbias = torch.zeros(h, device="cuda")
+    ops.layernorm_bwd(dy, x, mean, sigma, a, 1e-6, dx_f32=dx, dx_bf16=dxbf, dropout_p=p, seed=seed, dbias=dbias)
+    torch.cuda.synchronize()
+    keep = ops.dropout_keep_mask(rows * h, p, seed).view(rows, h).cuda()
+    ref = torch.where(keep, dx / (1 - p), torch.zeros((), device="cuda"))
+    assert torch.equal(dxbf, ref.to(torch.bfloat16))
+    assert (dbias - ref.sum(0)).abs().max() < 1e-3
+
+
+def test_layernorm_constant_row_gives_b2():
+    ops = _ops()
+    x = torch.full((8, 512), 3.0, device="cuda")
+    a = torch.rand(512, device="cuda"); b = torch.randn(512, device="cuda")
+    y = torch.empty_like(x)
+    ops.layernorm_fwd(x, a, b, 1e-6, y_f32=y)
+    torch.cuda.synchronize()
+    assert torch.equal(y, b.expand_as(y))
+
+
+def _attn_ref(q, k, v, mask, scale, keep=None, p=0.0):
+    # q [B,h,Sq,d] etc., mask bool [B,Sk]
+    s = torch.matmul(q, k.transpose(-2, -1)) * scale
+    if mask is not None:
+        s = s.masked_fill(mask[:, None, None, :], -1e9)
+    pr = torch.softmax(s, dim=-1)
+    if keep is not None:
+        pr = pr * keep / (1 - p)
+    return torch.matmul(pr, v)
+
+
+ATTN_CASES = [
+    # batch, heads, sq, sk, d, mask kind
+    (4, 8, 14, 14, 64, "prefix"),
+    (3, 8, 100, 100, 64, "random"),
+    (3, 8, 100, 14, 64, "prefix"),
+    (2, 8, 100, 100, 128, "random"),
+    (2, 16, 60, 60, 64, "none"),
+    (2, 4, 1, 1, 64, "none"),
+    (2, 4, 128, 128, 64, "allmasked"),
+    (2, 2, 33, 77, 128, "random"),
+]
+
+
+def _make_attn(batch, heads, sq, sk, d, kind, seed=0):
+    g = torch.Generator().manual_seed(seed + sq * 131 + sk)
+    H = heads * d
+    qkv = torch.randn(batch * max(sq, sk), 3 * H, generator=g).to(torch.bfloat16).cuda()
+    q = qkv[: batch * sq, :H]
+    k = qkv[: batch * sk, H:2 * H]
+    v = qkv[: batch * sk, 2 * H:]
+    if kind == "none":
+        mask = None
+    elif kind == "prefix":
+        lens = torch.randint(1, sk + 1, (batch,), generator=g)
+        mask = (torch.arange(sk)[None, :] >= lens[:, None])
+    elif kind == "random":
+        mask = torch.rand(batch, sk, generator=g) < 0.3
+    else:
+        mask = torch.rand(batch, sk, generator=g) < 0.3
+        mask[0, :] = True     # fully masked sample -> uniform softmax
+    return q, k, v, (None if mask is None else mask.cuda())
+
+
+def _heads(t, batch, s, heads, d):
+    return t.float().reshape(batch, s, heads, d).transpose(1, 2)
+
+
+@pytest.mark.parametrize("batch,heads,sq,sk,d,kind", ATTN_CASES)
+def test_attention_fwd_bwd(batch, heads, sq, sk, d, kind):
+    ops = _ops()
+    q, k, v, mask = _make_attn(batch, heads, sq, sk, d, kind)
+    H = heads * d
+    scale = 1.0 / math.sqrt(d)
+    mask_u8 = None if mask is None else mask.to(torch.uint8).contiguous()
+    out = torch.full((batch * sq, H), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.attn_fwd(q, k, v, mask_u8, out, batch=batch, heads=heads, sq=sq, sk=sk, head_dim=d, scale=scale)
+    qh = _heads(q, batch, sq, heads, d).requires_grad_(True)
+    kh = _heads(k, batch, sk, heads, d).requires_grad_(True)
+    vh = _heads(v, batch, sk, heads, d).requires_grad_(True)
+    ref = _attn_ref(qh, kh, vh, mask, scale)
+    torch.cuda.synchronize()
+    got = _heads(out, batch, sq, heads, d)
+    assert (got - ref).abs().max().item() < 2e-2 * max(1.0, ref.abs().max().item()), (got - ref).abs().max().item()
+
+    dout = (torch.randn(batch * sq, H, device="cuda") * 0.5).to(torch.bfloat16)
+    dqkv = torch.zeros(batch * max(sq, sk), 3 * H, device="cuda", dtype=torch.bfloat16)
+    dq, dk, dv = dqkv[: batch * sq, :H], dqkv[: batch * sk, H:2 * H], dqkv[: batch * sk, 2 * H:]
+    ops.attn_bwd(q, k, v, mask_u8, dout, dq, dk, dv, batch=batch, heads=heads, sq=sq, sk=sk, head_dim=d, scale=scale)
+    ref.backward(_heads(dout, batch, sq, heads, d))
+    torch.cuda.synchronize()
+    for name, gt, rf, s in (("dq", dq, qh.grad, sq), ("dk", dk, kh.grad, sk), ("dv", dv, vh.grad, sk)):
+        gt = _heads(gt, batch, s, heads, d)
+        err = (gt - rf).abs().max().item()
+        assert err < 3e-2 * max(1.0, rf.abs().max().item()), (name, err, rf.abs().max().item())
+
+
+def test_attention_dropout_matches_host_hash():
+    ops = _ops()
+    batch, heads, sq, sk, d, p, seed = 2, 8, 100, 100, 64, 0.1, 4242
+    q, k, v, mask = _make_attn(batch, heads, sq, sk, d, "random")
+    H = heads * d
+    scale = 1.0 / math.sqrt(d)
+    mask_u8 = mask.to(torch.uint8).contiguous()
+    out = torch.empty(batch * sq, H, device="cuda", dtype=torch.bfloat16)
+    ops.attn_fwd(q, k, v, mask_u8, out, batch=batch, heads=heads, sq=sq, sk=sk, head_dim=d, scale=scale, dropout_p=p, seed=seed)
+    keep = ops.dropout_keep_mask(batch * heads * sq * sk, p, seed).view(batch, heads, sq, sk).cuda().float()
+    qh = _heads(q, batch, sq, heads, d).requires_grad_(True)
+    kh = _heads(k, batch, sk, heads, d).requires_grad_(True)
+    vh = _heads(v, batch, sk, heads, d).requires_grad_(True)
+    ref = _attn_ref(qh, kh, vh, mask, scale, keep, p)
+    torch.cuda.synchronize()
+    assert (_heads(out, batch, sq, heads, d) - ref).abs().max().item() < 3e-2
+    dout = (torch.randn(batch * sq, H, device="cuda") * 0.5).to(torch.bfloat16)
+    dq, dk, dv = (torch.zeros(batch * s, H, device="cuda", dtype=torch.bfloat16) for s in (sq, sk, sk))
+    ops.attn_bwd(q, k, v, mask_u8, dout, dq, dk, dv, batch=batch, heads=heads, sq=sq, sk=sk, head_dim=d, scale=scale, dropout_p=p, seed=seed)
+    ref.backward(_heads(dout, batch, sq, heads, d))
+    torch.cuda.synchronize()
+    for gt, rf, s in ((dq, qh.grad, sq), (dk, kh.grad, sk), (dv, vh.grad, sk)):
+        err = (_heads(gt, batch, s, heads, d) - rf).abs().max().item()
+        assert err < 3e-2 * max(1.0, rf.abs().max().item())
+
+
+@pytest.mark.parametrize("batch,s,h,mlp,glimpses", [(8, 100, 512, 512, 1), (4, 14, 1024, 512, 1), (3, 60, 512, 512, 2), (2, 100, 512, 256, 3)])
+def test_attflat_pool_fwd_bwd(batch, s, h, mlp, glimpses):
+    ops = _ops()
+    g = torch.Generator().manual_seed(batch * 7 + s)
+    hmid = torch.relu(torch.randn(batch * s, mlp, generator=g)).to(torch.bfloat16).cuda()
+    w2 = (torch.randn(glimpses, mlp, generator=g) * 0.1).cuda().requires_grad_(True)
+    b2 = torch.randn(glimpses, generator=g).cuda().requires_grad_(True)
+    x = torch.randn(batch * s, h, generator=g).cuda().requires_grad_(True)
+    mask = torch.rand(batch, s, generator=g) < 0.3
+    mask[0, :] = True if batch > 2 else mask[0, :]
+    mask = mask.cuda()
+    att_w = torch.empty(batch, s, glimpses, device="cuda")
+    p32 = torch.empty(batch, glimpses * h, device="cuda")
+    pbf = torch.empty(batch, glimpses * h, device="cuda", dtype=torch.bfloat16)
+    mu8 = mask.to(torch.uint8).contiguous()
+    ops.attflat_pool_fwd(hmid, w2.detach(), b2.detach(), mu8, x.detach(), batch=batch, s=s, h=h, mlp=mlp,
+                         glimpses=glimpses, att_w=att_w, pooled_f32=p32, pooled_bf16=pbf)
+    hm = hmid.float().view(batch, s, mlp).requires_grad_(True)
+    logit = hm @ w2.t() + b2
+    logit = logit.masked_fill(mask[:, :, None], -1e9)
+    aw = torch.softmax(logit, dim=1)
+    pooled = torch.cat([(aw[:, :, i:i + 1] * x.view(batch, s, h)).sum(1) for i in range(glimpses)], dim=1)
+    torch.cuda.synchronize()
+    assert (att_w - aw).abs().max() < 1e-5
+    assert (p32 - pooled).abs().max() < 1e-4
+    assert torch.equal(pbf, p32.to(torch.bfloat16))
+
+    dpooled = torch.randn(batch, glimpses * h, generator=g).cuda()
+    pooled.backward(dpooled)
+    dx = torch.empty(batch * s, h, device="cuda")
+    dh = torch.empty(batch * s, mlp, device="cuda", dtype=torch.bfloat16)
+    dw2 = torch.zeros(glimpses, mlp, device="cuda"); db2 = torch.zeros(glimpses, device="cuda")
+    ops.attflat_pool_bwd(dpooled, hmid, w2.detach(), mu8, x.detach(), att_w, batch=batch, s=s, h=h, mlp=mlp,
+                         glimpses=glimpses, gate_scale=1.0, dx=dx, dhmid=dh, dw2=dw2, db2=db2)
+    torch.cuda.synchronize()
+    assert (dx - x.grad).abs().max() < 1e-4 * max(1.0, x.grad.abs().max().item())
+    ref_dh = torch.where(hmid.float().view(batch, s, mlp) > 0, hm.grad, torch.zeros((), device="cuda")).view(batch * s, mlp)
+    assert (dh.float() - ref_dh).abs().max() < 1e-2 * max(1e-3, ref_dh.abs().max().item())
+    assert (dw2 - w2.grad).abs().max() < 1e-3 * max(1.0, w2.grad.abs().max().item())
+    assert (db2 - b2.grad).abs().max() < 1e-3 * max(1.0, b2.grad.abs().max().item())
+
+
+def test_cast_and_colsum():
+    ops = _ops()
+    x = torch.randn(1000, 1027, device="cuda").contiguous()
+    hi = torch.empty_like(x, dtype=torch.bfloat16); lo = torch.empty_like(x, dtype=torch.bfloat16)
+    ops.cast_bf16(x, hi, lo)
+    torch.cuda.synchronize()
+    assert torch.equal(hi, x.to(torch.bfloat16))
+    assert torch.equal(lo, (x - hi.float()).to(torch.bfloat16))
+    y = torch.randn(6400, 1536, device="cuda")
+    out = torch.zeros(1536, device="cuda")
+    ops.colsum(y, out)
+    ybf = y.to(torch.bfloat16)
+    out2 = torch.zeros(512, device="cuda")
+    ops.colsum(ybf[:, 512:1024], out2)
+    torch.cuda.synchronize()
+    assert (out - y.sum(0)).abs().max() < 1e-2
+    assert (out2 - ybf[:, 512:1024].float().sum(0)).abs().max() < 1e-2
