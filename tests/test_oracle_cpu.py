@@ -127,8 +127,8 @@ def test_reference_semantics_edge_cases():
     out = orc.attention(v, k, q, torch.ones(1, 1, 1, 5, dtype=torch.bool))
     assert torch.allclose(out, v.mean(2, keepdim=True).expand_as(out))
     # warm-up schedule (optim.py:36-49)
-    assert [orc.warmup_rate(s, 1e-4, 100, 10) for s in (1, 10, 11, 20, 21, 30, 31)] == \
-        [2.5e-5, 2.5e-5, 5e-5, 5e-5, 7.5e-5, 7.5e-5, 1e-4]
+    got = [orc.warmup_rate(s, 1e-4, 100, 10) for s in (1, 10, 11, 20, 21, 30, 31)]
+    assert np.allclose(got, [2.5e-5, 2.5e-5, 5e-5, 5e-5, 7.5e-5, 7.5e-5, 1e-4], rtol=1e-12, atol=0)
 
 
 def test_synth_is_deterministic_and_matches_state_dict_contract():
