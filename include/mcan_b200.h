@@ -21,7 +21,9 @@
  *   - "bf16" pointers are `void*` to __nv_bfloat16 data; activations are row-major
  *     [rows, features] with rows = batch * sequence.
  *   - dropout masks are never stored: forward and backward regenerate them from
- *     (seed, element index) with the hash in csrc/common.cuh.
+ *     (seed, element index) with the hash in csrc/common.cuh.  The effective seed is
+ *     dropout_seed ^ *dropout_seed_dev when the device pointer is given, so a captured CUDA
+ *     graph draws a fresh mask on every replay by updating one device word.
  */
 #ifndef MCAN_B200_H_
 #define MCAN_B200_H_
@@ -79,6 +81,7 @@ typedef struct mcan_gemm_args {
     int32_t relu;
     float dropout_p;
     uint32_t dropout_seed;
+    const uint32_t* dropout_seed_dev; /* optional device word XOR-ed into dropout_seed (CUDA graphs) */
     const void* gate;
     int64_t ldg;
     float gate_scale;
@@ -120,6 +123,7 @@ typedef struct mcan_attn_args {
     float scale;
     float dropout_p;
     uint32_t dropout_seed;
+    const uint32_t* dropout_seed_dev; /* optional device word XOR-ed into dropout_seed */
     void* stream;
 } mcan_attn_args;
 
@@ -156,8 +160,9 @@ int mcan_layernorm_fwd(const float* x, int64_t rows, int64_t h, const float* a2,
  */
 int mcan_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* sigma,
                        const float* a2, float eps, int64_t rows, int64_t h, float* dx_f32,
-                       void* dx_bf16, float dropout_p, uint32_t dropout_seed, float* da2,
-                       float* db2, float* dbias, void* stream);
+                       void* dx_bf16, float dropout_p, uint32_t dropout_seed,
+                       const uint32_t* dropout_seed_dev, float* da2, float* db2, float* dbias,
+                       void* stream);
 
 /* -- F1: AttFlat pooling (net.py:38-55) ----------------------------------------------
  * Input hmid = dropout(relu(x W1^T + b1)) comes from mcan_gemm (bf16 [batch*s, mlp]).
@@ -184,6 +189,9 @@ int mcan_attflat_pool_bwd(const float* dpooled, const void* hmid, const float* w
 /* -- small memory-bound helpers -------------------------------------------------------- */
 /* hi = bf16(x); lo (optional) = bf16(x - hi).  n elements. */
 int mcan_cast_bf16(const float* x, int64_t n, void* hi, void* lo, void* stream);
+/* out = bf16(act > 0 ? dy * scale : 0): gradient through FC's ReLU + dropout (net_utils.py:28-32)
+ * from the saved bf16 activation; n contiguous elements. */
+int mcan_gate_bf16(const float* dy, const void* act, float scale, void* out, int64_t n, void* stream);
 /* out[c] += sum_r x[r,c]   (x bf16 [rows, cols] with leading dimension ld; fp32 atomics) */
 int mcan_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64_t ld, float* out,
                      void* stream);

@@ -1,0 +1,641 @@
+"""Forward / backward of the MCAN blocks as chains of libmcan_b200 kernels.
+
+This is the host side of the hot path: it owns no arithmetic, only the order of kernel
+launches, the activation buffers (torch tensors used as plain device memory) and the
+bookkeeping autograd needs.  Reference semantics (all in /root/reference):
+
+    MHAtt  core/model/mca.py:30-78      FFN   core/model/mca.py:85-98 (+ net_utils.py:11-45)
+    SA     core/model/mca.py:118-127    SGA   core/model/mca.py:150-164
+    MCA_ED core/model/mca.py:178-186    AttFlat core/model/net.py:38-55
+    LayerNorm core/model/net_utils.py:56-60
+
+Data layout in HBM.  Every activation is a row-major [rows, features] matrix, rows =
+batch*sequence.  The residual stream is kept twice: fp32 (residual adds, LayerNorm input) and
+bf16 (the A operand of the next tcgen05 GEMM), both written by the LayerNorm kernel.  Q/K/V
+live in one bf16 [rows, 3H] buffer written by one fused GEMM; heads are column slices, so the
+reference's view/transpose/contiguous copies (mca.py:33-59) do not exist.  For MCA_ED the K/V
+projections of the final encoder output for ALL decoder layers are one GEMM into a
+[rows_q, L*2H] buffer.  Weights: fp32 masters (the nn.Parameters the optimiser updates) and
+cached bf16 copies stacked per GEMM ([q|k|v] = [3H,H]); dgrad and wgrad read the same bf16
+buffers MN-major, no transposed copies.  Dropout masks are never materialised.
+
+Per sub-layer launch chain (forward):
+    self-attention: GEMM[qkv] -> attention -> GEMM[merge + bias + dropout + residual] -> LayerNorm
+    FFN:            GEMM[fc + bias + ReLU + dropout] -> GEMM[out + bias + dropout + residual] -> LayerNorm
+"""
+import math
+
+import torch
+
+from . import ops
+
+_BF16 = torch.bfloat16
+_F32 = torch.float32
+
+# When True the bf16 operand copies of the weights are re-cast on every training forward
+# (needed under CUDA-graph replay, where Python cannot observe optimizer updates).
+ALWAYS_RECAST = False
+
+
+def _mix32(x):
+    x &= 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x7FEB352D) & 0xFFFFFFFF
+    x ^= x >> 15
+    x = (x * 0x846CA68B) & 0xFFFFFFFF
+    x ^= x >> 16
+    return x
+
+
+_seed_counter = [0]
+
+
+class Runtime(object):
+    """Per-forward settings: dropout probability (0 in eval) and the dropout seed stream."""
+
+    def __init__(self, training, dropout_rate):
+        self.p = float(dropout_rate) if training else 0.0
+        _seed_counter[0] += 1
+        self.base = _mix32((torch.initial_seed() & 0xFFFFFFFF) ^ (_seed_counter[0] * 0x9E3779B9))
+        self.n = 0
+        self.bufs = []      # flat fp32 gradient buffers produced since the last drain (for dp.py)
+
+    def seed(self):
+        self.n += 1
+        return _mix32(self.base + self.n * 0x85EBCA6B)
+
+    @property
+    def keep_scale(self):
+        return 1.0 / (1.0 - self.p) if self.p > 0 else 1.0
+
+
+class Act(object):
+    """An activation in the formats the kernels consume: fp32 (residual stream) and bf16 (GEMM operand)."""
+    __slots__ = ("f32", "bf")
+
+    def __init__(self, f32=None, bf=None):
+        self.f32 = f32
+        self.bf = bf
+
+
+def act_from_f32(x2d):
+    bf = torch.empty(x2d.shape, dtype=_BF16, device=x2d.device)
+    ops.cast_bf16(x2d, bf)
+    return Act(x2d, bf)
+
+
+def _empty(rows, cols, dtype, device):
+    return torch.empty((rows, cols), dtype=dtype, device=device)
+
+
+def _bf_padded(rows, cols, device):
+    """bf16 [rows, cols] view whose leading dimension is a multiple of 8 (TMA stride alignment)."""
+    ld = (cols + 7) // 8 * 8
+    buf = torch.zeros((rows, ld), dtype=_BF16, device=device) if ld != cols else \
+        torch.empty((rows, ld), dtype=_BF16, device=device)
+    return buf[:, :cols]
+
+
+class LinearParams(object):
+    """bf16 GEMM-operand copy of one or more nn.Linear layers stacked along the output dim.
+
+    `pairs` = [(weight Parameter [n_i, k], bias Parameter [n_i]), ...].  The copy is refreshed
+    when a master's version counter or storage changes (optimizer step, load_state_dict, .cuda()).
+    """
+
+    def __init__(self, pairs):
+        self.pairs = list(pairs)
+        self.sizes = [w.shape[0] for w, _ in self.pairs]
+        self.n = sum(self.sizes)
+        self.k = self.pairs[0][0].shape[1]
+        self.w = None
+        self.b = None
+        self._stamp = None
+
+    def _current_stamp(self):
+        return tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in self.pairs)
+
+    def get(self, force=False):
+        stamp = self._current_stamp()
+        dev = self.pairs[0][0].device
+        if self.w is None or self.w.device != dev:
+            ld = (self.k + 7) // 8 * 8
+            self.w = torch.zeros((self.n, ld), dtype=_BF16, device=dev)[:, :self.k]
+            self.b = torch.empty((self.n,), dtype=_F32, device=dev)
+            self._stamp = None
+        if force or stamp != self._stamp:
+            r = 0
+            for (w, b), n in zip(self.pairs, self.sizes):
+                wd = w.detach()
+                if self.w.stride(0) == self.k:
+                    ops.cast_bf16(wd if wd.is_contiguous() else wd.contiguous(), self.w[r:r + n])
+                else:   # padded leading dimension (k % 8 != 0): plumbing copy, not on the hot path
+                    self.w[r:r + n].copy_(wd)
+                self.b[r:r + n].copy_(b.detach())
+                r += n
+            self._stamp = stamp
+        return self
+
+    def rows(self, i0, i1):
+        """(weight rows, bias) of stacked members i0..i1-1."""
+        r0 = sum(self.sizes[:i0])
+        r1 = sum(self.sizes[:i1])
+        return self.w[r0:r1], self.b[r0:r1]
+
+
+class GradBuf(object):
+    """Zero-initialised fp32 gradient storage for members [i0, i1) of a stacked LinearParams
+    (wgrad accumulates with atomics, so the buffer must start at zero)."""
+
+    def __init__(self, rt, lp, i0=0, i1=None):
+        i1 = len(lp.sizes) if i1 is None else i1
+        self.lp, self.i0, self.i1 = lp, i0, i1
+        self.sizes = lp.sizes[i0:i1]
+        n = sum(self.sizes)
+        self.flat = torch.zeros(n * lp.k + n, dtype=_F32, device=lp.w.device)
+        self.w = self.flat[: n * lp.k].view(n, lp.k)
+        self.b = self.flat[n * lp.k:]
+        rt.bufs.append(self.flat)
+
+    def _range(self, j0, j1):
+        r0 = sum(self.lp.sizes[self.i0:j0])
+        return r0, r0 + sum(self.lp.sizes[j0:j1])
+
+    def rows_w(self, j0, j1):
+        r0, r1 = self._range(j0, j1)
+        return self.w[r0:r1]
+
+    def rows_b(self, j0, j1):
+        r0, r1 = self._range(j0, j1)
+        return self.b[r0:r1]
+
+    def per_param(self):
+        """[(dW_i, db_i)] views for members i0..i1-1."""
+        out = []
+        r = 0
+        for n in self.sizes:
+            out.append((self.w[r:r + n], self.b[r:r + n]))
+            r += n
+        return out
+
+
+class Bag(object):
+    pass
+
+
+def _force(rt_training):
+    return ALWAYS_RECAST and rt_training
+
+
+# ------------------------------------------------------------------------------------------
+# LayerNorm
+# ------------------------------------------------------------------------------------------
+def ln_fwd(norm, s_f32, want_bf=True):
+    """s_f32 [rows, h] fp32 -> (Act(y_f32, y_bf), mean, sigma)."""
+    rows, h = s_f32.shape
+    dev = s_f32.device
+    y32 = _empty(rows, h, _F32, dev)
+    ybf = _empty(rows, h, _BF16, dev) if want_bf else None
+    mean = torch.empty(rows, dtype=_F32, device=dev)
+    sigma = torch.empty(rows, dtype=_F32, device=dev)
+    ops.layernorm_fwd(s_f32, norm.a_2.detach(), norm.b_2.detach(), norm.eps, y_f32=y32, y_bf16=ybf,
+                      mean=mean, sigma=sigma)
+    return Act(y32, ybf), mean, sigma
+
+
+def ln_bwd(rt, norm, dy, s_f32, mean, sigma, p=0.0, seed=0, want_bf=True, dbias=None):
+    """Returns (dx_f32, dx_bf gated by the dropout mask of the producing GEMM, da2, db2)."""
+    rows, h = s_f32.shape
+    dev = s_f32.device
+    dx = _empty(rows, h, _F32, dev)
+    dxbf = _empty(rows, h, _BF16, dev) if want_bf else None
+    dab = torch.zeros(2 * h, dtype=_F32, device=dev)
+    rt.bufs.append(dab)
+    ops.layernorm_bwd(dy, s_f32, mean, sigma, norm.a_2.detach(), norm.eps, dx_f32=dx, dx_bf16=dxbf,
+                      dropout_p=p, seed=seed, da2=dab[:h], db2=dab[h:], dbias=dbias)
+    return dx, dxbf, dab[:h], dab[h:]
+
+
+# ------------------------------------------------------------------------------------------
+# attention sub-layer:  LN(x + dropout(merge(att(...))))   (mca.py:119-121, 152-158)
+# With norm=None it is the bare MHAtt module (merge output, fp32, no residual).
+# ------------------------------------------------------------------------------------------
+def att_fwd(rt, mh, x, B, Sq, kv_src=None, Sk=None, key_mask=None, kv=None, norm=None, v_src=None):
+    """x: Act of the query-side input [B*Sq, H].
+    kv_src None and kv None -> self-attention (fused QKV GEMM).
+    kv_src Act             -> K,V projected from kv_src (fused KV GEMM); v_src Act additionally
+                              gives V its own input (fully general MHAtt(v,k,q)).
+    kv (k_view, v_view)    -> K,V already projected (MCA_ED cross-layer batch).
+    Returns (Act or fp32 tensor, ctx)."""
+    H = mh.hidden_size
+    heads, d = mh.multi_head, mh.head_dim
+    dev = x.bf.device
+    M = B * Sq
+    c = Bag()
+    c.B, c.Sq, c.mask = B, Sq, key_mask
+    lp = mh.lp_qkv().get(_force(rt.p > 0 or torch.is_grad_enabled()))
+    c.lp = lp
+    c.x_bf = x.bf
+    c.mode = "self" if (kv_src is None and kv is None) else ("kv" if kv is not None else "cross")
+    if c.mode == "self":
+        Sk = Sq
+        w, b = lp.rows(0, 3)
+        qkv = _empty(M, 3 * H, _BF16, dev)
+        ops.gemm(x.bf, w, bias=b, out_bf16=qkv)
+        q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+    else:
+        w, b = lp.rows(0, 1)
+        q = _empty(M, H, _BF16, dev)
+        ops.gemm(x.bf, w, bias=b, out_bf16=q)
+        if c.mode == "kv":
+            k, v = kv
+        else:
+            kvb = _empty(B * Sk, 2 * H, _BF16, dev)
+            k, v = kvb[:, :H], kvb[:, H:]
+            if v_src is None:
+                w, b = lp.rows(1, 3)
+                ops.gemm(kv_src.bf, w, bias=b, out_bf16=kvb)
+            else:
+                w, b = lp.rows(1, 2)
+                ops.gemm(kv_src.bf, w, bias=b, out_bf16=k)
+                w, b = lp.rows(2, 3)
+                ops.gemm(v_src.bf, w, bias=b, out_bf16=v)
+                c.v_bf = v_src.bf
+            c.kv_bf = kv_src.bf
+    c.Sk = Sk
+    c.q, c.k, c.v = q, k, v
+    att = _empty(M, H, _BF16, dev)
+    c.seed_att = rt.seed()
+    ops.attn_fwd(q, k, v, key_mask, att, batch=B, heads=heads, sq=Sq, sk=Sk, head_dim=d,
+                 scale=1.0 / math.sqrt(d), dropout_p=rt.p, seed=c.seed_att)
+    c.att = att
+    lpm = mh.lp_merge().get(_force(rt.p > 0 or torch.is_grad_enabled()))
+    c.lpm = lpm
+    s = _empty(M, H, _F32, dev)
+    if norm is None:
+        ops.gemm(att, lpm.w, bias=lpm.b, out_f32=s)
+        return s, c
+    c.seed_out = rt.seed()
+    ops.gemm(att, lpm.w, bias=lpm.b, dropout_p=rt.p, seed=c.seed_out, resid=x.f32, out_f32=s)
+    out, c.mean, c.sigma = ln_fwd(norm, s)
+    c.s = s
+    return out, c
+
+
+def att_bwd(rt, mh, c, dout, norm=None, dkv=None, need_dx=True):
+    """dout: fp32 grad of the sub-layer output (or of the bare merge output when norm is None).
+    Returns (dx_f32, dkv_src_f32 or None, dv_src_f32 or None, grads) where grads maps
+    parameter -> gradient tensor.  With dkv=(dk_view, dv_view) the K/V gradients are written
+    there (MCA_ED cross-layer batch) instead of being back-projected here."""
+    H = mh.hidden_size
+    heads, d = mh.multi_head, mh.head_dim
+    dev = dout.device
+    B, Sq, Sk = c.B, c.Sq, c.Sk
+    M = B * Sq
+    grads = {}
+    gm = GradBuf(rt, c.lpm)
+    if norm is None:
+        ds_f32 = None
+        ds_bf = _empty(M, H, _BF16, dev)
+        ops.cast_bf16(dout.contiguous(), ds_bf)
+        ops.colsum(dout, gm.b)
+    else:
+        ds_f32, ds_bf, da2, db2 = ln_bwd(rt, norm, dout, c.s, c.mean, c.sigma, p=rt.p, seed=c.seed_out, dbias=gm.b)
+        grads[norm.a_2], grads[norm.b_2] = da2, db2
+    # merge linear: wgrad + dgrad
+    ops.gemm(ds_bf, c.att, a_layout=1, b_layout=1, out_f32=gm.w, accumulate=True)
+    datt = _empty(M, H, _BF16, dev)
+    ops.gemm(ds_bf, c.lpm.w, b_layout=1, out_bf16=datt)
+    (wm, bm), = gm.per_param()
+    grads[mh.linear_merge.weight], grads[mh.linear_merge.bias] = wm, bm
+    # attention backward
+    lp = c.lp
+    g = GradBuf(rt, lp, 0, 1 if c.mode == "kv" else 3)
+    dkv_src = dv_src = None
+    if c.mode == "self":
+        dqkv = _empty(M, 3 * H, _BF16, dev)
+        dq, dk, dv = dqkv[:, :H], dqkv[:, H:2 * H], dqkv[:, 2 * H:]
+    else:
+        dq = _empty(M, H, _BF16, dev)
+        if dkv is not None:
+            dk, dv = dkv
+        else:
+            dkvb = _empty(B * Sk, 2 * H, _BF16, dev)
+            dk, dv = dkvb[:, :H], dkvb[:, H:]
+    ops.attn_bwd(c.q, c.k, c.v, c.mask, datt, dq, dk, dv, batch=B, heads=heads, sq=Sq, sk=Sk, head_dim=d,
+                 scale=1.0 / math.sqrt(d), dropout_p=rt.p, seed=c.seed_att)
+    dx = None
+    if c.mode == "self":
+        ops.colsum(dqkv, g.b)
+        ops.gemm(dqkv, c.x_bf, a_layout=1, b_layout=1, out_f32=g.w, accumulate=True)
+        if need_dx:
+            dx = _empty(M, H, _F32, dev)
+            ops.gemm(dqkv, lp.w, b_layout=1, resid=ds_f32, out_f32=dx)
+    else:
+        ops.colsum(dq, g.rows_b(0, 1))
+        ops.gemm(dq, c.x_bf, a_layout=1, b_layout=1, out_f32=g.rows_w(0, 1), accumulate=True)
+        if need_dx:
+            dx = _empty(M, H, _F32, dev)
+            ops.gemm(dq, lp.rows(0, 1)[0], b_layout=1, resid=ds_f32, out_f32=dx)
+        if c.mode == "cross":
+            Mk = B * Sk
+            if hasattr(c, "v_bf"):
+                ops.colsum(dk, g.rows_b(1, 2))
+                ops.colsum(dv, g.rows_b(2, 3))
+                ops.gemm(dk, c.kv_bf, a_layout=1, b_layout=1, out_f32=g.rows_w(1, 2), accumulate=True)
+                ops.gemm(dv, c.v_bf, a_layout=1, b_layout=1, out_f32=g.rows_w(2, 3), accumulate=True)
+                dkv_src = _empty(Mk, H, _F32, dev)
+                dv_src = _empty(Mk, H, _F32, dev)
+                ops.gemm(dk, lp.rows(1, 2)[0], b_layout=1, out_f32=dkv_src)
+                ops.gemm(dv, lp.rows(2, 3)[0], b_layout=1, out_f32=dv_src)
+            else:
+                ops.colsum(dkvb, g.rows_b(1, 3))
+                ops.gemm(dkvb, c.kv_bf, a_layout=1, b_layout=1, out_f32=g.rows_w(1, 3), accumulate=True)
+                dkv_src = _empty(Mk, H, _F32, dev)
+                ops.gemm(dkvb, lp.rows(1, 3)[0], b_layout=1, out_f32=dkv_src)
+    # (in "kv" mode the K/V weights belong to the caller's batched projection)
+    for (lin, (gw, gb)) in zip((mh.linear_q, mh.linear_k, mh.linear_v), g.per_param()):
+        grads[lin.weight], grads[lin.bias] = gw, gb
+    return dx, dkv_src, dv_src, grads
+
+
+# ------------------------------------------------------------------------------------------
+# MLP / FFN sub-layer:  LN(x + dropout(W2 dropout(relu(W1 x))))   (mca.py:123-125, net_utils.py:25-45)
+# With norm=None: the bare MLP module (fp32 output, no residual).
+# ------------------------------------------------------------------------------------------
+def mlp_fwd(rt, mlp, x, norm=None):
+    dev = x.bf.device
+    M = x.bf.shape[0]
+    c = Bag()
+    force = _force(rt.p > 0 or torch.is_grad_enabled())
+    lp1 = mlp.lp_fc().get(force)
+    lp2 = mlp.lp_out().get(force)
+    c.lp1, c.lp2, c.x_bf = lp1, lp2, x.bf
+    p_mid = rt.p if mlp.fc.dropout_r > 0 else 0.0
+    c.p_mid = p_mid
+    hmid = _empty(M, lp1.n, _BF16, dev)
+    c.seed_mid = rt.seed()
+    ops.gemm(x.bf, lp1.w, bias=lp1.b, relu=mlp.fc.use_relu, dropout_p=p_mid, seed=c.seed_mid, out_bf16=hmid)
+    c.hmid = hmid
+    if norm is None:
+        if lp2.n % 8 == 0:
+            out = _empty(M, lp2.n, _F32, dev)
+            ops.gemm(hmid, lp2.w, bias=lp2.b, out_f32=out)
+        else:   # narrow head (e.g. AttFlat glimpses): padded fp32 output buffer
+            ldp = (lp2.n + 3) // 4 * 4
+            out = torch.empty((M, ldp), dtype=_F32, device=dev)[:, :lp2.n]
+            ops.gemm(hmid, lp2.w, bias=lp2.b, out_f32=out)
+        return out, c
+    s = _empty(M, lp2.n, _F32, dev)
+    c.seed_out = rt.seed()
+    ops.gemm(hmid, lp2.w, bias=lp2.b, dropout_p=rt.p, seed=c.seed_out, resid=x.f32, out_f32=s)
+    out, c.mean, c.sigma = ln_fwd(norm, s)
+    c.s = s
+    return out, c
+
+
+def mlp_bwd(rt, mlp, c, dout, norm=None, need_dx=True):
+    """Returns (dx_f32, grads)."""
+    dev = dout.device
+    M = c.x_bf.shape[0]
+    grads = {}
+    g1, g2 = GradBuf(rt, c.lp1), GradBuf(rt, c.lp2)
+    if norm is None:
+        ds_f32 = None
+        ds_bf = _bf_padded(M, c.lp2.n, dev)
+        if ds_bf.stride(0) == c.lp2.n:
+            ops.cast_bf16(dout.contiguous(), ds_bf)
+        else:
+            ds_bf.copy_(dout)
+        ops.colsum(dout if dout.stride(-1) == 1 and dout.stride(0) % 4 == 0 else dout.contiguous(), g2.b)
+    else:
+        ds_f32, ds_bf, da2, db2 = ln_bwd(rt, norm, dout, c.s, c.mean, c.sigma, p=rt.p, seed=c.seed_out, dbias=g2.b)
+        grads[norm.a_2], grads[norm.b_2] = da2, db2
+    ops.gemm(ds_bf, c.hmid, a_layout=1, b_layout=1, out_f32=g2.w, accumulate=True)
+    dh = _empty(M, c.lp1.n, _BF16, dev)
+    gate = c.hmid if (mlp.fc.use_relu or c.p_mid > 0) else None
+    gate_scale = 1.0 / (1.0 - c.p_mid) if c.p_mid > 0 else 1.0
+    if gate is not None and not mlp.fc.use_relu:
+        raise ops.capi.McanError("dropout without ReLU in FC is not supported by the fused gate")
+    ops.gemm(ds_bf, c.lp2.w, b_layout=1, gate=gate, gate_scale=gate_scale, out_bf16=dh)
+    ops.colsum(dh, g1.b)
+    ops.gemm(dh, c.x_bf, a_layout=1, b_layout=1, out_f32=g1.w, accumulate=True)
+    dx = None
+    if need_dx:
+        dx = _empty(M, c.lp1.k, _F32, dev)
+        ops.gemm(dh, c.lp1.w, b_layout=1, resid=ds_f32, out_f32=dx)
+    (w1, b1), = g1.per_param()
+    (w2, b2), = g2.per_param()
+    grads[mlp.fc.linear.weight], grads[mlp.fc.linear.bias] = w1, b1
+    grads[mlp.linear.weight], grads[mlp.linear.bias] = w2, b2
+    return dx, grads
+
+
+# ------------------------------------------------------------------------------------------
+# SA / SGA layers
+# ------------------------------------------------------------------------------------------
+def sa_fwd(rt, sa, x, B, S, mask):
+    y, c1 = att_fwd(rt, sa.mhatt, x, B, S, key_mask=mask, norm=sa.norm1)
+    z, c2 = mlp_fwd(rt, sa.ffn.mlp, y, norm=sa.norm2)
+    return z, (c1, c2)
+
+
+def sa_bwd(rt, sa, ctx, dz):
+    c1, c2 = ctx
+    dy, grads = mlp_bwd(rt, sa.ffn.mlp, c2, dz, norm=sa.norm2)
+    dx, _, _, g1 = att_bwd(rt, sa.mhatt, c1, dy, norm=sa.norm1)
+    grads.update(g1)
+    return dx, grads
+
+
+def sga_fwd(rt, sga, x, y, B, Sx, Sy, x_mask, y_mask, kv=None):
+    """x: image-side Act [B*Sx,H]; y: question-side Act [B*Sy,H] (or kv=(K,V) pre-projected)."""
+    a, c1 = att_fwd(rt, sga.mhatt1, x, B, Sx, key_mask=x_mask, norm=sga.norm1)
+    if kv is None:
+        b, c2 = att_fwd(rt, sga.mhatt2, a, B, Sx, kv_src=y, Sk=Sy, key_mask=y_mask, norm=sga.norm2)
+    else:
+        b, c2 = att_fwd(rt, sga.mhatt2, a, B, Sx, Sk=Sy, key_mask=y_mask, kv=kv, norm=sga.norm2)
+    z, c3 = mlp_fwd(rt, sga.ffn.mlp, b, norm=sga.norm3)
+    return z, (c1, c2, c3)
+
+
+def sga_bwd(rt, sga, ctx, dz, dkv=None):
+    c1, c2, c3 = ctx
+    db, grads = mlp_bwd(rt, sga.ffn.mlp, c3, dz, norm=sga.norm3)
+    da, dy, _, g2 = att_bwd(rt, sga.mhatt2, c2, db, norm=sga.norm2, dkv=dkv)
+    dx, _, _, g1 = att_bwd(rt, sga.mhatt1, c1, da, norm=sga.norm1)
+    grads.update(g2)
+    grads.update(g1)
+    return dx, dy, grads
+
+
+# ------------------------------------------------------------------------------------------
+# MCA_ED (mca.py:178-186) as ONE kernel chain with the cross-layer K/V batch
+# ------------------------------------------------------------------------------------------
+def mca_ed_fwd(rt, m, x32, y32, B, Sx, Sy, x_mask, y_mask):
+    """x32: question features fp32 [B*Sx, H]; y32: image features fp32 [B*Sy, H]."""
+    H = m.hidden_size
+    L = len(m.dec_list)
+    dev = x32.device
+    x = act_from_f32(x32)
+    y = act_from_f32(y32)
+    enc_ctx = []
+    for enc in m.enc_list:
+        x, c = sa_fwd(rt, enc, x, B, Sx, x_mask)
+        enc_ctx.append(c)
+    # K/V of the final encoder output for all decoder layers: one GEMM [B*Sx, H] x [H, L*2H]
+    lpkv = m.lp_kv_all().get(_force(rt.p > 0 or torch.is_grad_enabled()))
+    kv_all = _empty(B * Sx, 2 * H * L, _BF16, dev)
+    if L > 0:
+        ops.gemm(x.bf, lpkv.w, bias=lpkv.b, out_bf16=kv_all)
+    dec_ctx = []
+    for i, dec in enumerate(m.dec_list):
+        kv = (kv_all[:, 2 * H * i: 2 * H * i + H], kv_all[:, 2 * H * i + H: 2 * H * (i + 1)])
+        y, c = sga_fwd(rt, dec, y, x, B, Sy, Sx, y_mask, x_mask, kv=kv)
+        dec_ctx.append(c)
+    ctx = Bag()
+    ctx.enc, ctx.dec, ctx.lpkv, ctx.xenc_bf, ctx.B, ctx.Sx, ctx.Sy = enc_ctx, dec_ctx, lpkv, x.bf, B, Sx, Sy
+    return x.f32, y.f32, ctx
+
+
+def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
+    """dx_out/dy_out: fp32 grads of the two outputs.  after_layer(bufs) is called with the flat
+    gradient buffers of a layer as soon as its kernels are enqueued (hook for the overlapped
+    gradient all-reduce in dp.py)."""
+    H = m.hidden_size
+    L = len(m.dec_list)
+    B, Sx, Sy = ctx.B, ctx.Sx, ctx.Sy
+    dev = dy_out.device
+    grads = {}
+    dkv_all = _empty(B * Sx, 2 * H * L, _BF16, dev)
+    dy = dy_out
+    for i in range(L - 1, -1, -1):
+        dec = m.dec_list[i]
+        dkv = (dkv_all[:, 2 * H * i: 2 * H * i + H], dkv_all[:, 2 * H * i + H: 2 * H * (i + 1)])
+        dy, _, g = sga_bwd(rt, dec, ctx.dec[i], dy, dkv=dkv)
+        grads.update(g)
+        if after_layer is not None:
+            after_layer(rt.bufs)
+            rt.bufs = []
+    dx = dx_out
+    if L > 0:
+        gkv = GradBuf(rt, ctx.lpkv)
+        ops.colsum(dkv_all, gkv.b)
+        ops.gemm(dkv_all, ctx.xenc_bf, a_layout=1, b_layout=1, out_f32=gkv.w, accumulate=True)
+        dxe = _empty(B * Sx, H, _F32, dev)
+        ops.gemm(dkv_all, ctx.lpkv.w, b_layout=1, resid=dx_out, out_f32=dxe)
+        dx = dxe
+        gk = {}
+        for (w, b), (gw, gb) in zip(ctx.lpkv.pairs, gkv.per_param()):
+            gk[w], gk[b] = gw, gb
+        grads.update(gk)
+        if after_layer is not None:
+            after_layer(rt.bufs)
+            rt.bufs = []
+    for i in range(len(m.enc_list) - 1, -1, -1):
+        dx, g = sa_bwd(rt, m.enc_list[i], ctx.enc[i], dx)
+        grads.update(g)
+        if after_layer is not None:
+            after_layer(rt.bufs)
+            rt.bufs = []
+    return dx, dy, grads
+
+
+# ------------------------------------------------------------------------------------------
+# AttFlat (net.py:38-55)
+# ------------------------------------------------------------------------------------------
+def attflat_fwd(rt, af, x, B, S, mask):
+    """x: Act [B*S, H] -> (x_atted fp32 [B,O], att_w fp32 [B,S,G], ctx)."""
+    H, G, M = af.hidden_size, af.flat_glimpses, af.flat_mlp_size
+    dev = x.bf.device
+    c = Bag()
+    force = _force(rt.p > 0 or torch.is_grad_enabled())
+    lp1 = af.mlp.lp_fc().get(force)
+    lpm = af.lp_merge().get(force)
+    c.lp1, c.lpm, c.x, c.B, c.S, c.mask = lp1, lpm, x, B, S, mask
+    p_mid = rt.p if af.mlp.fc.dropout_r > 0 else 0.0
+    c.p_mid = p_mid
+    hmid = _empty(B * S, M, _BF16, dev)
+    c.seed_mid = rt.seed()
+    ops.gemm(x.bf, lp1.w, bias=lp1.b, relu=True, dropout_p=p_mid, seed=c.seed_mid, out_bf16=hmid)
+    att_w = torch.empty((B, S, G), dtype=_F32, device=dev)
+    pooled = _empty(B, G * H, _BF16, dev)
+    w2 = af.mlp.linear.weight.detach()
+    b2 = af.mlp.linear.bias.detach()
+    ops.attflat_pool_fwd(hmid, w2, b2, mask, x.f32, batch=B, s=S, h=H, mlp=M, glimpses=G, att_w=att_w,
+                         pooled_bf16=pooled)
+    out = _empty(B, lpm.n, _F32, dev)
+    ops.gemm(pooled, lpm.w, bias=lpm.b, out_f32=out)
+    c.hmid, c.att_w, c.pooled = hmid, att_w, pooled
+    return out, att_w, c
+
+
+def attflat_bwd(rt, af, c, dout, need_dx=True):
+    H, G, M = af.hidden_size, af.flat_glimpses, af.flat_mlp_size
+    dev = dout.device
+    B, S = c.B, c.S
+    grads = {}
+    gm, g1 = GradBuf(rt, c.lpm), GradBuf(rt, c.lp1)
+    dout = dout.contiguous()
+    dout_bf = _empty(B, c.lpm.n, _BF16, dev)
+    ops.cast_bf16(dout, dout_bf)
+    ops.colsum(dout, gm.b)
+    ops.gemm(dout_bf, c.pooled, a_layout=1, b_layout=1, out_f32=gm.w, accumulate=True)
+    dpooled = _empty(B, G * H, _F32, dev)
+    ops.gemm(dout_bf, c.lpm.w, b_layout=1, out_f32=dpooled)
+    dx = _empty(B * S, H, _F32, dev)
+    dh = _empty(B * S, M, _BF16, dev)
+    gw2 = torch.zeros(G * M + G, dtype=_F32, device=dev)
+    rt.bufs.append(gw2)
+    ops.attflat_pool_bwd(dpooled, c.hmid, af.mlp.linear.weight.detach(), c.mask, c.x.f32, c.att_w, batch=B,
+                         s=S, h=H, mlp=M, glimpses=G, gate_scale=1.0 / (1.0 - c.p_mid) if c.p_mid > 0 else 1.0,
+                         dx=dx, dhmid=dh, dw2=gw2[: G * M], db2=gw2[G * M:])
+    ops.colsum(dh, g1.b)
+    ops.gemm(dh, c.x.bf, a_layout=1, b_layout=1, out_f32=g1.w, accumulate=True)
+    if need_dx:
+        ops.gemm(dh, c.lp1.w, b_layout=1, resid=dx, out_f32=dx)   # in place: dx += dh W1
+    (w1, b1), = g1.per_param()
+    (wm, bm), = gm.per_param()
+    grads[af.mlp.fc.linear.weight], grads[af.mlp.fc.linear.bias] = w1, b1
+    grads[af.mlp.linear.weight], grads[af.mlp.linear.bias] = gw2[: G * M].view(G, M), gw2[G * M:]
+    grads[af.linear_merge.weight], grads[af.linear_merge.bias] = wm, bm
+    return (dx if need_dx else None), grads
+
+
+# ------------------------------------------------------------------------------------------
+# plain linear on the tcgen05 GEMM (img_feat_linear / proj: the rows next to the hot path)
+# ------------------------------------------------------------------------------------------
+def linear_fwd(lp, x32):
+    dev = x32.device
+    M = x32.shape[0]
+    c = Bag()
+    xbf = _bf_padded(M, lp.k, dev)
+    if xbf.stride(0) == lp.k:
+        ops.cast_bf16(x32.contiguous(), xbf)
+    else:
+        xbf.copy_(x32)
+    ldo = (lp.n + 3) // 4 * 4
+    out = torch.empty((M, ldo), dtype=_F32, device=dev)[:, :lp.n]
+    ops.gemm(xbf, lp.w, bias=lp.b, out_f32=out)
+    c.xbf, c.lp = xbf, lp
+    return out, c
+
+
+def linear_bwd(rt, c, dout, need_dx=True):
+    lp = c.lp
+    dev = dout.device
+    M = dout.shape[0]
+    g = GradBuf(rt, lp)
+    dbf = _bf_padded(M, lp.n, dev)
+    if dbf.stride(0) == lp.n and dout.is_contiguous():
+        ops.cast_bf16(dout, dbf)
+    else:
+        dbf.copy_(dout)
+    ops.colsum(dbf, g.b)
+    ops.gemm(dbf, c.xbf, a_layout=1, b_layout=1, out_f32=g.w, accumulate=True)
+    dx = None
+    if need_dx:
+        dx = _empty(M, lp.k, _F32, dev)
+        ops.gemm(dbf, lp.w, b_layout=1, out_f32=dx)
+    (gw, gb), = g.per_param()
+    return dx, gw, gb

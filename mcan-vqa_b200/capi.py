@@ -35,6 +35,7 @@ class GemmArgs(ctypes.Structure):
         ("relu", c_int32),
         ("dropout_p", c_float),
         ("dropout_seed", c_uint32),
+        ("dropout_seed_dev", c_void_p),
         ("gate", c_void_p),
         ("ldg", c_int64),
         ("gate_scale", c_float),
@@ -71,6 +72,7 @@ class AttnArgs(ctypes.Structure):
         ("scale", c_float),
         ("dropout_p", c_float),
         ("dropout_seed", c_uint32),
+        ("dropout_seed_dev", c_void_p),
         ("stream", c_void_p),
     ]
 
@@ -101,7 +103,7 @@ SYMBOLS = {
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcan_layernorm_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                           c_int64, c_int64, c_void_p, c_void_p, c_float, c_uint32,
-                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcan_attflat_pool_fwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                              c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                              c_void_p, c_void_p]),
@@ -109,6 +111,7 @@ SYMBOLS = {
                                              c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcan_cast_bf16": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mcan_gate_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "mcan_colsum_bf16": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "mcan_colsum_f32": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
 }

@@ -33,6 +33,7 @@ struct AttnParams {
     uint32_t drop_thr;
     float drop_scale;
     uint32_t drop_seed;
+    const uint32_t* drop_seed_dev;
     // backward only
     const bf16* dout;
     long long lddo;
@@ -208,6 +209,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
     const int nwarps = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int nkt = skp / 8;
+    const uint32_t drop_seed =
+        p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
 
     for (int mt = warp; mt < sqp / 16; mt += nwarps) {
         float acc[kAttnMaxNT][4];
@@ -224,9 +227,9 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const uint32_t key = nt * 8 + 2 * t + j;
-                        acc[nt][j] = dropout_u16(base0 + key, p.drop_seed) >= p.drop_thr
+                        acc[nt][j] = dropout_u16(base0 + key, drop_seed) >= p.drop_thr
                                          ? acc[nt][j] * p.drop_scale : 0.f;
-                        acc[nt][2 + j] = dropout_u16(base1 + key, p.drop_seed) >= p.drop_thr
+                        acc[nt][2 + j] = dropout_u16(base1 + key, drop_seed) >= p.drop_thr
                                              ? acc[nt][2 + j] * p.drop_scale : 0.f;
                     }
                 }
@@ -299,6 +302,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnParams p) {
     const int g = lane >> 2, t = lane & 3;
     const int mi = lane >> 3, r = lane & 7;
     const int nkt = skp / 8;
+    const uint32_t drop_seed =
+        p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
 
     // ---- phase 1: per 16-query tile: P, dPd, dS, dQ ----
     for (int mt = warp; mt < sqp / 16; mt += nwarps) {
@@ -327,7 +332,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnParams p) {
                     const uint32_t base = (j < 2) ? base0 : base1;
                     float keep = 1.f;
                     if (p.drop_thr != 0)
-                        keep = dropout_u16(base + key, p.drop_seed) >= p.drop_thr ? p.drop_scale : 0.f;
+                        keep = dropout_u16(base + key, drop_seed) >= p.drop_thr ? p.drop_scale : 0.f;
                     pd[j] = acc[nt][j] * keep;
                     dp[nt][j] *= keep;
                     if (j < 2) d0 += acc[nt][j] * dp[nt][j]; else d1 += acc[nt][j] * dp[nt][j];
@@ -471,6 +476,7 @@ static void fill_attn_params(AttnParams& p, const mcan_attn_args* a) {
     p.drop_thr = a->dropout_p > 0.f ? dropout_threshold(a->dropout_p) : 0;
     p.drop_scale = a->dropout_p > 0.f ? 1.f / (1.f - a->dropout_p) : 1.f;
     p.drop_seed = a->dropout_seed;
+    p.drop_seed_dev = a->dropout_seed_dev;
 }
 
 template <typename K>

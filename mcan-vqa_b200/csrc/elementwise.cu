@@ -34,11 +34,20 @@ cast_bf16_kernel(const float* __restrict__ x, long long n, bf16* __restrict__ hi
     }
 }
 
+// out = act > 0 ? dy * scale : 0   (backward through ReLU + dropout using the saved activation)
+__global__ void __launch_bounds__(256)
+gate_bf16_kernel(const float* __restrict__ dy, const bf16* __restrict__ act, float scale,
+                 bf16* __restrict__ out, long long n) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __float2bfloat16_rn(__bfloat162float(act[i]) > 0.f ? dy[i] * scale : 0.f);
+}
+
 // out[c] += sum_r x[r,c].  Block = 32 column groups x 8 row lanes; grid.y slices the rows.
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, long long rows, long long cols, long long ld,
-              float* __restrict__ out) {
+              float* __restrict__ out, int vec_ok) {
     __shared__ float s_part[8][32 * VEC + 1];
     const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const long long c0 = ((long long)blockIdx.x * 32 + cg) * VEC;
@@ -48,7 +57,7 @@ colsum_kernel(const T* __restrict__ x, long long rows, long long cols, long long
     if (c0 < cols) {
         for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) {
             const T* p = x + r * ld + c0;
-            if (c0 + VEC <= cols) {
+            if (vec_ok && c0 + VEC <= cols) {
                 if constexpr (sizeof(T) == 2) {
                     const uint4 v = *reinterpret_cast<const uint4*>(p);
                     acc[0] += bf16_lo_to_f(v.x); acc[1] += bf16_hi_to_f(v.x);
@@ -80,7 +89,7 @@ colsum_kernel(const T* __restrict__ x, long long rows, long long cols, long long
 template <typename T, int VEC>
 static int launch_colsum(const T* x, int64_t rows, int64_t cols, int64_t ld, float* out, void* stream) {
     MCAN_REQUIRE(x && out && rows > 0 && cols > 0, "mcan_colsum: bad args");
-    MCAN_REQUIRE(ld % VEC == 0 && ((uintptr_t)x & 15) == 0, "mcan_colsum: alignment (ld %% %d)", VEC);
+    const int vec_ok = (ld % VEC == 0 && ((uintptr_t)x & 15) == 0) ? 1 : 0;
     const int sms = device_num_sms();
     MCAN_REQUIRE(sms > 0, "mcan_colsum: no CUDA device");
     const int gx = (int)((cols + 32 * VEC - 1) / (32 * VEC));
@@ -89,7 +98,7 @@ static int launch_colsum(const T* x, int64_t rows, int64_t cols, int64_t ld, flo
     if (gy > maxy) gy = maxy;
     if (gy < 1) gy = 1;
     colsum_kernel<T, VEC><<<dim3(gx, (unsigned)gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, rows, cols, ld, out);
+        x, rows, cols, ld, out, vec_ok);
     MCAN_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -120,4 +129,17 @@ extern "C" int mcan_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64
 extern "C" int mcan_colsum_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out,
                                void* stream) {
     return launch_colsum<float, 4>(x, rows, cols, ld, out, stream);
+}
+
+extern "C" int mcan_gate_bf16(const float* dy, const void* act, float scale, void* out, int64_t n,
+                              void* stream) {
+    MCAN_REQUIRE(dy && act && out && n > 0, "mcan_gate_bf16: bad args");
+    const int sms = device_num_sms();
+    MCAN_REQUIRE(sms > 0, "mcan_gate_bf16: no CUDA device");
+    long long blocks = (n + 255) / 256;
+    if (blocks > 16LL * sms) blocks = 16LL * sms;
+    gate_bf16_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        dy, reinterpret_cast<const bf16*>(act), scale, reinterpret_cast<bf16*>(out), n);
+    MCAN_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }

@@ -44,6 +44,7 @@ struct alignas(64) GemmParams {
     uint32_t drop_thr;
     float drop_scale;
     uint32_t drop_seed;
+    const uint32_t* drop_seed_dev;
     const bf16* gate;
     long long ldg;
     float gate_scale;
@@ -77,7 +78,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 // Applies the fused epilogue to 8 consecutive columns of one output row and stores them.
 // `full` = all 8 columns are inside N (vector path), otherwise per-element guards.
 __device__ __forceinline__ void epilogue_store8(const GemmParams& p, float (&v)[8], long long row,
-                                                int n0, bool full) {
+                                                int n0, bool full, uint32_t drop_seed) {
     const int nvalid = full ? 8 : max(0, min(8, p.n - n0));
     if (nvalid == 0) return;
     if (p.bias != nullptr) {
@@ -98,10 +99,19 @@ __device__ __forceinline__ void epilogue_store8(const GemmParams& p, float (&v)[
     }
     if (p.drop_thr != 0) {
         const uint32_t base = (uint32_t)(row * (long long)p.n + n0);
+        if ((base & 1U) == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint32_t u = dropout_u16(base + j, p.drop_seed);
-            v[j] = (u >= p.drop_thr) ? v[j] * p.drop_scale : 0.f;
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t r = dropout_bits_pair((base >> 1) + j, drop_seed);
+                v[2 * j] = ((r & 0xFFFFU) >= p.drop_thr) ? v[2 * j] * p.drop_scale : 0.f;
+                v[2 * j + 1] = ((r >> 16) >= p.drop_thr) ? v[2 * j + 1] * p.drop_scale : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t u = dropout_u16(base + j, drop_seed);
+                v[j] = (u >= p.drop_thr) ? v[j] * p.drop_scale : 0.f;
+            }
         }
     }
     if (p.gate != nullptr) {
@@ -318,6 +328,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     } else {
         // ===================== epilogue: TMEM -> registers -> global =====================
         const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) belong to this warp
+        const uint32_t drop_seed =
+            p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
@@ -343,7 +355,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                         float v[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-                        epilogue_store8(p, v, row, nc + g * 8, full);
+                        epilogue_store8(p, v, row, nc + g * 8, full, drop_seed);
                     }
                 }
             }
@@ -571,6 +583,7 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     p.drop_thr = a->dropout_p > 0.f ? dropout_threshold(a->dropout_p) : 0;
     p.drop_scale = a->dropout_p > 0.f ? 1.0f / (1.0f - a->dropout_p) : 1.0f;
     p.drop_seed = a->dropout_seed;
+    p.drop_seed_dev = a->dropout_seed_dev;
     p.gate = reinterpret_cast<const bf16*>(a->gate);
     p.ldg = a->ldg;
     p.gate_scale = a->gate_scale;

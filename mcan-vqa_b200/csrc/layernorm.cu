@@ -94,11 +94,14 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
               const float* __restrict__ mean_in, const float* __restrict__ sigma_in,
               const float* __restrict__ a2, float eps, long long rows, int h,
               float* __restrict__ dx32, bf16* __restrict__ dxbf, uint32_t drop_thr,
-              float drop_scale, uint32_t drop_seed, float* __restrict__ da2,
+              float drop_scale, uint32_t drop_seed_in, const uint32_t* __restrict__ drop_seed_dev,
+              float* __restrict__ da2,
               float* __restrict__ db2, float* __restrict__ dbias) {
     extern __shared__ float s_red[];  // [3][h]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = h >> 2;
+    const uint32_t drop_seed =
+        drop_seed_in ^ ((drop_thr != 0 && drop_seed_dev != nullptr) ? __ldg(drop_seed_dev) : 0U);
     for (int i = threadIdx.x; i < 3 * h; i += blockDim.x) s_red[i] = 0.f;
     __syncthreads();
 
@@ -228,8 +231,8 @@ extern "C" int mcan_layernorm_fwd(const float* x, int64_t rows, int64_t h, const
 extern "C" int mcan_layernorm_bwd(const float* dy, const float* x, const float* mean,
                                   const float* sigma, const float* a2, float eps, int64_t rows,
                                   int64_t h, float* dx_f32, void* dx_bf16, float dropout_p,
-                                  uint32_t dropout_seed, float* da2, float* db2, float* dbias,
-                                  void* stream) {
+                                  uint32_t dropout_seed, const uint32_t* dropout_seed_dev,
+                                  float* da2, float* db2, float* dbias, void* stream) {
     MCAN_REQUIRE(dy && x && mean && sigma && a2, "mcan_layernorm_bwd: null input");
     MCAN_REQUIRE(rows > 0 && h >= 8 && h % 4 == 0 && h <= 2048, "mcan_layernorm_bwd: rows=%lld h=%lld",
                  (long long)rows, (long long)h);
@@ -247,7 +250,7 @@ extern "C" int mcan_layernorm_bwd(const float* dy, const float* x, const float* 
     const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
     const size_t smem = (size_t)3 * h * sizeof(float);
     bf16* dbf = reinterpret_cast<bf16*>(dx_bf16);
-#define LN_BWD(MV) ln_bwd_kernel<MV><<<grid, kLnWarps * 32, smem, st>>>(dy, x, mean, sigma, a2, eps, rows, (int)h, dx_f32, dbf, thr, scale, dropout_seed, da2, db2, dbias)
+#define LN_BWD(MV) ln_bwd_kernel<MV><<<grid, kLnWarps * 32, smem, st>>>(dy, x, mean, sigma, a2, eps, rows, (int)h, dx_f32, dbf, thr, scale, dropout_seed, dropout_seed_dev, da2, db2, dbias)
     if (h <= 512) LN_BWD(4);
     else if (h <= 1024) LN_BWD(8);
     else LN_BWD(16);

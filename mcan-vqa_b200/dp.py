@@ -1,0 +1,135 @@
+"""Data-parallel gradient exchange: one process per GPU, NCCL all-reduce(SUM) over NVLink.
+
+Replaces the reference's nn.DataParallel (core/exec.py:62-63): there, replicas are re-broadcast
+every forward, outputs gathered on GPU 0 and gradients summed onto GPU 0
+(reduce_add_coalesced).  Here every rank owns a persistent replica and its own batch shard;
+the only exchange is ONE all-reduce(SUM) of the gradients per optimiser step -- SUM, not mean,
+because the loss is BCELoss(reduction='sum') (core/exec.py:67), so the result equals the
+single-process gradient of the global batch.
+
+Two modes:
+  * overlap (bench / training harness, grad_accu_steps == 1): MCA_ED's backward hands the flat
+    gradient buffers of each finished layer to `on_bufs`, which launches a coalesced async
+    all-reduce while the next layer's kernels run; parameters outside the backbone are caught
+    by post-accumulate-grad hooks; an end-of-backward callback waits for everything.
+  * at-step (reference exec.py unchanged, any grad_accu_steps): `sync_all_grads` reduces all
+    .grad tensors once, called from the overlay WarmupOptimizer.step().
+"""
+import torch
+import torch.distributed as dist
+from torch.autograd import Variable
+
+_active = None
+
+
+def world_size(group=None):
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+class GradSync(object):
+    def __init__(self, model, group=None, overlap=True, backbone_prefix="backbone."):
+        self.group = group
+        self.world = world_size(group)
+        self.overlap = overlap
+        self.pending = []
+        self.ready = []
+        self._queued = False
+        self.launches = 0
+        self.hooks = []
+        if self.world > 1 and overlap:
+            for name, p in model.named_parameters():
+                if p.requires_grad and not name.startswith(backbone_prefix):
+                    self.hooks.append(p.register_post_accumulate_grad_hook(self._param_ready))
+
+    # -- overlap mode ---------------------------------------------------------------------
+    def _param_ready(self, p):
+        self.ready.append(p.grad)
+        self._ensure_final_callback()
+
+    def on_bufs(self, bufs):
+        """Called inside MCA_ED.backward with the flat fp32 gradient buffers of one layer."""
+        self._flush_ready()
+        self._launch(list(bufs))
+        self._ensure_final_callback()
+
+    def _flush_ready(self):
+        if self.ready:
+            self._launch(self.ready)
+            self.ready = []
+
+    def _launch(self, tensors):
+        if self.world == 1 or not tensors:
+            return
+        with dist._coalescing_manager(self.group, device=tensors[0].device, async_ops=True) as cm:
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        self.pending.append(cm)
+        self.launches += 1
+
+    def _ensure_final_callback(self):
+        if not self._queued:
+            Variable._execution_engine.queue_callback(self._final)
+            self._queued = True
+
+    def _final(self):
+        self._flush_ready()
+        for w in self.pending:
+            w.wait()          # current stream waits for the NCCL stream; no host sync
+        self.pending = []
+        self._queued = False
+
+    def remove(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
+
+
+def attach(model, group=None, overlap=True, broadcast=True):
+    """Makes `model` data parallel across the default (or given) process group."""
+    global _active
+    if _active is not None:
+        _active.remove()
+    _active = GradSync(model, group=group, overlap=overlap)
+    if broadcast and _active.world > 1:
+        broadcast_params(model, group)
+    return _active
+
+
+def detach():
+    global _active
+    if _active is not None:
+        _active.remove()
+    _active = None
+
+
+def active():
+    return _active
+
+
+def layer_hook():
+    """The per-layer callback MCA_ED's backward should use (None when not data parallel)."""
+    if _active is not None and _active.world > 1 and _active.overlap:
+        return _active.on_bufs
+    return None
+
+
+def broadcast_params(model, group=None, src=0):
+    with torch.no_grad():
+        for p in model.parameters():
+            dist.broadcast(p.data, src=src, group=group)
+        for b in model.buffers():
+            dist.broadcast(b.data, src=src, group=group)
+
+
+def sync_all_grads(params, group=None):
+    """At-step mode: all-reduce(SUM) every existing .grad once (coalesced) and wait."""
+    if world_size(group) == 1:
+        return 0
+    grads = [p.grad for p in params if p.grad is not None]
+    if not grads:
+        return 0
+    with dist._coalescing_manager(group, device=grads[0].device, async_ops=True) as cm:
+        for g in grads:
+            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
+    cm.wait()
+    return len(grads)

@@ -36,6 +36,22 @@ def _req2d(t, dtype, name):
         raise capi.McanError("%s must be 2-D with unit inner stride" % name)
 
 
+_seed_dev = None
+
+
+def set_seed_tensor(t):
+    """Registers a 1-element int32/uint32 CUDA tensor whose value is XOR-ed into every dropout seed
+    on the device (None to clear).  Lets a captured CUDA graph draw new masks on each replay."""
+    global _seed_dev
+    if t is not None and not (t.is_cuda and t.numel() == 1 and t.element_size() == 4):
+        raise capi.McanError("seed tensor must be a 1-element 32-bit CUDA tensor")
+    _seed_dev = t
+
+
+def _seed_ptr():
+    return None if _seed_dev is None else _seed_dev.data_ptr()
+
+
 def num_sms():
     return capi.load().mcan_num_sms()
 
@@ -78,6 +94,7 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, 
     args.relu = 1 if relu else 0
     args.dropout_p = float(dropout_p)
     args.dropout_seed = int(seed) & 0xFFFFFFFF
+    args.dropout_seed_dev = _seed_ptr()
     if gate is not None:
         _req2d(gate, _BF16, "gemm gate")
         args.gate, args.ldg = gate.data_ptr(), gate.stride(0)
@@ -118,6 +135,7 @@ def _attn_args(q, k, v, key_mask, batch, heads, sq, sk, head_dim, scale, dropout
     args.scale = float(scale)
     args.dropout_p = float(dropout_p)
     args.dropout_seed = int(seed) & 0xFFFFFFFF
+    args.dropout_seed_dev = _seed_ptr()
     args.stream = _stream()
     return args
 
@@ -169,7 +187,7 @@ def layernorm_bwd(dy, x, mean, sigma, a2, eps, *, dx_f32=None, dx_bf16=None, dro
     rows = x.numel() // h
     capi.check(lib.mcan_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), sigma.data_ptr(),
                                       a2.data_ptr(), float(eps), rows, h, _ptr(dx_f32), _ptr(dx_bf16),
-                                      float(dropout_p), int(seed) & 0xFFFFFFFF, _ptr(da2), _ptr(db2),
+                                      float(dropout_p), int(seed) & 0xFFFFFFFF, _seed_ptr(), _ptr(da2), _ptr(db2),
                                       _ptr(dbias), _stream()), "mcan_layernorm_bwd")
 
 
@@ -205,6 +223,18 @@ def cast_bf16(x, hi, lo=None):
         raise capi.McanError("cast tensors must be contiguous")
     capi.check(lib.mcan_cast_bf16(x.data_ptr(), x.numel(), hi.data_ptr(), _ptr(lo), _stream()),
                "mcan_cast_bf16")
+
+
+def gate_bf16(dy, act, scale, out):
+    """out = bf16(act > 0 ? dy * scale : 0) -- backward through ReLU (+dropout) of a saved activation."""
+    lib = capi.load()
+    _req(dy, _F32, "gate dy")
+    _req(act, _BF16, "gate act")
+    _req(out, _BF16, "gate out")
+    if not (dy.is_contiguous() and act.is_contiguous() and out.is_contiguous()):
+        raise capi.McanError("gate tensors must be contiguous")
+    capi.check(lib.mcan_gate_bf16(dy.data_ptr(), act.data_ptr(), float(scale), out.data_ptr(), dy.numel(),
+                                  _stream()), "mcan_gate_bf16")
 
 
 def colsum(x, out):

@@ -1,0 +1,234 @@
+"""Parity of the overlay modules (core/model/*, CUDA kernels through the C ABI) against the CPU
+oracle and the golden fixtures generated from the unmodified reference.
+
+bf16 mode tolerances (north star): probabilities within 1e-2 relative error; gradients are
+compared per tensor by relative L2 error (bf16 operands, fp32 accumulation)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import mcan_oracle as orc  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOL_OUT = 1e-2       # relative (max abs err / max abs ref) on activations, bf16 mode
+TOL_GRAD = 4e-2      # relative L2 on gradients, bf16 mode
+
+
+def _rel_max(got, ref):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    return ((got - ref).abs().max() / (ref.abs().max() + 1e-30)).item()
+
+
+def _rel_l2(got, ref):
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    return ((got - ref).norm() / (ref.norm() + 1e-30)).item()
+
+
+def _load_params(module, params):
+    sd = {k: v.float() for k, v in params.items()}
+    module.load_state_dict(sd, strict=True)
+    return module.cuda()
+
+
+def _module_case(tag):
+    g = np.load(os.path.join(GOLD, "modules_tiny.npz"))
+    names = [str(n) for n in g[tag + "_pnames"]]
+    params = orc.seeded_params(names, g[tag + "_pshapes"], orc.MODULE_SEEDS[tag])
+    return g, params
+
+
+def _check_module(tag, build, call, oracle_call, tol_out=TOL_OUT, tol_grad=TOL_GRAD):
+    g, params = _module_case(tag)
+    cfg = orc.Cfg(dropout_rate=0.0, **orc.TINY)
+    mod = _load_params(build(cfg), params).train()       # dropout_rate = 0 -> deterministic
+    x = torch.from_numpy(g["x"]).float().cuda().requires_grad_(True)
+    y = torch.from_numpy(g["y"]).float().cuda().requires_grad_(True)
+    x_mask = torch.from_numpy(g["x_mask"]).cuda()
+    y_mask = torch.from_numpy(g["y_mask"]).cuda()
+    res = call(mod, x, y, x_mask, y_mask)
+    out = res[0] if isinstance(res, tuple) else res
+    # (a) against the golden fixture from the unmodified reference
+    assert _rel_max(out, torch.from_numpy(g[tag + "_out"])) < tol_out, tag
+    if isinstance(res, tuple):
+        assert _rel_max(res[1], torch.from_numpy(g[tag + "_out2"])) < tol_out, tag
+    gout = torch.from_numpy(g[tag + "_gout"]).float().cuda()
+    out.backward(gout)
+    if tag + "_dx" in g.files:
+        assert _rel_l2(x.grad, torch.from_numpy(g[tag + "_dx"])) < tol_grad, (tag, "dx")
+    if tag + "_dy" in g.files:
+        assert _rel_l2(y.grad, torch.from_numpy(g[tag + "_dy"])) < tol_grad, (tag, "dy")
+    # (b) every parameter gradient against the oracle's autograd (fp64, CPU)
+    p64 = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    xo = torch.from_numpy(g["x"]).requires_grad_(True)
+    yo = torch.from_numpy(g["y"]).requires_grad_(True)
+    ro = oracle_call(p64, cfg, xo, yo, torch.from_numpy(g["x_mask"]), torch.from_numpy(g["y_mask"]))
+    ro = ro[0] if isinstance(ro, tuple) else ro
+    ro.backward(torch.from_numpy(g[tag + "_gout"]))
+    worst = 0.0
+    for n, p in mod.named_parameters():
+        assert p.grad is not None, (tag, n)
+        worst = max(worst, _rel_l2(p.grad, p64[n].grad))
+        assert _rel_l2(p.grad, p64[n].grad) < tol_grad, (tag, n, _rel_l2(p.grad, p64[n].grad))
+    return worst
+
+
+def test_layernorm_module():
+    from core.model.net_utils import LayerNorm
+    _check_module("ln", lambda cfg: LayerNorm(cfg.hidden_size), lambda m, x, y, xm, ym: m(x),
+                  lambda p, cfg, x, y, xm, ym: orc.layer_norm(x, p["a_2"], p["b_2"]), tol_out=1e-5, tol_grad=1e-4)
+
+
+def test_mhatt_self_and_guided():
+    from core.model.mca import MHAtt
+    _check_module("mhatt_self", MHAtt, lambda m, x, y, xm, ym: m(x, x, x, xm),
+                  lambda p, cfg, x, y, xm, ym: orc.mhatt(p, "", x, x, x, xm, cfg))
+    _check_module("mhatt_guided", MHAtt, lambda m, x, y, xm, ym: m(y, y, x, ym),
+                  lambda p, cfg, x, y, xm, ym: orc.mhatt(p, "", y, y, x, ym, cfg))
+
+
+def test_sa_and_sga_layers():
+    from core.model.mca import SA, SGA
+    _check_module("sa", SA, lambda m, x, y, xm, ym: m(x, xm), lambda p, cfg, x, y, xm, ym: orc.sa(p, "", x, xm, cfg))
+    _check_module("sga", SGA, lambda m, x, y, xm, ym: m(x, y, xm, ym),
+                  lambda p, cfg, x, y, xm, ym: orc.sga(p, "", x, y, xm, ym, cfg))
+
+
+def test_attflat_module():
+    from core.model.net import AttFlat
+    _check_module("attflat", AttFlat, lambda m, x, y, xm, ym: m(x, xm),
+                  lambda p, cfg, x, y, xm, ym: orc.attflat(p, "", x, xm, cfg))
+
+
+def test_mhatt_three_distinct_inputs_and_no_mask():
+    from core.model.mca import MHAtt
+    cfg = orc.Cfg(dropout_rate=0.0, **orc.TINY)
+    torch.manual_seed(0)
+    m = MHAtt(cfg).cuda()
+    p = {k: v.detach().double().cpu().requires_grad_(True) for k, v in m.state_dict().items()}
+    v, k, q = (torch.randn(2, s, cfg.hidden_size).cuda().requires_grad_(True) for s in (7, 7, 5))
+    out = m(v, k, q, None)
+    vo, ko, qo = (t.detach().double().cpu().requires_grad_(True) for t in (v, k, q))
+    ref = orc.mhatt(p, "", vo, ko, qo, None, cfg)
+    assert _rel_max(out, ref) < TOL_OUT
+    go = torch.randn_like(out)
+    out.backward(go)
+    ref.backward(go.double().cpu())
+    for a, b in ((v, vo), (k, ko), (q, qo)):
+        assert _rel_l2(a.grad, b.grad) < TOL_GRAD
+    for n, prm in m.named_parameters():
+        assert _rel_l2(prm.grad, p[n].grad) < TOL_GRAD, n
+
+
+WHOLE = {
+    "tiny_dense": orc.TINY, "tiny_prefix": orc.TINY, "tiny_random": orc.TINY,
+    "tiny_d128": dict(orc.TINY, hidden_size=256, multi_head=2, flat_glimpses=1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(WHOLE))
+def test_net_against_reference_golden(name):
+    """Whole Net forward + BCE(sum) backward vs the fixture produced by the unmodified reference."""
+    from core.model.net import Net, Net2
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    batch, regions, tokens, token_size, answer_size, wseed, bseed = [int(v) for v in g["meta"]]
+    cfg = orc.Cfg(dropout_rate=0.0, **WHOLE[name])
+    sd = orc.synth_state_dict(cfg, token_size, answer_size, seed=wseed)
+    net = _load_params(Net(cfg, None, token_size, answer_size), sd).train()
+    v = torch.from_numpy(g["img_feat"]).float().cuda()
+    q = torch.from_numpy(g["ques_ix"]).cuda()
+    ans = torch.from_numpy(g["ans"]).float().cuda()
+    probs, v_out, v_mask, v_w, q_out, q_mask, q_w, a = net(v, q)
+    assert np.array_equal(v_mask.cpu().numpy(), g["v_mask"]) and np.array_equal(q_mask.cpu().numpy(), g["q_mask"])
+    assert _rel_max(probs, torch.from_numpy(g["probs"])) < TOL_OUT
+    # valid (unmasked) rows of the returned features; padded query rows are finite garbage in the reference too
+    vm = ~torch.from_numpy(g["v_mask"]).reshape(batch, regions)
+    qm = ~torch.from_numpy(g["q_mask"]).reshape(batch, tokens)
+    assert _rel_max(v_out.cpu()[vm], torch.from_numpy(g["v"])[vm]) < 3e-2
+    assert _rel_max(q_out.cpu()[qm], torch.from_numpy(g["q"])[qm]) < 3e-2
+    assert _rel_max(v_w, torch.from_numpy(g["v_w"])) < 3e-2 and _rel_max(q_w, torch.from_numpy(g["q_w"])) < 3e-2
+    loss = torch.nn.BCELoss(reduction="sum")(probs, ans)
+    assert abs(loss.item() - float(g["loss"])) < 2e-3 * abs(float(g["loss"]))
+    loss.backward()
+    names = [str(n) for n in g["grad_names"]]
+    norms = {n: d[0] for n, d in zip(names, g["grad_digests"])}
+    for n, p in net.named_parameters():
+        assert p.grad is not None, n
+        if norms[n] > 1e-6:
+            assert abs(p.grad.double().norm().item() - norms[n]) < 6e-2 * norms[n], (n, p.grad.norm().item(), norms[n])
+    # Net2 shares parameters and probabilities
+    net2 = _load_params(Net2(cfg, None, token_size, answer_size), sd).eval()
+    with torch.no_grad():
+        out2 = net2(v, q)
+    assert len(out2) == 5 and _rel_max(out2[0], torch.from_numpy(g["probs"])) < TOL_OUT
+
+
+@pytest.mark.parametrize("model,ragged", [("small", "prefix"), ("small", "random"), ("large", "prefix")])
+def test_net_full_size_against_oracle(model, ragged):
+    """MCAN-small / -large (BASELINE.json configs), ragged masks: probabilities and top-1 vs the fp32 oracle."""
+    from core.model.net import Net
+    cfgd = orc.SMALL if model == "small" else orc.LARGE
+    cfg = orc.Cfg(dropout_rate=0.0, **cfgd)
+    token_size, answer_size, B = 1000, 3129, 6 if model == "small" else 3
+    sd = orc.synth_state_dict(cfg, token_size, answer_size, seed=0)
+    v, q, ans = orc.synth_batch(cfg, B, 100, 14, token_size, answer_size, seed=1234, ragged=ragged)
+    with torch.no_grad():
+        ref = orc.net_forward(sd, v, q, cfg)
+    net = _load_params(Net(cfg, None, token_size, answer_size), sd).eval()
+    with torch.no_grad():
+        out = net(v.cuda(), q.cuda())
+    rel = ((out[0].cpu() - ref[0]).abs() / ref[0].abs().clamp_min(1e-6)).max().item()
+    assert rel < TOL_OUT, rel                          # element-wise relative error of the answer probs
+    # top-1 must agree wherever the oracle's own top-1/top-2 margin exceeds twice our max abs error
+    err = (out[0].cpu() - ref[0]).abs().max().item()
+    top2 = ref[0].topk(2, dim=1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 2 * err
+    assert (out[0].cpu().argmax(1)[safe] == ref[0].argmax(1)[safe]).all()
+
+
+def test_mca_ed_gradients_small_config():
+    """Backbone only, MCAN-small shapes: every parameter gradient vs oracle autograd."""
+    from core.model.mca import MCA_ED
+    cfg = orc.Cfg(dropout_rate=0.0, **dict(orc.SMALL, layer=2))
+    torch.manual_seed(1)
+    m = MCA_ED(cfg).cuda().train()
+    p = {k: v.detach().cpu().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    B = 4
+    x = torch.randn(B, 14, 512).cuda().requires_grad_(True)
+    y = torch.randn(B, 100, 512).cuda().requires_grad_(True)
+    xm = torch.zeros(B, 1, 1, 14, dtype=torch.bool); xm[:, :, :, 9:] = True
+    ym = torch.rand(B, 1, 1, 100) < 0.3
+    xo, yo = m(x, y, xm.cuda(), ym.cuda())
+    gx, gy = torch.randn_like(xo), torch.randn_like(yo)
+    torch.autograd.backward([xo, yo], [gx, gy])
+    xr = x.detach().cpu().double().requires_grad_(True)
+    yr = y.detach().cpu().double().requires_grad_(True)
+    rx, ry = orc.mca_ed(p, "", xr, yr, xm, ym, cfg)
+    torch.autograd.backward([rx, ry], [gx.cpu().double(), gy.cpu().double()])
+    assert _rel_max(xo, rx) < 2e-2 and _rel_max(yo, ry) < 2e-2
+    assert _rel_l2(x.grad, xr.grad) < TOL_GRAD and _rel_l2(y.grad, yr.grad) < TOL_GRAD
+    for n, prm in m.named_parameters():
+        assert _rel_l2(prm.grad, p[n].grad) < TOL_GRAD, (n, _rel_l2(prm.grad, p[n].grad))
+
+
+def test_dropout_statistics_and_determinism():
+    """Train-mode dropout: different masks per call, right keep rate, eval mode deterministic."""
+    from core.model.mca import SA
+    cfg = orc.Cfg(dropout_rate=0.1, **orc.TINY)
+    torch.manual_seed(0)
+    m = SA(cfg).cuda()
+    x = torch.randn(8, 14, cfg.hidden_size).cuda()
+    xm = torch.zeros(8, 1, 1, 14, dtype=torch.bool).cuda()
+    m.train()
+    a, b = m(x, xm), m(x, xm)
+    assert not torch.equal(a, b)
+    m.eval()
+    c, d = m(x, xm), m(x, xm)
+    assert torch.equal(c, d)
+    assert _rel_max(a, c) < 1.0 and torch.isfinite(a).all()
