@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""MCAN training-throughput benchmark (BASELINE.json metric: MCAN train samples/sec at 1/2/4/8 B200).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps K --warmup W      # CPU arm (oracle port of the reference)
+
+A step = one full training step of Net (embedding+LSTM, img_feat_linear, MCA_ED, AttFlat x2,
+proj, sigmoid, BCE(sum), backward, AdamW) on one synthetic batch of 64 samples per GPU
+(100 x 2048 region features, 14 tokens, 3129 answers), dropout 0.1, bf16 tensor-core GEMMs.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODELS = {
+    "small": dict(hidden_size=512, multi_head=8, layer=6, flat_mlp_size=512, flat_glimpses=1, flat_out_size=512),
+    "large": dict(hidden_size=1024, multi_head=16, layer=6, flat_mlp_size=512, flat_glimpses=1, flat_out_size=2048),
+}
+TOKEN_SIZE, ANSWER_SIZE, REGIONS, TOKENS, IMG_FEAT, BATCH = 20000, 3129, 100, 14, 2048, 64
+
+
+class Cfg(object):
+    def __init__(self, d, dropout_rate=0.1):
+        self.__dict__.update(d)
+        self.ff_size = 4 * self.hidden_size
+        self.hidden_size_head = self.hidden_size // self.multi_head
+        self.dropout_rate = dropout_rate
+        self.word_embed_size = 300
+        self.img_feat_size = IMG_FEAT
+        self.use_glove = False
+
+
+def hot_path_train_flops_per_sample(c):
+    """3 x forward FLOPs of MCA_ED + 2 x AttFlat, dense padded shapes."""
+    H, L, Sq, Sv, M, G, O = c.hidden_size, c.layer, TOKENS, REGIONS, c.flat_mlp_size, c.flat_glimpses, c.flat_out_size
+    sa = 24 * Sq * H * H + 4 * Sq * Sq * H
+    sga = (28 * Sv + 4 * Sq) * H * H + 4 * Sv * Sv * H + 4 * Sv * Sq * H
+    flat = sum(2 * S * H * M + 2 * S * M * G + 2 * S * H * G + 2 * H * G * O for S in (Sq, Sv))
+    return 3 * (L * (sa + sga) + flat)
+
+
+def synth_batch(batch, seed, device=None, pin=False):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(batch, REGIONS, IMG_FEAT, generator=g).abs_()
+    ques = torch.randint(1, TOKEN_SIZE, (batch, TOKENS), generator=g)
+    ans = torch.zeros(batch, ANSWER_SIZE)
+    idx = torch.randint(0, ANSWER_SIZE, (batch, 3), generator=g)
+    val = torch.tensor([0.3, 0.6, 0.9, 1.0])[torch.randint(0, 4, (batch, 3), generator=g)]
+    ans.scatter_(1, idx, val)
+    out = (img, ques, ans)
+    if pin:
+        out = tuple(t.pin_memory() for t in out)
+    if device is not None:
+        out = tuple(t.to(device) for t in out)
+    return out
+
+
+class ClockSampler(object):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], None, set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1]); pw.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def cpu_port_step_time(model, batch, iters, warm, threads=None):
+    """Times the oracle port of the reference (torch CPU fp32, dropout on, BCE(sum), backward,
+    AdamW) -- the ONLY use of oracle/ here: the CPU baseline leg."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mcan_oracle as orc
+    if threads:
+        torch.set_num_threads(threads)
+    cfg = orc.Cfg(dropout_rate=0.1, **MODELS[model])
+    cfg.training = True
+    torch.manual_seed(0)
+    sd = orc.synth_state_dict(cfg, TOKEN_SIZE, ANSWER_SIZE, seed=0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=2.5e-5, weight_decay=1e-4)
+    img, ques, ans = synth_batch(batch, 1234)
+    times = []
+    for it in range(warm + iters):
+        t0 = time.perf_counter()
+        opt.zero_grad(set_to_none=True)
+        probs = orc.net_forward(params, img, ques, cfg)[0]
+        loss = orc.bce_sum(probs, ans)
+        loss.backward()
+        opt.step()
+        if it >= warm:
+            times.append(time.perf_counter() - t0)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_b = args.cpu_batch
+    t, cores = cpu_port_step_time(args.model, sample_b, args.steps, args.warmup)
+    val = sample_b / t
+    line = {
+        "impl": "reference", "metric": "MCAN train samples/sec", "value": val, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "MCAN-%s training step (CPU oracle port of the reference, torch fp32, dropout 0.1, AdamW)" % args.model,
+                   "batch_per_step": sample_b},
+        "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "%d-sample training steps (fwd+bwd+AdamW), %d timed after %d warm-up" % (sample_b, args.steps, args.warmup)},
+        "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def gemm_roofline(trainer, batch_dev, peaks):
+    """One instrumented training step: CUDA events around every tcgen05 GEMM launch (on the launching
+    stream).  achieved = sum of algorithmic FLOPs / sum of launch durations."""
+    import torch
+    from mcan_vqa_b200 import ops
+    records = []
+    real = ops.gemm
+
+    def timed(a, b, **kw):
+        a0 = a[0] if isinstance(a, (list, tuple)) else a
+        b0 = b[0] if isinstance(b, (list, tuple)) else b
+        nseg = len(a) if isinstance(a, (list, tuple)) else 1
+        m, k = (a0.shape[0], a0.shape[1]) if kw.get("a_layout", 0) == 0 else (a0.shape[1], a0.shape[0])
+        n = b0.shape[0] if kw.get("b_layout", 0) == 0 else b0.shape[1]
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        real(a, b, **kw)
+        e.record()
+        records.append((2.0 * m * n * k * nseg, s, e))
+
+    ops.gemm = timed
+    try:
+        for _ in range(2):
+            records.clear()
+            trainer._raw_step(*batch_dev)
+            torch.cuda.synchronize()
+    finally:
+        ops.gemm = real
+    flops = sum(r[0] for r in records)
+    secs = sum(r[1].elapsed_time(r[2]) for r in records) * 1e-3
+    achieved = flops / secs / 1e12
+    peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+            "traffic": None, "kernel": "gemm_tcgen05_kernel (all %d launches of one training step)" % len(records),
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)"
+            if "bf16_tflops_sustained" in peaks else "fallback 1590 (B200_PROFILING.md)",
+            "gemm_ms_per_step": secs * 1e3, "gemm_flops_per_step": flops}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="large", choices=sorted(MODELS))
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of one CUDA graph per step")
+    ap.add_argument("--cpu-batch", type=int, default=8, help="samples per CPU-baseline step")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the MCAN hot path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__
+    __graft_entry__.build()
+    from mcan_vqa_b200 import capi
+    from mcan_vqa_b200.train import Trainer
+
+    cfg = Cfg(MODELS[args.model])
+    torch.manual_seed(0)           # identical random-init replicas on every rank
+    use_graph = not args.no_graph
+    graph_note = "cuda-graph"
+    trainer = Trainer(cfg, TOKEN_SIZE, ANSWER_SIZE, dev, lr_base=1e-4 if args.model == "small" else 5e-5,
+                      data_size=64 * 1000 * world, batch_size=BATCH * world, use_graph=use_graph,
+                      data_parallel=world > 1)
+    host = synth_batch(BATCH, 1234 + rank, pin=True)
+    batch_dev = tuple(t.to(dev) for t in host)
+    if use_graph:
+        try:
+            trainer.capture(*batch_dev)
+        except Exception as e:  # capture is an optimisation; fall back to eager launches and say so
+            graph_note = "eager (graph capture failed: %s)" % str(e).split("\n")[0][:120]
+            trainer.graph = None
+            trainer.use_graph = False
+            torch.cuda.synchronize()
+    else:
+        graph_note = "eager"
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_region(fn, steps):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            fn(i)
+        e.record()
+        barrier()
+        t = torch.tensor([s.elapsed_time(e) * 1e-3], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- device-resident throughput --------------------------------------------------------
+    for _ in range(args.warmup):
+        trainer.step(*batch_dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    secs = timed_region(lambda i: trainer.step(*batch_dev), args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(trainer.loss.item()) if trainer.graph is not None else None
+    value = world * BATCH * args.steps / secs
+
+    # ---- end to end: pinned host -> device copies and a device -> host read every step ------
+    copy_stream = torch.cuda.Stream()
+    bufs = [tuple(torch.empty_like(t, device=dev) for t in host) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    loss_host = torch.zeros(args.steps + args.warmup, dtype=torch.float32).pin_memory()
+
+    def prefetch(slot):
+        with torch.cuda.stream(copy_stream):
+            for d, h in zip(bufs[slot], host):
+                d.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    state = {"i": 0}
+    prefetch(0)
+    prefetch(1)
+
+    # simple, correct double buffering: slot i&1 is refilled right after step i consumed it
+    def e2e_step2(_):
+        i = state["i"]
+        slot = i & 1
+        torch.cuda.current_stream().wait_event(ready[slot])
+        loss = trainer.step(*bufs[slot])
+        done = torch.cuda.Event()
+        done.record()
+        copy_stream.wait_event(done)
+        prefetch(slot)
+        loss_host[i % loss_host.numel()].copy_(loss, non_blocking=True)
+        state["i"] = i + 1
+
+    for _ in range(args.warmup):
+        e2e_step2(0)
+    e2e_secs = timed_region(e2e_step2, args.steps)
+    e2e_value = world * BATCH * args.steps / e2e_secs
+    h2d = sum(t.numel() * t.element_size() for t in host)
+
+    # ---- instrumented eager steps (all ranks take part: the backward all-reduces) -------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    probe = Trainer.__new__(Trainer)
+    probe.__dict__.update(trainer.__dict__)
+    probe.graph, probe.use_graph = None, False
+    c0 = capi.launch_count
+    probe._raw_step(*batch_dev)      # kernels per step, counted on an eager step (the graph replays exactly these)
+    torch.cuda.synchronize()
+    per_step = capi.launch_count - c0
+    roof = gemm_roofline(probe, batch_dev, peaks)
+
+    if rank == 0:
+        flops_sample = hot_path_train_flops_per_sample(cfg)
+        sustained = peaks.get("bf16_tflops_sustained", 1400.0)
+        line = {
+            "metric": "MCAN train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "MCAN-%s full training step (Net fwd + BCE(sum) + bwd + AdamW), batch %d per GPU, "
+                                   "100x2048 region feats, 14 tokens, 3129 answers, dropout 0.1, random init" % (args.model, BATCH),
+                       "global_batch": BATCH * world, "parallelism": "dp%d" % world, "launch": graph_note,
+                       "l2": "working set per step (fp32 masters + bf16 copies + activations, > 1 GB) exceeds the 126 MB L2; no explicit flush"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_secs / args.steps * 1e3},
+            "gpu_launches": per_step * args.steps,
+            "kernels_per_step": per_step,
+            "roofline": roof,
+            "step_mfu": {"hot_path_train_flops_per_sample": flops_sample,
+                         "achieved_tflops": value / world * flops_sample / 1e12,
+                         "frac_of_sustained_peak": value / world * flops_sample / 1e12 / sustained},
+            "loss": loss_val,
+        }
+        if world == 1 and not args.skip_cpu:
+            t, cores = cpu_port_step_time(args.model, args.cpu_batch, 2, 1)
+            line["cpu_baseline"] = {"value": args.cpu_batch / t, "unit": "samples/s", "cores": cores, "kind": "port",
+                                    "sample": "oracle port, %d-sample training steps (fwd+bwd+AdamW, dropout 0.1), 2 timed after 1 warm-up" % args.cpu_batch}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

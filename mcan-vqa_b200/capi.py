@@ -141,7 +141,12 @@ def load():
     return lib
 
 
+launch_count = 0   # successful C-ABI calls == kernels enqueued by this process
+
+
 def check(rc, what):
+    global launch_count
+    launch_count += 1
     if rc != 0:
         msg = load().mcan_last_error()
         raise McanError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))

@@ -49,6 +49,7 @@ class Cfg(object):
         self.word_embed_size = word_embed_size
         self.img_feat_size = img_feat_size
         self.use_glove = use_glove
+        self.training = False   # True: apply nn.Dropout where the reference does (CPU-baseline timing)
         for k, v in extra.items():
             setattr(self, k, v)
 
@@ -64,6 +65,13 @@ TINY = dict(hidden_size=128, multi_head=2, layer=2, flat_mlp_size=64, flat_glimp
 # ------------------------------------------------------------------------------------------
 # primitives
 # ------------------------------------------------------------------------------------------
+def _drop(x, cfg):
+    """nn.Dropout(cfg.dropout_rate) in training mode, identity otherwise."""
+    if cfg is not None and getattr(cfg, "training", False) and cfg.dropout_rate > 0:
+        return torch.nn.functional.dropout(x, cfg.dropout_rate, True)
+    return x
+
+
 def linear(x, w, b):
     """nn.Linear: y = x W^T + b (weights are (out, in))."""
     return torch.matmul(x, w.t()) + b
@@ -90,7 +98,7 @@ def layer_norm_backward(dy, x, a2, eps=1e-6):
     return dx, (dy * c / s).sum(red), dy.sum(red)
 
 
-def attention(value, key, query, mask, dropout_keep=None, dropout_p=0.0):
+def attention(value, key, query, mask, dropout_keep=None, dropout_p=0.0, cfg=None):
     """core/model/mca.py:65-78.  value/key/query: [B,h,S,d]; mask: bool [B,1,1,Sk] or None.
     dropout_keep: optional bool [B,h,Sq,Sk] keep-mask standing in for nn.Dropout (mca.py:76)."""
     d_k = query.size(-1)
@@ -100,6 +108,7 @@ def attention(value, key, query, mask, dropout_keep=None, dropout_p=0.0):
     att_map = torch.softmax(scores, dim=-1)
     if dropout_keep is not None:
         att_map = att_map * dropout_keep.to(att_map.dtype) / (1.0 - dropout_p)
+    att_map = _drop(att_map, cfg)
     return torch.matmul(att_map, value)
 
 
@@ -133,34 +142,34 @@ def mhatt(p, pre, v, k, q, mask, cfg):
     vv = split(linear(v, p[pre + "linear_v.weight"], p[pre + "linear_v.bias"]))
     kk = split(linear(k, p[pre + "linear_k.weight"], p[pre + "linear_k.bias"]))
     qq = split(linear(q, p[pre + "linear_q.weight"], p[pre + "linear_q.bias"]))
-    atted = attention(vv, kk, qq, mask)
+    atted = attention(vv, kk, qq, mask, cfg=cfg)
     atted = atted.transpose(1, 2).contiguous().view(n, -1, cfg.hidden_size)
     return linear(atted, p[pre + "linear_merge.weight"], p[pre + "linear_merge.bias"])
 
 
-def mlp(p, pre, x):
+def mlp(p, pre, x, cfg=None):
     """core/model/net_utils.py:25-45: Linear -> ReLU -> (dropout) -> Linear."""
-    hmid = torch.relu(linear(x, p[pre + "fc.linear.weight"], p[pre + "fc.linear.bias"]))
+    hmid = _drop(torch.relu(linear(x, p[pre + "fc.linear.weight"], p[pre + "fc.linear.bias"])), cfg)
     return linear(hmid, p[pre + "linear.weight"], p[pre + "linear.bias"])
 
 
-def ffn(p, pre, x):
+def ffn(p, pre, x, cfg=None):
     """core/model/mca.py:85-98."""
-    return mlp(p, pre + "mlp.", x)
+    return mlp(p, pre + "mlp.", x, cfg)
 
 
 def sa(p, pre, x, x_mask, cfg):
     """core/model/mca.py:118-127 (post-LN residual blocks; dropout = identity in eval)."""
-    x = layer_norm(x + mhatt(p, pre + "mhatt.", x, x, x, x_mask, cfg), p[pre + "norm1.a_2"], p[pre + "norm1.b_2"])
-    x = layer_norm(x + ffn(p, pre + "ffn.", x), p[pre + "norm2.a_2"], p[pre + "norm2.b_2"])
+    x = layer_norm(x + _drop(mhatt(p, pre + "mhatt.", x, x, x, x_mask, cfg), cfg), p[pre + "norm1.a_2"], p[pre + "norm1.b_2"])
+    x = layer_norm(x + _drop(ffn(p, pre + "ffn.", x, cfg), cfg), p[pre + "norm2.a_2"], p[pre + "norm2.b_2"])
     return x
 
 
 def sga(p, pre, x, y, x_mask, y_mask, cfg):
     """core/model/mca.py:150-164: self-attention on x, then attention guided by y, then FFN."""
-    x = layer_norm(x + mhatt(p, pre + "mhatt1.", x, x, x, x_mask, cfg), p[pre + "norm1.a_2"], p[pre + "norm1.b_2"])
-    x = layer_norm(x + mhatt(p, pre + "mhatt2.", y, y, x, y_mask, cfg), p[pre + "norm2.a_2"], p[pre + "norm2.b_2"])
-    x = layer_norm(x + ffn(p, pre + "ffn.", x), p[pre + "norm3.a_2"], p[pre + "norm3.b_2"])
+    x = layer_norm(x + _drop(mhatt(p, pre + "mhatt1.", x, x, x, x_mask, cfg), cfg), p[pre + "norm1.a_2"], p[pre + "norm1.b_2"])
+    x = layer_norm(x + _drop(mhatt(p, pre + "mhatt2.", y, y, x, y_mask, cfg), cfg), p[pre + "norm2.a_2"], p[pre + "norm2.b_2"])
+    x = layer_norm(x + _drop(ffn(p, pre + "ffn.", x, cfg), cfg), p[pre + "norm3.a_2"], p[pre + "norm3.b_2"])
     return x
 
 
@@ -182,7 +191,7 @@ def mca_classifier(p, pre, y, y_mask, cfg):
 
 def attflat(p, pre, x, x_mask, cfg):
     """core/model/net.py:38-55.  Returns (x_atted [B,O], att_w [B,S,G]); softmax over dim=1."""
-    att_w = mlp(p, pre + "mlp.", x)
+    att_w = mlp(p, pre + "mlp.", x, cfg)
     att_w = att_w.masked_fill(x_mask.squeeze(1).squeeze(1).unsqueeze(2), -1e9)
     att_w = torch.softmax(att_w, dim=1)
     att_list = [torch.sum(att_w[:, :, i:i + 1] * x, dim=1) for i in range(cfg.flat_glimpses)]

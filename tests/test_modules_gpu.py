@@ -31,6 +31,22 @@ def _rel_l2(got, ref):
     return ((got - ref).norm() / (ref.norm() + 1e-30)).item()
 
 
+def _check_param_grads(named_params, ref_grads, tol, tag=""):
+    """Per-tensor relative L2 error.  Gradients that are exactly zero in exact arithmetic (K bias:
+    softmax is shift invariant; AttFlat glimpse bias) are compared against a floor of 1 % of the
+    largest gradient norm instead of their own ~1e-16 reference norm."""
+    refs = {n: ref_grads[n].detach().double().cpu() for n, _ in named_params}
+    floor = 1e-2 * max(r.norm().item() for r in refs.values())
+    worst = 0.0
+    for n, p in named_params:
+        assert p.grad is not None, (tag, n)
+        err = (p.grad.detach().double().cpu() - refs[n]).norm().item()
+        rel = err / max(refs[n].norm().item(), floor)
+        worst = max(worst, rel)
+        assert rel < tol, (tag, n, rel)
+    return worst
+
+
 def _load_params(module, params):
     sd = {k: v.float() for k, v in params.items()}
     module.load_state_dict(sd, strict=True)
@@ -71,12 +87,7 @@ def _check_module(tag, build, call, oracle_call, tol_out=TOL_OUT, tol_grad=TOL_G
     ro = oracle_call(p64, cfg, xo, yo, torch.from_numpy(g["x_mask"]), torch.from_numpy(g["y_mask"]))
     ro = ro[0] if isinstance(ro, tuple) else ro
     ro.backward(torch.from_numpy(g[tag + "_gout"]))
-    worst = 0.0
-    for n, p in mod.named_parameters():
-        assert p.grad is not None, (tag, n)
-        worst = max(worst, _rel_l2(p.grad, p64[n].grad))
-        assert _rel_l2(p.grad, p64[n].grad) < tol_grad, (tag, n, _rel_l2(p.grad, p64[n].grad))
-    return worst
+    return _check_param_grads(list(mod.named_parameters()), {n: v.grad for n, v in p64.items()}, tol_grad, tag)
 
 
 def test_layernorm_module():
@@ -122,8 +133,7 @@ def test_mhatt_three_distinct_inputs_and_no_mask():
     ref.backward(go.double().cpu())
     for a, b in ((v, vo), (k, ko), (q, qo)):
         assert _rel_l2(a.grad, b.grad) < TOL_GRAD
-    for n, prm in m.named_parameters():
-        assert _rel_l2(prm.grad, p[n].grad) < TOL_GRAD, n
+    _check_param_grads(list(m.named_parameters()), {n: v.grad for n, v in p.items()}, TOL_GRAD, "mhatt3")
 
 
 WHOLE = {
@@ -213,8 +223,8 @@ def test_mca_ed_gradients_small_config():
     torch.autograd.backward([rx, ry], [gx.cpu().double(), gy.cpu().double()])
     assert _rel_max(xo, rx) < 2e-2 and _rel_max(yo, ry) < 2e-2
     assert _rel_l2(x.grad, xr.grad) < TOL_GRAD and _rel_l2(y.grad, yr.grad) < TOL_GRAD
-    for n, prm in m.named_parameters():
-        assert _rel_l2(prm.grad, p[n].grad) < TOL_GRAD, (n, _rel_l2(prm.grad, p[n].grad))
+    worst = _check_param_grads(list(m.named_parameters()), {n: v.grad for n, v in p.items()}, TOL_GRAD, "mca_ed")
+    print("worst relative L2 gradient error: %.3g" % worst)
 
 
 def test_dropout_statistics_and_determinism():
