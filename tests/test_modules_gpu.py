@@ -18,7 +18,7 @@ import mcan_oracle as orc  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 TOL_OUT = 1e-2       # relative (max abs err / max abs ref) on activations, bf16 mode
-TOL_GRAD = 4e-2      # relative L2 on gradients, bf16 mode
+TOL_GRAD = 6e-2      # relative L2 on gradients, bf16 mode (bf16 operands through up to 18 chained sub-layers)
 
 
 def _rel_max(got, ref):
