@@ -121,25 +121,60 @@ __device__ __forceinline__ void qk_tile(const bf16* sQ, const bf16* sK, int mt, 
     }
 }
 
-// In-register masked softmax of the score tile (rows g and g+8 of this thread's quad).
-// Matches: scores/sqrt(d) -> masked_fill(mask, -1e9) -> softmax (mca.py:68-75).
-__device__ __forceinline__ void softmax_tile(float (&acc)[kAttnMaxNT][4], const uint8_t* sMask,
-                                             int nkt, int sk, float scale, int lane) {
+// Per-thread key bitmaps: bit (2*nt + j) describes key nt*8 + 2*(lane&3) + j.
+__device__ __forceinline__ void key_bits(const uint8_t* sMask, int nkt, int sk, int lane,
+                                         uint32_t& masked, uint32_t& valid) {
     const int t = lane & 3;
+    masked = 0;
+    valid = 0;
+    for (int nt = 0; nt < nkt; ++nt)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int key = nt * 8 + 2 * t + j;
+            if (key < sk) {
+                valid |= 1U << (2 * nt + j);
+                if (sMask[key]) masked |= 1U << (2 * nt + j);
+            }
+        }
+}
+
+// keep-scale factors of two adjacent elements idx, idx+1 (one hash when idx is even)
+__device__ __forceinline__ void dropout_pair(uint32_t idx, uint32_t seed, uint32_t thr, float scale,
+                                             float& k0, float& k1) {
+    uint32_t u0, u1;
+    if ((idx & 1U) == 0) {
+        const uint32_t r = dropout_bits_pair(idx >> 1, seed);
+        u0 = r & 0xFFFFU;
+        u1 = r >> 16;
+    } else {
+        u0 = dropout_u16(idx, seed);
+        u1 = dropout_u16(idx + 1, seed);
+    }
+    k0 = u0 >= thr ? scale : 0.f;
+    k1 = u1 >= thr ? scale : 0.f;
+}
+
+// In-register masked softmax of the score tile (rows g and g+8 of this thread's quad).
+// Matches: scores/sqrt(d) -> masked_fill(mask, -1e9) -> softmax (mca.py:68-75), evaluated in the
+// log2 domain: p = exp2(s*log2e - max).
+__device__ __forceinline__ void softmax_tile(float (&acc)[kAttnMaxNT][4], uint32_t masked,
+                                             uint32_t valid, int nkt, float scale) {
+    const float c = scale * kLog2e;
+    const float kMasked = -1e9f * kLog2e;
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < kAttnMaxNT; ++nt) {
         if (nt < nkt) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const int key = nt * 8 + 2 * t + j;
-                float s0 = acc[nt][j] * scale, s1 = acc[nt][2 + j] * scale;
-                if (key >= sk) {
+                const uint32_t bit = 1U << (2 * nt + j);
+                float s0 = acc[nt][j] * c, s1 = acc[nt][2 + j] * c;
+                if (!(valid & bit)) {
                     s0 = -INFINITY;
                     s1 = -INFINITY;
-                } else if (sMask[key]) {
-                    s0 = -1e9f;
-                    s1 = -1e9f;
+                } else if (masked & bit) {
+                    s0 = kMasked;
+                    s1 = kMasked;
                 }
                 acc[nt][j] = s0;
                 acc[nt][2 + j] = s1;
@@ -158,8 +193,8 @@ __device__ __forceinline__ void softmax_tile(float (&acc)[kAttnMaxNT][4], const 
         if (nt < nkt) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-                const float e0 = exp2f((acc[nt][j] - mx0) * kLog2e);
-                const float e1 = exp2f((acc[nt][2 + j] - mx1) * kLog2e);
+                const float e0 = exp2f(acc[nt][j] - mx0);
+                const float e1 = exp2f(acc[nt][2 + j] - mx1);
                 acc[nt][j] = e0;
                 acc[nt][2 + j] = e1;
                 sum0 += e0;
@@ -211,11 +246,13 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
     const int nkt = skp / 8;
     const uint32_t drop_seed =
         p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
+    uint32_t kmasked, kvalid;
+    key_bits(sMask, nkt, p.sk, lane, kmasked, kvalid);
 
     for (int mt = warp; mt < sqp / 16; mt += nwarps) {
         float acc[kAttnMaxNT][4];
         qk_tile<D>(sQ, sK, mt, nkt, lane, acc);
-        softmax_tile(acc, sMask, nkt, p.sk, p.scale, lane);
+        softmax_tile(acc, kmasked, kvalid, nkt, p.scale);
 
         const int row0 = mt * 16 + g, row1 = row0 + 8;
         if (p.drop_thr != 0) {
@@ -224,14 +261,14 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 #pragma unroll
             for (int nt = 0; nt < kAttnMaxNT; ++nt) {
                 if (nt < nkt) {
-#pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const uint32_t key = nt * 8 + 2 * t + j;
-                        acc[nt][j] = dropout_u16(base0 + key, drop_seed) >= p.drop_thr
-                                         ? acc[nt][j] * p.drop_scale : 0.f;
-                        acc[nt][2 + j] = dropout_u16(base1 + key, drop_seed) >= p.drop_thr
-                                             ? acc[nt][2 + j] * p.drop_scale : 0.f;
-                    }
+                    const uint32_t key = nt * 8 + 2 * t;
+                    float k0, k1;
+                    dropout_pair(base0 + key, drop_seed, p.drop_thr, p.drop_scale, k0, k1);
+                    acc[nt][0] *= k0;
+                    acc[nt][1] *= k1;
+                    dropout_pair(base1 + key, drop_seed, p.drop_thr, p.drop_scale, k0, k1);
+                    acc[nt][2] *= k0;
+                    acc[nt][3] *= k1;
                 }
             }
         }
@@ -274,7 +311,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 // backward
 // ------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
     constexpr int LDS = D + 8;
     extern __shared__ __align__(16) uint8_t smem_attn[];
     const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
@@ -304,12 +341,14 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnParams p) {
     const int nkt = skp / 8;
     const uint32_t drop_seed =
         p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
+    uint32_t kmasked, kvalid;
+    key_bits(sMask, nkt, p.sk, lane, kmasked, kvalid);
 
     // ---- phase 1: per 16-query tile: P, dPd, dS, dQ ----
     for (int mt = warp; mt < sqp / 16; mt += nwarps) {
         float acc[kAttnMaxNT][4];
         qk_tile<D>(sQ, sK, mt, nkt, lane, acc);
-        softmax_tile(acc, sMask, nkt, p.sk, p.scale, lane);
+        softmax_tile(acc, kmasked, kvalid, nkt, p.scale);
 
         // dPd = dO V^T (same operand pattern as Q K^T)
         float dp[kAttnMaxNT][4];
@@ -325,16 +364,16 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnParams p) {
 #pragma unroll
         for (int nt = 0; nt < kAttnMaxNT; ++nt) {
             if (nt < nkt) {
-                float pd[4];
+                float pd[4], keep[4] = {1.f, 1.f, 1.f, 1.f};
+                if (p.drop_thr != 0) {
+                    const uint32_t key = nt * 8 + 2 * t;
+                    dropout_pair(base0 + key, drop_seed, p.drop_thr, p.drop_scale, keep[0], keep[1]);
+                    dropout_pair(base1 + key, drop_seed, p.drop_thr, p.drop_scale, keep[2], keep[3]);
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const uint32_t key = nt * 8 + 2 * t + (j & 1);
-                    const uint32_t base = (j < 2) ? base0 : base1;
-                    float keep = 1.f;
-                    if (p.drop_thr != 0)
-                        keep = dropout_u16(base + key, drop_seed) >= p.drop_thr ? p.drop_scale : 0.f;
-                    pd[j] = acc[nt][j] * keep;
-                    dp[nt][j] *= keep;
+                    pd[j] = acc[nt][j] * keep[j];
+                    dp[nt][j] *= keep[j];
                     if (j < 2) d0 += acc[nt][j] * dp[nt][j]; else d1 += acc[nt][j] * dp[nt][j];
                 }
                 const int col = nt * 8 + 2 * t;
@@ -351,8 +390,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const AttnParams p) {
             if (nt < nkt) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int key = nt * 8 + 2 * t + (j & 1);
-                    const bool dead = (key >= p.sk) || sMask[key] || !((j < 2) ? v0 : v1);
+                    const uint32_t bit = 1U << (2 * nt + (j & 1));
+                    const bool dead = !(kvalid & bit) || (kmasked & bit) || !((j < 2) ? v0 : v1);
                     dp[nt][j] = dead ? 0.f : acc[nt][j] * (dp[nt][j] - ((j < 2) ? d0 : d1)) * p.scale;
                 }
                 const int col = nt * 8 + 2 * t;
@@ -534,7 +573,7 @@ extern "C" int mcan_attn_bwd(const mcan_attn_bwd_args* a) {
     const size_t smem = attn_bwd_smem(a->fwd.sq, a->fwd.sk, a->fwd.head_dim);
     const int mtiles = (a->fwd.sq + 15) / 16, ktiles = (a->fwd.sk + 15) / 16;
     const int mx = mtiles > ktiles ? mtiles : ktiles;
-    const int threads = 32 * (mx < 4 ? mx : 4);
+    const int threads = 32 * (mx < 8 ? mx : 8);
     const int grid = a->fwd.batch * a->fwd.heads;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a->fwd.stream);
     static size_t cfg64 = 48 * 1024, cfg128 = 48 * 1024;

@@ -55,22 +55,44 @@ colsum_kernel(const T* __restrict__ x, long long rows, long long cols, long long
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
     if (c0 < cols) {
-        for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8) {
-            const T* p = x + r * ld + c0;
-            if (vec_ok && c0 + VEC <= cols) {
+        const long long rstride = (long long)gridDim.y * 8;
+        const bool vec = vec_ok && (c0 + VEC <= cols);
+        for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += 4 * rstride) {
+            if (vec) {
+                // 4 independent 16-byte loads in flight per thread
                 if constexpr (sizeof(T) == 2) {
-                    const uint4 v = *reinterpret_cast<const uint4*>(p);
-                    acc[0] += bf16_lo_to_f(v.x); acc[1] += bf16_hi_to_f(v.x);
-                    acc[2] += bf16_lo_to_f(v.y); acc[3] += bf16_hi_to_f(v.y);
-                    acc[4] += bf16_lo_to_f(v.z); acc[5] += bf16_hi_to_f(v.z);
-                    acc[6] += bf16_lo_to_f(v.w); acc[7] += bf16_hi_to_f(v.w);
+                    uint4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        v[u] = (r + u * rstride < rows)
+                                   ? *reinterpret_cast<const uint4*>(x + (r + u * rstride) * ld + c0)
+                                   : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        acc[0] += bf16_lo_to_f(v[u].x); acc[1] += bf16_hi_to_f(v[u].x);
+                        acc[2] += bf16_lo_to_f(v[u].y); acc[3] += bf16_hi_to_f(v[u].y);
+                        acc[4] += bf16_lo_to_f(v[u].z); acc[5] += bf16_hi_to_f(v[u].z);
+                        acc[6] += bf16_lo_to_f(v[u].w); acc[7] += bf16_hi_to_f(v[u].w);
+                    }
                 } else {
-                    const float4 v = *reinterpret_cast<const float4*>(p);
-                    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+                    float4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        v[u] = (r + u * rstride < rows)
+                                   ? *reinterpret_cast<const float4*>(x + (r + u * rstride) * ld + c0)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        acc[0] += v[u].x; acc[1] += v[u].y; acc[2] += v[u].z; acc[3] += v[u].w;
+                    }
                 }
             } else {
-                for (int j = 0; j < VEC; ++j)
-                    if (c0 + j < cols) acc[j] += (float)p[j];
+                for (int u = 0; u < 4; ++u) {
+                    if (r + u * rstride >= rows) break;
+                    const T* p = x + (r + u * rstride) * ld + c0;
+                    for (int j = 0; j < VEC; ++j)
+                        if (c0 + j < cols) acc[j] += (float)p[j];
+                }
             }
         }
     }

@@ -66,7 +66,8 @@ struct GemmCfg {
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
     static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
     static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 16;
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarrierBytes + 1024;
+    static constexpr uint32_t kEpiBytes = kEpilogueWarps * 32 * 68 * 4;   // per-warp transpose tiles
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -75,126 +76,104 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                  : "memory");
 }
 
-// Applies the fused epilogue to 8 consecutive columns of one output row and stores them.
-// `full` = all 8 columns are inside N (vector path), otherwise per-element guards.
-__device__ __forceinline__ void epilogue_store8(const GemmParams& p, float (&v)[8], long long row,
-                                                int n0, bool full, uint32_t drop_seed) {
-    const int nvalid = full ? 8 : max(0, min(8, p.n - n0));
-    if (nvalid == 0) return;
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// Epilogue of one 32-row x 64-column chunk, executed by one warp AFTER the chunk has been
+// transposed through shared memory: lane l owns columns col, col+1 (col = nc + 2*l) of every
+// row, so each global load/store instruction of the warp covers one contiguous 128/256-byte
+// row segment (fully coalesced), the bias is loaded once per chunk and one dropout hash serves
+// an element pair.  `stage` = this warp's [32][kStageLd] fp32 staging tile.
+constexpr int kStageLd = 68;   // floats; 16-byte aligned rows, conflict-free v4 writes / v2 reads
+constexpr int kChunkN = 64;
+
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* stage, int lane,
+                                               long long row0, int rows_valid, int nc,
+                                               uint32_t drop_seed) {
+    const int col = nc + 2 * lane;
+    const bool c0 = col < p.n, c1 = col + 1 < p.n;
+    if (!c0) return;
+    const bool pair = c1;   // both columns valid -> vector accesses (col is even)
+    float b0 = 0.f, b1 = 0.f;
     if (p.bias != nullptr) {
-        if (full) {
-            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0));
-            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 4));
-            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < nvalid) v[j] += __ldg(p.bias + n0 + j);
-        }
+        b0 = __ldg(p.bias + col);
+        if (c1) b1 = __ldg(p.bias + col + 1);
     }
-    if (p.relu) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-    }
-    if (p.drop_thr != 0) {
-        const uint32_t base = (uint32_t)(row * (long long)p.n + n0);
-        if ((base & 1U) == 0) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint32_t r = dropout_bits_pair((base >> 1) + j, drop_seed);
-                v[2 * j] = ((r & 0xFFFFU) >= p.drop_thr) ? v[2 * j] * p.drop_scale : 0.f;
-                v[2 * j + 1] = ((r >> 16) >= p.drop_thr) ? v[2 * j + 1] * p.drop_scale : 0.f;
-            }
-        } else {
+    const bool drop_pair = ((p.n & 1) == 0);
+#pragma unroll 1
+    for (int r0 = 0; r0 < rows_valid; r0 += 8) {
+        float2 res[8];
+        uint32_t gt[8];
+        if (p.resid != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const uint32_t u = dropout_u16(base + j, drop_seed);
-                v[j] = (u >= p.drop_thr) ? v[j] * p.drop_scale : 0.f;
+                res[j] = make_float2(0.f, 0.f);
+                if (r0 + j < rows_valid) {
+                    const float* rp = p.resid + (row0 + r0 + j) * p.ldr + col;
+                    if (pair) res[j] = *reinterpret_cast<const float2*>(rp);
+                    else res[j].x = *rp;
+                }
             }
         }
-    }
-    if (p.gate != nullptr) {
-        const bf16* g = p.gate + row * p.ldg + n0;
-        if (full) {
-            const uint4 gv = __ldg(reinterpret_cast<const uint4*>(g));
-            const uint32_t gw[4] = {gv.x, gv.y, gv.z, gv.w};
+        if (p.gate != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                v[2 * j] = (bf16_lo_to_f(gw[j]) > 0.f) ? v[2 * j] * p.gate_scale : 0.f;
-                v[2 * j + 1] = (bf16_hi_to_f(gw[j]) > 0.f) ? v[2 * j + 1] * p.gate_scale : 0.f;
+            for (int j = 0; j < 8; ++j) {
+                gt[j] = 0;
+                if (r0 + j < rows_valid) {
+                    const bf16* gp = p.gate + (row0 + r0 + j) * p.ldg + col;
+                    if (pair) gt[j] = __ldg(reinterpret_cast<const uint32_t*>(gp));
+                    else gt[j] = (uint32_t)(*reinterpret_cast<const unsigned short*>(gp));
+                }
             }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < nvalid)
-                    v[j] = (__bfloat162float(g[j]) > 0.f) ? v[j] * p.gate_scale : 0.f;
         }
-    }
-    if (p.resid != nullptr) {
-        const float* r = p.resid + row * p.ldr + n0;
-        if (full) {
-            const float4 r0 = *reinterpret_cast<const float4*>(r);
-            const float4 r1 = *reinterpret_cast<const float4*>(r + 4);
-            v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w;
-            v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-        } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < nvalid) v[j] += r[j];
-        }
-    }
-    if (p.out_f32 != nullptr) {
-        float* o = p.out_f32 + row * p.ldo_f32 + n0;
-        if (p.accumulate) {
-            if (full) {
-                red_add_v4(o, v[0], v[1], v[2], v[3]);
-                red_add_v4(o + 4, v[4], v[5], v[6], v[7]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j < nvalid) atomicAdd(o + j, v[j]);
+        for (int j = 0; j < 8; ++j) {
+            if (r0 + j >= rows_valid) break;
+            const long long row = row0 + r0 + j;
+            const float2 a = *reinterpret_cast<const float2*>(stage + (r0 + j) * kStageLd + 2 * lane);
+            float v0 = a.x + b0, v1 = a.y + b1;
+            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            if (p.drop_thr != 0) {
+                const uint32_t idx = (uint32_t)(row * (long long)p.n + col);
+                uint32_t u0, u1;
+                if (drop_pair) {
+                    const uint32_t rnd = dropout_bits_pair(idx >> 1, drop_seed);
+                    u0 = rnd & 0xFFFFU; u1 = rnd >> 16;
+                } else {
+                    u0 = dropout_u16(idx, drop_seed); u1 = dropout_u16(idx + 1, drop_seed);
+                }
+                v0 = (u0 >= p.drop_thr) ? v0 * p.drop_scale : 0.f;
+                v1 = (u1 >= p.drop_thr) ? v1 * p.drop_scale : 0.f;
             }
-        } else if (full) {
-            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < nvalid) o[j] = v[j];
-        }
-    }
-    if (p.out_bf16 != nullptr) {
-        bf16* o = p.out_bf16 + row * p.ldo_bf16 + n0;
-        if (full) {
-            uint4 w;
-            w.x = pack_bf16x2(v[0], v[1]);
-            w.y = pack_bf16x2(v[2], v[3]);
-            w.z = pack_bf16x2(v[4], v[5]);
-            w.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(o) = w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < nvalid) o[j] = __float2bfloat16_rn(v[j]);
-        }
-    }
-    if (p.out_lo != nullptr) {
-        bf16* o = p.out_lo + row * p.ldo_bf16 + n0;
-        float l[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) l[j] = v[j] - __bfloat162float(__float2bfloat16_rn(v[j]));
-        if (full) {
-            uint4 w;
-            w.x = pack_bf16x2(l[0], l[1]);
-            w.y = pack_bf16x2(l[2], l[3]);
-            w.z = pack_bf16x2(l[4], l[5]);
-            w.w = pack_bf16x2(l[6], l[7]);
-            *reinterpret_cast<uint4*>(o) = w;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (j < nvalid) o[j] = __float2bfloat16_rn(l[j]);
+            if (p.gate != nullptr) {
+                v0 = (bf16_lo_to_f(gt[j]) > 0.f) ? v0 * p.gate_scale : 0.f;
+                v1 = (bf16_hi_to_f(gt[j]) > 0.f) ? v1 * p.gate_scale : 0.f;
+            }
+            if (p.resid != nullptr) { v0 += res[j].x; v1 += res[j].y; }
+            if (p.out_f32 != nullptr) {
+                float* o = p.out_f32 + row * p.ldo_f32 + col;
+                if (p.accumulate) {
+                    if (pair) red_add_v2(o, v0, v1);
+                    else atomicAdd(o, v0);
+                } else if (pair) {
+                    *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
+                } else {
+                    *o = v0;
+                }
+            }
+            if (p.out_bf16 != nullptr) {
+                bf16* o = p.out_bf16 + row * p.ldo_bf16 + col;
+                const uint32_t packed = pack_bf16x2(v0, v1);
+                if (pair) *reinterpret_cast<uint32_t*>(o) = packed;
+                else *o = __float2bfloat16_rn(v0);
+                if (p.out_lo != nullptr) {
+                    bf16* ol = p.out_lo + row * p.ldo_bf16 + col;
+                    const float l0 = v0 - bf16_lo_to_f(packed), l1 = v1 - bf16_hi_to_f(packed);
+                    if (pair) *reinterpret_cast<uint32_t*>(ol) = pack_bf16x2(l0, l1);
+                    else *ol = __float2bfloat16_rn(l0);
+                }
+            }
         }
     }
 }
@@ -205,10 +184,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BLOCK_N>;
     constexpr int kStages = Cfg::kStages;
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>(
-        (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static shared memory, so the
+    // dynamic window starts at the (1024-aligned) base of the CTA's shared memory.
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw;
+    if ((smem_u32(smem) & 1023U) != 0) {
+        if (threadIdx.x == 0) printf("mcan gemm: dynamic smem base not 1024-byte aligned\n");
+        __trap();
+    }
+    float* epi_stage = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full_bar = empty_bar + kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -326,42 +311,48 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             }
         }
     } else {
-        // ===================== epilogue: TMEM -> registers -> global =====================
+        // ========== epilogue: TMEM -> registers -> smem transpose -> coalesced global ==========
         const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) belong to this warp
         const uint32_t drop_seed =
             p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
+        float* stage = epi_stage + (warp - 2) * (32 * kStageLd);
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
             const int tile = unit % tiles;
             const int m0 = (tile / p.n_tiles) * BLOCK_M;
             const int n0 = (tile % p.n_tiles) * BLOCK_N;
-            const long long row = m0 + quad * 32 + lane;
-            const bool row_ok = row < p.m;
+            const long long row0 = m0 + quad * 32;
+            const int rows_valid = (int)max(0LL, min(32LL, (long long)p.m - row0));
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+            const int nchunks = min(BLOCK_N / kChunkN, (p.n - n0 + kChunkN - 1) / kChunkN);
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N / 32; ++c) {
-                const int nc = n0 + c * 32;
-                if (nc >= p.n) break;  // warp-uniform
+            for (int c = 0; c < nchunks; ++c) {
                 uint32_t r[32];
-                tmem_ld_32x32(taddr + (uint32_t)(c * 32), r);
-                tmem_ld_wait();
-                if (row_ok) {
-                    const bool full = (nc + 32 <= p.n);
+                float4* srow = reinterpret_cast<float4*>(stage + lane * kStageLd);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        float v[8];
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    tmem_ld_32x32(taddr + (uint32_t)(c * kChunkN + hlf * 32), r);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-                        epilogue_store8(p, v, row, nc + g * 8, full, drop_seed);
-                    }
+                    for (int q = 0; q < 8; ++q)
+                        srow[hlf * 8 + q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
                 }
+                if (c == nchunks - 1) {
+                    // the accumulator stage is fully drained: hand it back to the MMA warp now
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                } else {
+                    __syncwarp();
+                }
+                if (rows_valid > 0)
+                    epilogue_chunk(p, stage, lane, row0, rows_valid, n0 + c * kChunkN, drop_seed);
+                __syncwarp();   // staging tile is reused by the next chunk
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }

@@ -86,116 +86,103 @@ ln_fwd_kernel(const float* __restrict__ x, long long rows, int h, const float* _
 // Backward.  ghat = dy*a_2, c = x-mean, s = sigma+eps:
 //   dx = (ghat - mean(ghat))/s - c * sum(ghat*c) / (s^2 * sigma * (N-1))
 //   da_2 += dy*c/s ; db_2 += dy ; dbias += gated dx
-// Each warp walks rows with stride gridDim*warps and keeps per-lane column partial sums in
-// registers; the CTA folds them through shared memory and issues one atomicAdd per column.
-template <int MAXV>
-__global__ void __launch_bounds__(kLnWarps * 32)
+// A CTA owns a block of up to 32 consecutive rows.  Pass A (warp per row, streaming, a handful
+// of registers) reduces the two row statistics into shared memory.  Pass B re-reads the block
+// from L1/L2 with the threads laid out along the columns: each thread owns one float4 column
+// group for all rows of the block, so the a_2 / b_2 / bias column sums are 12 registers and
+// every global access is a coalesced 16-byte vector; one atomicAdd per column per CTA.
+constexpr int kLnBwdMaxRows = 32;
+constexpr int kLnBwdThreads = 256;
+
+__global__ void __launch_bounds__(kLnBwdThreads)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
               const float* __restrict__ mean_in, const float* __restrict__ sigma_in,
-              const float* __restrict__ a2, float eps, long long rows, int h,
+              const float* __restrict__ a2, float eps, long long rows, int h, int rows_per_cta,
               float* __restrict__ dx32, bf16* __restrict__ dxbf, uint32_t drop_thr,
               float drop_scale, uint32_t drop_seed_in, const uint32_t* __restrict__ drop_seed_dev,
-              float* __restrict__ da2,
-              float* __restrict__ db2, float* __restrict__ dbias) {
-    extern __shared__ float s_red[];  // [3][h]
+              float* __restrict__ da2, float* __restrict__ db2, float* __restrict__ dbias) {
+    __shared__ float s_mean[kLnBwdMaxRows], s_invs[kLnBwdMaxRows], s_mg[kLnBwdMaxRows], s_k2[kLnBwdMaxRows];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = h >> 2;
+    const long long row_base = (long long)blockIdx.x * rows_per_cta;
+    const int nrows = (int)min((long long)rows_per_cta, rows - row_base);
     const uint32_t drop_seed =
         drop_seed_in ^ ((drop_thr != 0 && drop_seed_dev != nullptr) ? __ldg(drop_seed_dev) : 0U);
-    for (int i = threadIdx.x; i < 3 * h; i += blockDim.x) s_red[i] = 0.f;
-    __syncthreads();
-
-    float4 acc_a[MAXV], acc_b[MAXV], acc_bias[MAXV];
-#pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-        acc_a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        acc_b[j] = acc_a[j];
-        acc_bias[j] = acc_a[j];
-    }
     const float4* ar = reinterpret_cast<const float4*>(a2);
-    const float inv_n = 1.f / (float)h;
 
-    for (long long row = (long long)blockIdx.x * kLnWarps + warp; row < rows;
-         row += (long long)gridDim.x * kLnWarps) {
+    // ---- pass A: row statistics ----
+    for (int r = warp; r < nrows; r += kLnBwdThreads / 32) {
+        const long long row = row_base + r;
         const float mean = mean_in[row], sigma = sigma_in[row];
-        const float s = sigma + eps, inv_s = 1.f / s;
         const float4* xr = reinterpret_cast<const float4*>(x + row * h);
         const float4* gr = reinterpret_cast<const float4*>(dy + row * h);
-        float4 c[MAXV], gh[MAXV];
         float sum_g = 0.f, sum_gc = 0.f;
-#pragma unroll
-        for (int j = 0; j < MAXV; ++j) {
-            const int i = lane + 32 * j;
-            if (i < nv) {
-                const float4 xv = xr[i], gv = gr[i], a = __ldg(ar + i);
-                c[j] = make_float4(xv.x - mean, xv.y - mean, xv.z - mean, xv.w - mean);
-                gh[j] = make_float4(gv.x * a.x, gv.y * a.y, gv.z * a.z, gv.w * a.w);
-                sum_g += (gh[j].x + gh[j].y) + (gh[j].z + gh[j].w);
-                sum_gc += (gh[j].x * c[j].x + gh[j].y * c[j].y) + (gh[j].z * c[j].z + gh[j].w * c[j].w);
-                acc_a[j].x += gv.x * c[j].x * inv_s; acc_a[j].y += gv.y * c[j].y * inv_s;
-                acc_a[j].z += gv.z * c[j].z * inv_s; acc_a[j].w += gv.w * c[j].w * inv_s;
-                acc_b[j].x += gv.x; acc_b[j].y += gv.y; acc_b[j].z += gv.z; acc_b[j].w += gv.w;
-            } else {
-                c[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                gh[j] = c[j];
-            }
+        for (int i = lane; i < nv; i += 32) {
+            const float4 xv = xr[i], gv = gr[i], a = __ldg(ar + i);
+            const float g0 = gv.x * a.x, g1 = gv.y * a.y, g2 = gv.z * a.z, g3 = gv.w * a.w;
+            sum_g += (g0 + g1) + (g2 + g3);
+            sum_gc += (g0 * (xv.x - mean) + g1 * (xv.y - mean)) + (g2 * (xv.z - mean) + g3 * (xv.w - mean));
         }
         sum_g = warp_sum(sum_g);
         sum_gc = warp_sum(sum_gc);
-        const float mg = sum_g * inv_n;
-        // sigma == 0: the reference's autograd gives NaN; emit the finite limit instead.
-        const float k2 = (sigma > 0.f) ? sum_gc / (s * s * sigma * (float)(h - 1)) : 0.f;
-#pragma unroll
-        for (int j = 0; j < MAXV; ++j) {
-            const int i = lane + 32 * j;
-            if (i < nv) {
-                float4 d;
-                d.x = (gh[j].x - mg) * inv_s - c[j].x * k2;
-                d.y = (gh[j].y - mg) * inv_s - c[j].y * k2;
-                d.z = (gh[j].z - mg) * inv_s - c[j].z * k2;
-                d.w = (gh[j].w - mg) * inv_s - c[j].w * k2;
-                if (dx32) reinterpret_cast<float4*>(dx32 + row * h)[i] = d;
-                if (dxbf != nullptr || dbias != nullptr) {
-                    float4 gd = d;
-                    if (drop_thr != 0) {
-                        const uint32_t base = (uint32_t)(row * h + 4 * i);  // multiple of 4
-                        const uint32_t r0 = dropout_bits_pair(base >> 1, drop_seed);
-                        const uint32_t r1 = dropout_bits_pair((base >> 1) + 1, drop_seed);
-                        gd.x = ((r0 & 0xFFFFU) >= drop_thr) ? d.x * drop_scale : 0.f;
-                        gd.y = ((r0 >> 16) >= drop_thr) ? d.y * drop_scale : 0.f;
-                        gd.z = ((r1 & 0xFFFFU) >= drop_thr) ? d.z * drop_scale : 0.f;
-                        gd.w = ((r1 >> 16) >= drop_thr) ? d.w * drop_scale : 0.f;
-                    }
-                    if (dxbf) store_bf16x4(dxbf + row * h + 4 * i, gd.x, gd.y, gd.z, gd.w);
-                    acc_bias[j].x += gd.x; acc_bias[j].y += gd.y;
-                    acc_bias[j].z += gd.z; acc_bias[j].w += gd.w;
-                }
-            }
-        }
-    }
-    // fold the per-lane partial sums: registers -> shared atomics -> one global atomic per column
-#pragma unroll
-    for (int j = 0; j < MAXV; ++j) {
-        const int i = lane + 32 * j;
-        if (i < nv) {
-            float* sa = s_red + 4 * i;
-            atomicAdd(sa + 0, acc_a[j].x); atomicAdd(sa + 1, acc_a[j].y);
-            atomicAdd(sa + 2, acc_a[j].z); atomicAdd(sa + 3, acc_a[j].w);
-            float* sb = s_red + h + 4 * i;
-            atomicAdd(sb + 0, acc_b[j].x); atomicAdd(sb + 1, acc_b[j].y);
-            atomicAdd(sb + 2, acc_b[j].z); atomicAdd(sb + 3, acc_b[j].w);
-            if (dbias) {
-                float* sc = s_red + 2 * h + 4 * i;
-                atomicAdd(sc + 0, acc_bias[j].x); atomicAdd(sc + 1, acc_bias[j].y);
-                atomicAdd(sc + 2, acc_bias[j].z); atomicAdd(sc + 3, acc_bias[j].w);
-            }
+        if (lane == 0) {
+            const float s = sigma + eps;
+            s_mean[r] = mean;
+            s_invs[r] = 1.f / s;
+            s_mg[r] = sum_g / (float)h;
+            // sigma == 0: the reference's autograd gives NaN; emit the finite limit instead.
+            s_k2[r] = (sigma > 0.f) ? sum_gc / (s * s * sigma * (float)(h - 1)) : 0.f;
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < h; i += blockDim.x) {
-        if (da2) atomicAdd(da2 + i, s_red[i]);
-        if (db2) atomicAdd(db2 + i, s_red[h + i]);
-        if (dbias) atomicAdd(dbias + i, s_red[2 * h + i]);
+
+    // ---- pass B: dx and the column sums ----
+    for (int c = threadIdx.x; c < nv; c += kLnBwdThreads) {
+        const float4 a = __ldg(ar + c);
+        float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = acc_a, acc_bias = acc_a;
+#pragma unroll 4
+        for (int r = 0; r < nrows; ++r) {
+            const long long row = row_base + r;
+            const float4 xv = reinterpret_cast<const float4*>(x + row * h)[c];
+            const float4 gv = reinterpret_cast<const float4*>(dy + row * h)[c];
+            const float mean = s_mean[r], inv_s = s_invs[r], mg = s_mg[r], k2 = s_k2[r];
+            const float cx = xv.x - mean, cy = xv.y - mean, cz = xv.z - mean, cw = xv.w - mean;
+            float4 d;
+            d.x = (gv.x * a.x - mg) * inv_s - cx * k2;
+            d.y = (gv.y * a.y - mg) * inv_s - cy * k2;
+            d.z = (gv.z * a.z - mg) * inv_s - cz * k2;
+            d.w = (gv.w * a.w - mg) * inv_s - cw * k2;
+            acc_a.x += gv.x * cx * inv_s; acc_a.y += gv.y * cy * inv_s;
+            acc_a.z += gv.z * cz * inv_s; acc_a.w += gv.w * cw * inv_s;
+            acc_b.x += gv.x; acc_b.y += gv.y; acc_b.z += gv.z; acc_b.w += gv.w;
+            if (dx32) reinterpret_cast<float4*>(dx32 + row * h)[c] = d;
+            if (dxbf != nullptr || dbias != nullptr) {
+                float4 gd = d;
+                if (drop_thr != 0) {
+                    const uint32_t base = (uint32_t)(row * h + 4 * c);  // multiple of 4
+                    const uint32_t r0 = dropout_bits_pair(base >> 1, drop_seed);
+                    const uint32_t r1 = dropout_bits_pair((base >> 1) + 1, drop_seed);
+                    gd.x = ((r0 & 0xFFFFU) >= drop_thr) ? d.x * drop_scale : 0.f;
+                    gd.y = ((r0 >> 16) >= drop_thr) ? d.y * drop_scale : 0.f;
+                    gd.z = ((r1 & 0xFFFFU) >= drop_thr) ? d.z * drop_scale : 0.f;
+                    gd.w = ((r1 >> 16) >= drop_thr) ? d.w * drop_scale : 0.f;
+                }
+                if (dxbf) store_bf16x4(dxbf + row * h + 4 * c, gd.x, gd.y, gd.z, gd.w);
+                acc_bias.x += gd.x; acc_bias.y += gd.y; acc_bias.z += gd.z; acc_bias.w += gd.w;
+            }
+        }
+        if (da2) {
+            atomicAdd(da2 + 4 * c + 0, acc_a.x); atomicAdd(da2 + 4 * c + 1, acc_a.y);
+            atomicAdd(da2 + 4 * c + 2, acc_a.z); atomicAdd(da2 + 4 * c + 3, acc_a.w);
+        }
+        if (db2) {
+            atomicAdd(db2 + 4 * c + 0, acc_b.x); atomicAdd(db2 + 4 * c + 1, acc_b.y);
+            atomicAdd(db2 + 4 * c + 2, acc_b.z); atomicAdd(db2 + 4 * c + 3, acc_b.w);
+        }
+        if (dbias) {
+            atomicAdd(dbias + 4 * c + 0, acc_bias.x); atomicAdd(dbias + 4 * c + 1, acc_bias.y);
+            atomicAdd(dbias + 4 * c + 2, acc_bias.z); atomicAdd(dbias + 4 * c + 3, acc_bias.w);
+        }
     }
 }
 
@@ -244,17 +231,15 @@ extern "C" int mcan_layernorm_bwd(const float* dy, const float* x, const float* 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int sms = device_num_sms();
     MCAN_REQUIRE(sms > 0, "mcan_layernorm_bwd: no CUDA device");
-    long long want = (rows + kLnWarps - 1) / kLnWarps;
-    const int grid = (int)(want < 2LL * sms ? want : 2LL * sms);
+    // rows per CTA: 32 when that still gives >= 1 CTA per SM, fewer for short inputs
+    int rpc = kLnBwdMaxRows;
+    while (rpc > 4 && (rows + rpc - 1) / rpc < sms) rpc >>= 1;
+    const int grid = (int)((rows + rpc - 1) / rpc);
     const uint32_t thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0;
     const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
-    const size_t smem = (size_t)3 * h * sizeof(float);
-    bf16* dbf = reinterpret_cast<bf16*>(dx_bf16);
-#define LN_BWD(MV) ln_bwd_kernel<MV><<<grid, kLnWarps * 32, smem, st>>>(dy, x, mean, sigma, a2, eps, rows, (int)h, dx_f32, dbf, thr, scale, dropout_seed, dropout_seed_dev, da2, db2, dbias)
-    if (h <= 512) LN_BWD(4);
-    else if (h <= 1024) LN_BWD(8);
-    else LN_BWD(16);
-#undef LN_BWD
+    ln_bwd_kernel<<<grid, kLnBwdThreads, 0, st>>>(dy, x, mean, sigma, a2, eps, rows, (int)h, rpc, dx_f32,
+                                                reinterpret_cast<bf16*>(dx_bf16), thr, scale, dropout_seed,
+                                                dropout_seed_dev, da2, db2, dbias);
     MCAN_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
