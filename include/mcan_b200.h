@@ -97,6 +97,7 @@ typedef struct mcan_gemm_args {
     int32_t accumulate;
     int32_t split_k; /* 0 = choose automatically (only when accumulate != 0) */
     int32_t block_n; /* 0 = choose automatically, else 128 or 256 */
+    int32_t cta_group; /* 0 = choose automatically, 1 = one CTA per tile, 2 = CTA pair (256-row tiles) */
     void* stream;
 } mcan_gemm_args;
 

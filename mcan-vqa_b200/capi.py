@@ -49,6 +49,7 @@ class GemmArgs(ctypes.Structure):
         ("accumulate", c_int32),
         ("split_k", c_int32),
         ("block_n", c_int32),
+        ("cta_group", c_int32),
         ("stream", c_void_p),
     ]
 

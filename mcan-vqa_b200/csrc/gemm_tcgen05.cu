@@ -58,16 +58,19 @@ struct alignas(64) GemmParams {
     int accumulate;
 };
 
-template <int BLOCK_N>
+// CG = CTAs per MMA (cta_group): 1 = one SM per 128 x BLOCK_N tile, 2 = a CTA pair computes a
+// 256 x BLOCK_N tile with one tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A
+// and only HALF of the B tile, which halves the L2->smem operand traffic and the per-SM shared
+// memory read bandwidth of the UMMA (the two limits of the 1-CTA kernel).
+template <int BLOCK_N, int CG>
 struct GemmCfg {
-    static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
     static constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 2;
-    static constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K * 2;
+    static constexpr uint32_t kBBytes = (BLOCK_N / CG) * BLOCK_K * 2;
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (192 * 1024) / kStageBytes;
     static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
     static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 16;
-    static constexpr uint32_t kEpiBytes = kEpilogueWarps * 32 * 68 * 4;   // per-warp transpose tiles
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarrierBytes;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarrierBytes;
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -80,109 +83,164 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
-// Epilogue of one 32-row x 64-column chunk, executed by one warp AFTER the chunk has been
-// transposed through shared memory: lane l owns columns col, col+1 (col = nc + 2*l) of every
-// row, so each global load/store instruction of the warp covers one contiguous 128/256-byte
-// row segment (fully coalesced), the bias is loaded once per chunk and one dropout hash serves
-// an element pair.  `stage` = this warp's [32][kStageLd] fp32 staging tile.
-constexpr int kStageLd = 68;   // floats; 16-byte aligned rows, conflict-free v4 writes / v2 reads
+// Fused epilogue for a [16 rows x 64 columns] accumulator fragment held in the tcgen05.ld
+// 16x256b layout: thread (g = lane/4, t = lane%4) owns, for k < 8 and h < 2, the two adjacent
+// columns col0 + 8k + 2t, +1 of row row0 + g + 8h (register r[4k + 2h + c]).  Four neighbouring
+// lanes cover one contiguous 32-byte sector of a row with their float2 accesses -- no shared
+// memory staging, which would compete with the UMMA operand reads.
+//
+// The code is organised as one straight-line PASS per epilogue stage with the runtime flag tested
+// once per pass: the first version tested every flag for every element pair, unrolled to 4096
+// SASS instructions (64 KiB), and the epilogue warps starved on instruction-cache misses
+// (ncu: stall_no_inst on every line).
 constexpr int kChunkN = 64;
 
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const float* stage, int lane,
-                                               long long row0, int rows_valid, int nc,
-                                               uint32_t drop_seed) {
-    const int col = nc + 2 * lane;
-    const bool c0 = col < p.n, c1 = col + 1 < p.n;
-    if (!c0) return;
-    const bool pair = c1;   // both columns valid -> vector accesses (col is even)
-    float b0 = 0.f, b1 = 0.f;
-    if (p.bias != nullptr) {
-        b0 = __ldg(p.bias + col);
-        if (c1) b1 = __ldg(p.bias + col + 1);
-    }
-    const bool drop_pair = ((p.n & 1) == 0);
+// generic (slow) path for chunks that cross the N boundary or odd N: per element, rolled loops
+__device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const float* v, int lane,
+                                                  long long row0, int col0, uint32_t drop_seed) {
+    const int g = lane >> 2, t = lane & 3;
 #pragma unroll 1
-    for (int r0 = 0; r0 < rows_valid; r0 += 8) {
-        float2 res[8];
-        uint32_t gt[8];
-        if (p.resid != nullptr) {
+    for (int i = 0; i < 32; ++i) {
+        const int k = i >> 2, h = (i >> 1) & 1, c = i & 1;
+        const long long row = row0 + g + 8 * h;
+        const int col = col0 + 8 * k + 2 * t + c;
+        if (row >= p.m || col >= p.n) continue;
+        float x = v[i];
+        if (p.bias != nullptr) x += __ldg(p.bias + col);
+        if (p.relu) x = fmaxf(x, 0.f);
+        if (p.drop_thr != 0)
+            x = dropout_u16((uint32_t)(row * (long long)p.n + col), drop_seed) >= p.drop_thr ? x * p.drop_scale : 0.f;
+        if (p.gate != nullptr) x = __bfloat162float(p.gate[row * p.ldg + col]) > 0.f ? x * p.gate_scale : 0.f;
+        if (p.resid != nullptr) x += p.resid[row * p.ldr + col];
+        if (p.out_f32 != nullptr) {
+            if (p.accumulate) atomicAdd(p.out_f32 + row * p.ldo_f32 + col, x);
+            else p.out_f32[row * p.ldo_f32 + col] = x;
+        }
+        if (p.out_bf16 != nullptr) {
+            const bf16 hi = __float2bfloat16_rn(x);
+            p.out_bf16[row * p.ldo_bf16 + col] = hi;
+            if (p.out_lo != nullptr) p.out_lo[row * p.ldo_bf16 + col] = __float2bfloat16_rn(x - __bfloat162float(hi));
+        }
+    }
+}
+
+__device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_t (&r)[32], int lane,
+                                              long long row0, int col0, uint32_t drop_seed) {
+    const int g = lane >> 2, t = lane & 3;
+    float v[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                res[j] = make_float2(0.f, 0.f);
-                if (r0 + j < rows_valid) {
-                    const float* rp = p.resid + (row0 + r0 + j) * p.ldr + col;
-                    if (pair) res[j] = *reinterpret_cast<const float2*>(rp);
-                    else res[j].x = *rp;
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (col0 + kChunkN > p.n || (p.n & 1)) {
+        epilogue_frag_ragged(p, v, lane, row0, col0, drop_seed);
+        return;
+    }
+    const int col = col0 + 2 * t;   // + 8k
+    const long long rows[2] = {row0 + g, row0 + g + 8};
+    const bool ok[2] = {rows[0] < p.m, rows[1] < p.m};
+
+    if (p.bias != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float2 b = __ldg(reinterpret_cast<const float2*>(p.bias + col + 8 * k));
+            v[4 * k] += b.x; v[4 * k + 1] += b.y; v[4 * k + 2] += b.x; v[4 * k + 3] += b.y;
+        }
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (p.drop_thr != 0) {
+        const uint32_t thr = p.drop_thr;
+        const float sc = p.drop_scale;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const uint32_t base = (uint32_t)(rows[h] * (long long)p.n + col) >> 1;   // pair index (n even)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t rnd = dropout_bits_pair(base + 4 * k, drop_seed);
+                v[4 * k + 2 * h] = ((rnd & 0xFFFFU) >= thr) ? v[4 * k + 2 * h] * sc : 0.f;
+                v[4 * k + 2 * h + 1] = ((rnd >> 16) >= thr) ? v[4 * k + 2 * h + 1] * sc : 0.f;
+            }
+        }
+    }
+    if (p.gate != nullptr) {
+        const float gs = p.gate_scale;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (ok[h]) {
+                const uint32_t* gp = reinterpret_cast<const uint32_t*>(p.gate + rows[h] * p.ldg + col);
+                uint32_t gt[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gt[k] = __ldg(gp + 4 * k);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v[4 * k + 2 * h] = (bf16_lo_to_f(gt[k]) > 0.f) ? v[4 * k + 2 * h] * gs : 0.f;
+                    v[4 * k + 2 * h + 1] = (bf16_hi_to_f(gt[k]) > 0.f) ? v[4 * k + 2 * h + 1] * gs : 0.f;
                 }
             }
         }
-        if (p.gate != nullptr) {
+    }
+    if (p.resid != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                gt[j] = 0;
-                if (r0 + j < rows_valid) {
-                    const bf16* gp = p.gate + (row0 + r0 + j) * p.ldg + col;
-                    if (pair) gt[j] = __ldg(reinterpret_cast<const uint32_t*>(gp));
-                    else gt[j] = (uint32_t)(*reinterpret_cast<const unsigned short*>(gp));
+        for (int h = 0; h < 2; ++h) {
+            if (ok[h]) {
+                const float2* rp = reinterpret_cast<const float2*>(p.resid + rows[h] * p.ldr + col);
+                float2 res[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) res[k] = rp[4 * k];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v[4 * k + 2 * h] += res[k].x;
+                    v[4 * k + 2 * h + 1] += res[k].y;
                 }
             }
         }
+    }
+    if (p.out_f32 != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (r0 + j >= rows_valid) break;
-            const long long row = row0 + r0 + j;
-            const float2 a = *reinterpret_cast<const float2*>(stage + (r0 + j) * kStageLd + 2 * lane);
-            float v0 = a.x + b0, v1 = a.y + b1;
-            if (p.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            if (p.drop_thr != 0) {
-                const uint32_t idx = (uint32_t)(row * (long long)p.n + col);
-                uint32_t u0, u1;
-                if (drop_pair) {
-                    const uint32_t rnd = dropout_bits_pair(idx >> 1, drop_seed);
-                    u0 = rnd & 0xFFFFU; u1 = rnd >> 16;
-                } else {
-                    u0 = dropout_u16(idx, drop_seed); u1 = dropout_u16(idx + 1, drop_seed);
-                }
-                v0 = (u0 >= p.drop_thr) ? v0 * p.drop_scale : 0.f;
-                v1 = (u1 >= p.drop_thr) ? v1 * p.drop_scale : 0.f;
-            }
-            if (p.gate != nullptr) {
-                v0 = (bf16_lo_to_f(gt[j]) > 0.f) ? v0 * p.gate_scale : 0.f;
-                v1 = (bf16_hi_to_f(gt[j]) > 0.f) ? v1 * p.gate_scale : 0.f;
-            }
-            if (p.resid != nullptr) { v0 += res[j].x; v1 += res[j].y; }
-            if (p.out_f32 != nullptr) {
-                float* o = p.out_f32 + row * p.ldo_f32 + col;
+        for (int h = 0; h < 2; ++h) {
+            if (ok[h]) {
+                float* o = p.out_f32 + rows[h] * p.ldo_f32 + col;
                 if (p.accumulate) {
-                    if (pair) red_add_v2(o, v0, v1);
-                    else atomicAdd(o, v0);
-                } else if (pair) {
-                    *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) red_add_v2(o + 8 * k, v[4 * k + 2 * h], v[4 * k + 2 * h + 1]);
                 } else {
-                    *o = v0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        *reinterpret_cast<float2*>(o + 8 * k) = make_float2(v[4 * k + 2 * h], v[4 * k + 2 * h + 1]);
                 }
             }
-            if (p.out_bf16 != nullptr) {
-                bf16* o = p.out_bf16 + row * p.ldo_bf16 + col;
-                const uint32_t packed = pack_bf16x2(v0, v1);
-                if (pair) *reinterpret_cast<uint32_t*>(o) = packed;
-                else *o = __float2bfloat16_rn(v0);
+        }
+    }
+    if (p.out_bf16 != nullptr) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (ok[h]) {
+                uint32_t* o = reinterpret_cast<uint32_t*>(p.out_bf16 + rows[h] * p.ldo_bf16 + col);
+                uint32_t pk[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    pk[k] = pack_bf16x2(v[4 * k + 2 * h], v[4 * k + 2 * h + 1]);
+                    o[4 * k] = pk[k];
+                }
                 if (p.out_lo != nullptr) {
-                    bf16* ol = p.out_lo + row * p.ldo_bf16 + col;
-                    const float l0 = v0 - bf16_lo_to_f(packed), l1 = v1 - bf16_hi_to_f(packed);
-                    if (pair) *reinterpret_cast<uint32_t*>(ol) = pack_bf16x2(l0, l1);
-                    else *ol = __float2bfloat16_rn(l0);
+                    uint32_t* ol = reinterpret_cast<uint32_t*>(p.out_lo + rows[h] * p.ldo_bf16 + col);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        ol[4 * k] = pack_bf16x2(v[4 * k + 2 * h] - bf16_lo_to_f(pk[k]),
+                                                v[4 * k + 2 * h + 1] - bf16_hi_to_f(pk[k]));
                 }
             }
         }
     }
 }
 
-template <int BLOCK_N, int A_MN, int B_MN>
+template <int BLOCK_N, int A_MN, int B_MN, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
-    using Cfg = GemmCfg<BLOCK_N>;
+    using Cfg = GemmCfg<BLOCK_N, CG>;
     constexpr int kStages = Cfg::kStages;
+    constexpr int kBRows = BLOCK_N / CG;   // rows of the B tile staged by this CTA
 
     // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static shared memory, so the
     // dynamic window starts at the (1024-aligned) base of the CTA's shared memory.
@@ -192,8 +250,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         if (threadIdx.x == 0) printf("mcan gemm: dynamic smem base not 1024-byte aligned\n");
         __trap();
     }
-    float* epi_stage = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full_bar = empty_bar + kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -201,6 +258,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0U;   // position in the CTA pair
+    const bool leader = (rank == 0);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.num_seg; ++s) {
@@ -211,36 +270,42 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < kStages; ++s) {
-                mbar_init(&full_bar[s], 1);
+                mbar_init(&full_bar[s], 1);    // CG==2: only the leader's is used (bytes of both CTAs)
                 mbar_init(&empty_bar[s], 1);
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
-                mbar_init(&tmem_empty_bar[s], kEpilogueWarps);
+                mbar_init(&tmem_empty_bar[s], kEpilogueWarps * CG);   // CG==2: leader's, both CTAs arrive
             }
             fence_mbar_init();
         }
         __syncwarp();
-        tmem_alloc(tmem_slot, Cfg::kTmemCols);
-        tmem_relinquish();
+        if (CG == 2) {
+            tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
+            tmem_relinquish_cg2();
+        } else {
+            tmem_alloc(tmem_slot, Cfg::kTmemCols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int tiles = p.m_tiles * p.n_tiles;
+    const int tiles = p.m_tiles * p.n_tiles;      // m_tiles counts (128*CG)-row tiles
     const int units = tiles * p.splits;
+    const int first_unit = blockIdx.x / CG, unit_stride = gridDim.x / CG;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            for (int unit = first_unit; unit < units; unit += unit_stride) {
                 const int tile = unit % tiles, split = unit / tiles;
-                const int m0 = (tile / p.n_tiles) * BLOCK_M;
-                const int n0 = (tile % p.n_tiles) * BLOCK_N;
+                const int m0 = (tile / p.n_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
+                const int n0 = (tile % p.n_tiles) * BLOCK_N + (int)rank * kBRows;
                 const int kb0 = (int)((long long)p.kblocks * split / p.splits);
                 const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.splits);
                 for (int seg = 0; seg < p.num_seg; ++seg) {
@@ -248,22 +313,25 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::kStageBytes;
                         uint8_t* sb = sa + Cfg::kABytes;
-                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                        if (CG == 1) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                        else if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                        auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+                            if (CG == 2) tma_load_2d_cg2(dst, m, &full_bar[stage], c0, c1);
+                            else tma_load_2d(dst, m, &full_bar[stage], c0, c1);
+                        };
                         if (A_MN) {
 #pragma unroll
                             for (int c = 0; c < BLOCK_M / 64; ++c)
-                                tma_load_2d(sa + c * (BLOCK_K * 128), &p.tma_a[seg],
-                                            &full_bar[stage], m0 + c * 64, kb * BLOCK_K);
+                                load(sa + c * (BLOCK_K * 128), &p.tma_a[seg], m0 + c * 64, kb * BLOCK_K);
                         } else {
-                            tma_load_2d(sa, &p.tma_a[seg], &full_bar[stage], kb * BLOCK_K, m0);
+                            load(sa, &p.tma_a[seg], kb * BLOCK_K, m0);
                         }
                         if (B_MN) {
 #pragma unroll
-                            for (int c = 0; c < BLOCK_N / 64; ++c)
-                                tma_load_2d(sb + c * (BLOCK_K * 128), &p.tma_b[seg],
-                                            &full_bar[stage], n0 + c * 64, kb * BLOCK_K);
+                            for (int c = 0; c < kBRows / 64; ++c)
+                                load(sb + c * (BLOCK_K * 128), &p.tma_b[seg], n0 + c * 64, kb * BLOCK_K);
                         } else {
-                            tma_load_2d(sb, &p.tma_b[seg], &full_bar[stage], kb * BLOCK_K, n0);
+                            load(sb, &p.tma_b[seg], kb * BLOCK_K, n0);
                         }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
@@ -271,9 +339,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN, B_MN);
+        // ===================== MMA issuer (one thread of the leader CTA) =====================
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, BLOCK_N, A_MN, B_MN);
             constexpr uint32_t a_lbo = A_MN ? BLOCK_K * 128 : 0;
             constexpr uint32_t b_lbo = B_MN ? BLOCK_K * 128 : 0;
             constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);
@@ -282,7 +350,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+            for (int unit = first_unit; unit < units; unit += unit_stride) {
                 const int split = unit / tiles;
                 const int kb0 = (int)((long long)p.kblocks * split / p.splits);
                 const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.splits);
@@ -299,69 +367,67 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                     const uint64_t bdesc = make_smem_desc_sw128(sb, b_lbo, 1024);
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        umma_bf16(tmem_d, adesc + (uint64_t)((k * a_kstep) >> 4),
-                                  bdesc + (uint64_t)((k * b_kstep) >> 4), idesc,
-                                  (it > 0 || k > 0) ? 1U : 0U);
+                        const uint64_t ad = adesc + (uint64_t)((k * a_kstep) >> 4);
+                        const uint64_t bd = bdesc + (uint64_t)((k * b_kstep) >> 4);
+                        const uint32_t accum = (it > 0 || k > 0) ? 1U : 0U;
+                        if (CG == 2) umma_bf16_cg2(tmem_d, ad, bd, idesc, accum);
+                        else umma_bf16(tmem_d, ad, bd, idesc, accum);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot when the MMAs retire
+                    // frees the smem slot (in both CTAs) when the MMAs retire
+                    if (CG == 2) umma_commit_cg2(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full_bar[acc]);  // accumulator ready for the epilogue
+                // accumulator ready for the epilogue warps (of both CTAs)
+                if (CG == 2) umma_commit_cg2(&tmem_full_bar[acc], 3); else umma_commit(&tmem_full_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        // ========== epilogue: TMEM -> registers -> smem transpose -> coalesced global ==========
+        // ===================== epilogue: TMEM -> registers -> global =====================
         const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) belong to this warp
         const uint32_t drop_seed =
             p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
-        float* stage = epi_stage + (warp - 2) * (32 * kStageLd);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        for (int unit = first_unit; unit < units; unit += unit_stride) {
             const int tile = unit % tiles;
-            const int m0 = (tile / p.n_tiles) * BLOCK_M;
+            const int m0 = (tile / p.n_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
             const int n0 = (tile % p.n_tiles) * BLOCK_N;
             const long long row0 = m0 + quad * 32;
-            const int rows_valid = (int)max(0LL, min(32LL, (long long)p.m - row0));
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             const int nchunks = min(BLOCK_N / kChunkN, (p.n - n0 + kChunkN - 1) / kChunkN);
 #pragma unroll 1
             for (int c = 0; c < nchunks; ++c) {
-                uint32_t r[32];
-                float4* srow = reinterpret_cast<float4*>(stage + lane * kStageLd);
-#pragma unroll
-                for (int hlf = 0; hlf < 2; ++hlf) {
-                    tmem_ld_32x32(taddr + (uint32_t)(c * kChunkN + hlf * 32), r);
+#pragma unroll 1
+                for (int hb = 0; hb < 2; ++hb) {
+                    uint32_t r[32];
+                    tmem_ld_16x256b_x8(taddr + ((uint32_t)(hb * 16) << 16) + (uint32_t)(c * kChunkN), r);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        srow[hlf * 8 + q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                                        __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    if (c == nchunks - 1 && hb == 1) {
+                        // accumulator stage fully drained: hand it back to the MMA warp now
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 2) mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+                            else mbar_arrive(&tmem_empty_bar[acc]);
+                        }
+                    }
+                    if (row0 + hb * 16 < p.m)
+                        epilogue_frag(p, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed);
                 }
-                if (c == nchunks - 1) {
-                    // the accumulator stage is fully drained: hand it back to the MMA warp now
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-                } else {
-                    __syncwarp();
-                }
-                if (rows_valid > 0)
-                    epilogue_chunk(p, stage, lane, row0, rows_valid, n0 + c * kChunkN, drop_seed);
-                __syncwarp();   // staging tile is reused by the next chunk
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();   // the peer's smem / barriers stay alive until here
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if (CG == 2) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -458,40 +524,65 @@ int device_num_sms() {
     return sms[dev];
 }
 
-template <int BLOCK_N, int A_MN, int B_MN>
+template <int BLOCK_N, int A_MN, int B_MN, int CG>
 static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
-    using Cfg = GemmCfg<BLOCK_N>;
+    using Cfg = GemmCfg<BLOCK_N, CG>;
     static bool configured[64] = {false};
     int dev = 0;
     MCAN_CHECK_CUDA(cudaGetDevice(&dev));
+    auto kernel = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, CG>;
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        MCAN_CHECK_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MCAN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)Cfg::kSmemBytes));
         configured[dev] = true;
     }
-    gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(p);
-    MCAN_CHECK_CUDA(cudaGetLastError());
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(kGemmThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MCAN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
     return 0;
 }
 
-static int pick_block_n(int64_t m_tiles, int64_t n, int sms) {
-    if (n <= 128) return 128;
-    // cost model: waves x tile time; a 128-wide tile is smem-bandwidth bound (~15 % slower per flop)
-    const int64_t t256 = m_tiles * ((n + 255) / 256);
-    const int64_t t128 = m_tiles * ((n + 127) / 128);
-    const double c256 = (double)((t256 + sms - 1) / sms) * 2.0;
-    const double c128 = (double)((t128 + sms - 1) / sms) * 1.15;
-    return (c128 < c256) ? 128 : 256;
+// Tile configuration = (cta_group, BLOCK_N).  Cost model: number of waves over the SMs x the time
+// of one tile; relative tile throughputs measured on B200 (tools/gemm_bench.py): the CTA-pair
+// 256x256 tile has the highest arithmetic intensity, the single-CTA 128x128 tile the lowest.
+struct TileCfg { int cg, bn; };
+
+static TileCfg pick_tile(int64_t m, int64_t n, int sms) {
+    const TileCfg cand[4] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}};
+    const double rate[4] = {1.00, 0.62, 0.85, 0.62};
+    TileCfg best = cand[3];
+    double best_cost = 1e30;
+    for (int i = 0; i < 4; ++i) {
+        const int cg = cand[i].cg, bn = cand[i].bn;
+        if (bn == 256 && n <= 128) continue;
+        if (cg == 2 && m <= 128) continue;
+        const int64_t tiles = ((m + 128 * cg - 1) / (128 * cg)) * ((n + bn - 1) / bn);
+        const int64_t slots = sms / cg;
+        const int64_t waves = (tiles + slots - 1) / slots;
+        const double cost = (double)waves * (128.0 * bn) / rate[i];
+        if (cost < best_cost) { best_cost = cost; best = cand[i]; }
+    }
+    return best;
 }
 
-static int pick_splits(int64_t tiles, int kblocks, int sms) {
+static int pick_splits(int64_t tiles, int kblocks, int slots) {
     int best = 1;
     double best_cost = 1e30;
     const int max_s = kblocks < 32 ? kblocks : 32;
     for (int s = 1; s <= max_s; ++s) {
         const int64_t units = tiles * s;
-        const int64_t waves = (units + sms - 1) / sms;
+        const int64_t waves = (units + slots - 1) / slots;
         const double per_unit = (double)((kblocks + s - 1) / s) + 6.0;  // +epilogue/fill overhead
         const double cost = (double)waves * per_unit;
         if (cost < best_cost * 0.98) {
@@ -542,14 +633,19 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     p.m = (int)a->m;
     p.n = (int)a->n;
     p.k = (int)a->k;
-    p.m_tiles = (int)((a->m + BLOCK_M - 1) / BLOCK_M);
     p.kblocks = (int)((a->k + BLOCK_K - 1) / BLOCK_K);
-    int block_n = a->block_n ? a->block_n : pick_block_n(p.m_tiles, a->n, sms);
+    TileCfg tc = pick_tile(a->m, a->n, sms);
+    if (a->block_n) tc.bn = a->block_n;
+    if (a->cta_group) tc.cg = a->cta_group;
+    const int block_n = tc.bn, cg = tc.cg;
     MCAN_REQUIRE(block_n == 128 || block_n == 256, "mcan_gemm: block_n=%d", block_n);
+    MCAN_REQUIRE(cg == 1 || cg == 2, "mcan_gemm: cta_group=%d", cg);
+    p.m_tiles = (int)((a->m + BLOCK_M * cg - 1) / (BLOCK_M * cg));
     p.n_tiles = (int)((a->n + block_n - 1) / block_n);
+    const int slots = sms / cg;
     int splits = 1;
     if (a->accumulate) {
-        splits = a->split_k > 0 ? a->split_k : pick_splits((int64_t)p.m_tiles * p.n_tiles, p.kblocks, sms);
+        splits = a->split_k > 0 ? a->split_k : pick_splits((int64_t)p.m_tiles * p.n_tiles, p.kblocks, slots);
         if (splits > p.kblocks) splits = p.kblocks;
     }
     p.splits = splits;
@@ -563,7 +659,7 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
             rc = make_tmap(&p.tma_a[s], a->a[s], (uint64_t)a->m, (uint64_t)a->k, (uint64_t)a->lda, 64);
         if (rc) return rc;
         if (a->b_layout == 0)
-            rc = make_tmap(&p.tma_b[s], a->b[s], (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)block_n);
+            rc = make_tmap(&p.tma_b[s], a->b[s], (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)(block_n / cg));
         else
             rc = make_tmap(&p.tma_b[s], a->b[s], (uint64_t)a->n, (uint64_t)a->k, (uint64_t)a->ldb, 64);
         if (rc) return rc;
@@ -588,20 +684,19 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     p.accumulate = a->accumulate;
 
     const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
-    const int grid = (int)(units < sms ? units : sms);
+    const int grid = (int)(units < slots ? units : slots) * cg;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
     const int am = a->a_layout ? 1 : 0, bm = a->b_layout ? 1 : 0;
 
-#define MCAN_GEMM_CASE(BN, AM, BM) \
-    if (block_n == BN && am == AM && bm == BM) return launch_gemm<BN, AM, BM>(p, grid, st);
-    MCAN_GEMM_CASE(128, 0, 0)
-    MCAN_GEMM_CASE(128, 0, 1)
-    MCAN_GEMM_CASE(128, 1, 0)
-    MCAN_GEMM_CASE(128, 1, 1)
-    MCAN_GEMM_CASE(256, 0, 0)
-    MCAN_GEMM_CASE(256, 0, 1)
-    MCAN_GEMM_CASE(256, 1, 0)
-    MCAN_GEMM_CASE(256, 1, 1)
+#define MCAN_GEMM_CASE(BN, AM, BM, CG) \
+    if (block_n == BN && am == AM && bm == BM && cg == CG) return launch_gemm<BN, AM, BM, CG>(p, grid, st);
+#define MCAN_GEMM_CASES(BN, CG) \
+    MCAN_GEMM_CASE(BN, 0, 0, CG) MCAN_GEMM_CASE(BN, 0, 1, CG) MCAN_GEMM_CASE(BN, 1, 0, CG) MCAN_GEMM_CASE(BN, 1, 1, CG)
+    MCAN_GEMM_CASES(128, 1)
+    MCAN_GEMM_CASES(256, 1)
+    MCAN_GEMM_CASES(128, 2)
+    MCAN_GEMM_CASES(256, 2)
+#undef MCAN_GEMM_CASES
 #undef MCAN_GEMM_CASE
     set_last_error("mcan_gemm: no kernel for block_n=%d", block_n);
     return -1;

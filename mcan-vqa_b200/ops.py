@@ -58,7 +58,7 @@ def num_sms():
 
 def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, seed=0, gate=None,
          gate_scale=1.0, resid=None, out_f32=None, out_bf16=None, out_lo=None, accumulate=False,
-         split_k=0, block_n=0):
+         split_k=0, block_n=0, cta_group=0):
     """D[M,N] = epilogue(sum_s A_s B_s^T) on the tcgen05 GEMM (see include/mcan_b200.h).
 
     a / b: bf16 tensors or equal-length lists of them (segments).  a_layout 0: [M,K], 1: [K,M];
@@ -116,6 +116,7 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, 
     args.accumulate = 1 if accumulate else 0
     args.split_k = int(split_k)
     args.block_n = int(block_n)
+    args.cta_group = int(cta_group)
     args.stream = _stream()
     capi.check(lib.mcan_gemm(ctypes.byref(args)), "mcan_gemm")
 

@@ -32,48 +32,54 @@ SHAPES_NT = [
 
 @pytest.mark.parametrize("m,n,k", SHAPES_NT)
 @pytest.mark.parametrize("block_n", [128, 256])
-def test_gemm_nt_plain(m, n, k, block_n):
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_nt_plain(m, n, k, block_n, cta_group):
     ops = _ops()
     a, w = _rand((m, k), 1), _rand((n, k), 2, 0.05)
     out = torch.full((m, n), float("nan"), device="cuda")
-    ops.gemm(a, w, out_f32=out, block_n=block_n)
+    ops.gemm(a, w, out_f32=out, block_n=block_n, cta_group=cta_group)
     torch.cuda.synchronize()
     _close(out, a.float() @ w.float().t(), 2e-5, "NT plain")
 
 
 @pytest.mark.parametrize("m,n,k", [(256, 512, 512), (6400, 512, 2048), (100, 1024, 512)])
-def test_gemm_dgrad_layout(m, n, k):
+@pytest.mark.parametrize("cta_group,block_n", [(1, 0), (2, 128), (2, 256)])
+def test_gemm_dgrad_layout(m, n, k, cta_group, block_n):
     """dX[M,K'] = dY[M,N'] W[N',K']: B is read MN-major straight from the (out,in) weight."""
     ops = _ops()
     dy, w = _rand((m, k), 3), _rand((k, n), 4, 0.05)   # contraction k = N', output n = K'
     out = torch.full((m, n), float("nan"), device="cuda")
-    ops.gemm(dy, w, b_layout=1, out_f32=out)
+    ops.gemm(dy, w, b_layout=1, out_f32=out, cta_group=cta_group, block_n=block_n)
     torch.cuda.synchronize()
     _close(out, dy.float() @ w.float(), 2e-5, "dgrad layout")
 
 
 @pytest.mark.parametrize("rows,n,k", [(256, 512, 512), (6400, 1024, 512), (896, 512, 2048), (100, 256, 128), (1400, 512, 512)])
 @pytest.mark.parametrize("split_k", [0, 1, 3])
-def test_gemm_wgrad_layout_splitk(rows, n, k, split_k):
+@pytest.mark.parametrize("cta_group,block_n", [(1, 0), (2, 128), (2, 256)])
+def test_gemm_wgrad_layout_splitk(rows, n, k, split_k, cta_group, block_n):
     """dW[N',K'] = dY^T X: both operands MN-major, split-K with fp32 atomics into a zeroed buffer."""
     ops = _ops()
     dy, x = _rand((rows, n), 5, 0.1), _rand((rows, k), 6)
     out = torch.zeros((n, k), device="cuda")
-    ops.gemm(dy, x, a_layout=1, b_layout=1, out_f32=out, accumulate=True, split_k=split_k)
+    ops.gemm(dy, x, a_layout=1, b_layout=1, out_f32=out, accumulate=True, split_k=split_k, cta_group=cta_group,
+             block_n=block_n)
     torch.cuda.synchronize()
     _close(out, dy.float().t() @ x.float(), 5e-5, "wgrad")
 
 
-def test_gemm_a_mn_b_k():
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_a_mn_b_k(cta_group):
     ops = _ops()
     at, w = _rand((320, 256), 7), _rand((384, 320), 8, 0.05)   # A stored [K,M], B stored [N,K]
     out = torch.empty((256, 384), device="cuda")
-    ops.gemm(at, w, a_layout=1, b_layout=0, out_f32=out)
+    ops.gemm(at, w, a_layout=1, b_layout=0, out_f32=out, cta_group=cta_group)
     torch.cuda.synchronize()
     _close(out, at.float().t() @ w.float().t(), 2e-5, "A MN-major, B K-major")
 
 
-def test_gemm_epilogue_bias_relu_resid_outputs():
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_gemm_epilogue_bias_relu_resid_outputs(cta_group):
     ops = _ops()
     m, n, k = 384, 512, 256
     a, w = _rand((m, k), 9), _rand((n, k), 10, 0.1)
@@ -82,7 +88,7 @@ def test_gemm_epilogue_bias_relu_resid_outputs():
     o32 = torch.empty(m, n, device="cuda")
     obf = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
     olo = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
-    ops.gemm(a, w, bias=bias, relu=True, resid=resid, out_f32=o32, out_bf16=obf, out_lo=olo)
+    ops.gemm(a, w, bias=bias, relu=True, resid=resid, out_f32=o32, out_bf16=obf, out_lo=olo, cta_group=cta_group)
     torch.cuda.synchronize()
     ref = torch.relu(a.float() @ w.float().t() + bias) + resid
     _close(o32, ref, 2e-5, "bias+relu+resid fp32")

@@ -47,17 +47,17 @@ def main():
     for name, m, n, k, al, bl, acc in shapes:
         a = torch.randn((m, k) if al == 0 else (k, m), device="cuda").to(torch.bfloat16)
         b = (torch.randn((n, k) if bl == 0 else (k, n), device="cuda") * 0.05).to(torch.bfloat16)
-        for bn in (128, 256):
+        for cg, bn in ((1, 128), (1, 256), (2, 128), (2, 256), (0, 0)):
             if acc:
                 out = torch.zeros(m, n, device="cuda")
-                fn = lambda: ops.gemm(a, b, a_layout=al, b_layout=bl, out_f32=out, accumulate=True, block_n=bn)
+                fn = lambda: ops.gemm(a, b, a_layout=al, b_layout=bl, out_f32=out, accumulate=True, block_n=bn, cta_group=cg)
             else:
                 out = torch.empty(m, n, device="cuda", dtype=torch.bfloat16)
-                fn = lambda: ops.gemm(a, b, a_layout=al, b_layout=bl, out_bf16=out, block_n=bn)
+                fn = lambda: ops.gemm(a, b, a_layout=al, b_layout=bl, out_bf16=out, block_n=bn, cta_group=cg)
             t = timeit(fn)
             tf = 2.0 * m * n * k / t / 1e12
-            res.append({"name": name, "block_n": bn, "us": t * 1e6, "tflops": tf})
-            print("%-20s BN=%3d  %8.1f us  %7.1f TFLOP/s" % (name, bn, t * 1e6, tf), flush=True)
+            res.append({"name": name, "cta_group": cg, "block_n": bn, "us": t * 1e6, "tflops": tf})
+            print("%-20s CG=%d BN=%3d  %8.1f us  %7.1f TFLOP/s" % (name, cg, bn, t * 1e6, tf), flush=True)
         A = a if al == 0 else a.t()
         B = b.t() if bl == 0 else b
         t = timeit(lambda: torch.matmul(A, B))
