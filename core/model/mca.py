@@ -43,6 +43,9 @@ class MHAtt(nn.Module):
             self._lp_merge = LinearParams([(self.linear_merge.weight, self.linear_merge.bias)])
         return self._lp_merge
 
+    def all_lps(self):
+        return [self.lp_qkv(), self.lp_merge()]
+
     def forward(self, v, k, q, mask):
         return _ag.mhatt(self, v, k, q, mask)
 
@@ -75,6 +78,9 @@ class SA(nn.Module):
         self.dropout2 = nn.Dropout(self.dropout_rate)
         self.norm2 = LayerNorm(self.hidden_size)
 
+    def all_lps(self):
+        return self.mhatt.all_lps() + self.ffn.mlp.all_lps()
+
     def forward(self, x, x_mask):
         return _ag.sa(self, x, x_mask)
 
@@ -95,6 +101,9 @@ class SGA(nn.Module):
         self.norm2 = LayerNorm(self.hidden_size)
         self.dropout3 = nn.Dropout(self.dropout_rate)
         self.norm3 = LayerNorm(self.hidden_size)
+
+    def all_lps(self):
+        return self.mhatt1.all_lps() + self.mhatt2.all_lps() + self.ffn.mlp.all_lps()
 
     def forward(self, x, y, x_mask, y_mask):
         return _ag.sga(self, x, y, x_mask, y_mask)
@@ -123,6 +132,12 @@ class MCA_ED(nn.Module):
             self._lp_kv_all = LinearParams(pairs)
         return self._lp_kv_all
 
+    def all_lps(self):
+        out = [self.lp_kv_all()] if len(self.dec_list) else []
+        for layer in list(self.enc_list) + list(self.dec_list):
+            out += layer.all_lps()
+        return out
+
     def forward(self, x, y, x_mask, y_mask):
         return _ag.mca_ed(self, x, y, x_mask, y_mask)
 
@@ -135,6 +150,12 @@ class MCAClassifier(nn.Module):
         self.hidden_size = cfg_get(opt, "hidden_size")
         self.dropout_rate = cfg_get(opt, "dropout_rate")
         self.enc_list = nn.ModuleList([SA(opt) for _ in range(cfg_get(opt, "layer"))])
+
+    def all_lps(self):
+        out = []
+        for layer in self.enc_list:
+            out += layer.all_lps()
+        return out
 
     def forward(self, y, y_mask):
         return _ag.sa_stack(self, y, y_mask)

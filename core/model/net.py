@@ -15,7 +15,7 @@ from core.model.mca import MCA_ED, MCAClassifier
 from core.model.net_utils import FC, MLP, LayerNorm, TCLinear  # noqa: F401
 from mcan_vqa_b200 import autograd as _ag
 from mcan_vqa_b200.autograd import cfg_get
-from mcan_vqa_b200.blocks import LinearParams
+from mcan_vqa_b200.blocks import LinearParams, refresh_scope
 
 
 class AttFlat(nn.Module):
@@ -38,6 +38,9 @@ class AttFlat(nn.Module):
         if self._lp_merge is None:
             self._lp_merge = LinearParams([(self.linear_merge.weight, self.linear_merge.bias)])
         return self._lp_merge
+
+    def all_lps(self):
+        return [self.mlp.lp_fc(), self.lp_merge()]
 
     def forward(self, x, x_mask):
         return _ag.attflat(self, x, x_mask)
@@ -65,7 +68,15 @@ class _VQABase(nn.Module):
         self.proj_norm = LayerNorm(cfg_get(opt, "flat_out_size"))
         self.proj = TCLinear(cfg_get(opt, "flat_out_size"), answer_size)
 
+    def all_lps(self):
+        return (self.backbone.all_lps() + self.attflat_img.all_lps() + self.attflat_lang.all_lps() +
+                [self.img_feat_linear.lp(), self.proj.lp()])
+
     def _features(self, v, ques_ix):
+        with refresh_scope(self.all_lps(), self.training or torch.is_grad_enabled()):
+            return self._features_impl(v, ques_ix)
+
+    def _features_impl(self, v, ques_ix):
         q_mask = _make_mask(ques_ix.unsqueeze(2))
         v_mask = _make_mask(v)
         q, _ = self.lstm(self.embedding(ques_ix))
@@ -74,7 +85,7 @@ class _VQABase(nn.Module):
         lang, q_w = self.attflat_lang(q, q_mask)
         img, v_w = self.attflat_img(v, v_mask)
         a = self.proj_norm(lang + img)
-        return q, v, q_mask, v_mask, q_w, v_w, a
+        return q, v, q_mask, v_mask, q_w, v_w, a, self.proj(a)
 
     def make_mask(self, feature):
         return _make_mask(feature)
@@ -88,8 +99,8 @@ class Net(_VQABase):
         self._build(opt, pretrained_emb, token_size, answer_size, {})
 
     def forward(self, v, ques_ix):
-        q, v, q_mask, v_mask, q_w, v_w, a = self._features(v, ques_ix)
-        probs = torch.sigmoid(self.proj(a))
+        q, v, q_mask, v_mask, q_w, v_w, a, logits = self._features(v, ques_ix)
+        probs = torch.sigmoid(logits)
         return probs, v, v_mask, v_w, q, q_mask, q_w, a
 
 
@@ -104,8 +115,8 @@ class Net2(_VQABase):
             self._build(opt, pretrained_emb, token_size, answer_size, {"dropout": cfg_get(opt, "dropout_rate")})
 
     def forward(self, v, ques_ix):
-        q, v, q_mask, v_mask, _, _, a = self._features(v, ques_ix)
-        probs = torch.sigmoid(self.proj(a))
+        q, v, q_mask, v_mask, _, _, a, logits = self._features(v, ques_ix)
+        probs = torch.sigmoid(logits)
         return probs, v, v_mask, q, q_mask
 
 

@@ -69,6 +69,9 @@ class MLP(nn.Module):
             self._lp_out = LinearParams([(self.linear.weight, self.linear.bias)])
         return self._lp_out
 
+    def all_lps(self):
+        return [self.lp_fc(), self.lp_out()]
+
     def forward(self, x):
         return _ag.mlp(self, x)
 

@@ -339,7 +339,7 @@ class _LinearRunner(_Runner):
         (x,) = acts
         lin = self.module
         self.shape = x.shape
-        lp = lin.lp().get(blocks.ALWAYS_RECAST and torch.is_grad_enabled())
+        lp = lin.lp().get(blocks._force(torch.is_grad_enabled()))
         out, self.c = blocks.linear_fwd(lp, _as_f32_2d(x, lp.k))
         return out.contiguous().view(self.shape[:-1] + (lp.n,)) if out.stride(0) != lp.n else out.view(self.shape[:-1] + (lp.n,))
 

@@ -58,7 +58,35 @@ class Runtime(object):
         _seed_counter[0] += 1
         self.base = _mix32((torch.initial_seed() & 0xFFFFFFFF) ^ (_seed_counter[0] * 0x9E3779B9))
         self.n = 0
-        self.bufs = []      # flat fp32 gradient buffers produced since the last drain (for dp.py)
+        self.bufs = []      # loose fp32 gradient buffers produced since the last drain (for dp.py)
+        self.arena = None   # one zero-initialised flat buffer all gradients of a backward are carved from
+        self.arena_off = 0
+        self.arena_mark = 0
+
+    def use_arena(self, numel, device):
+        """One memset instead of one per gradient tensor; contiguous per-layer slices for dp.py."""
+        self.arena = torch.zeros(numel, dtype=_F32, device=device)
+        self.arena_off = 0
+        self.arena_mark = 0
+
+    def zeros(self, n, device):
+        n4 = (n + 3) // 4 * 4          # keep every carve-out 16-byte aligned
+        if self.arena is not None and self.arena.device == device and self.arena_off + n4 <= self.arena.numel():
+            v = self.arena[self.arena_off:self.arena_off + n]
+            self.arena_off += n4
+            return v
+        t = torch.zeros(n, dtype=_F32, device=device)
+        self.bufs.append(t)
+        return t
+
+    def drain(self):
+        """Gradient storage produced since the previous drain, as a list of flat tensors."""
+        out = list(self.bufs)
+        self.bufs = []
+        if self.arena is not None and self.arena_off > self.arena_mark:
+            out.append(self.arena[self.arena_mark:self.arena_off])
+            self.arena_mark = self.arena_off
+        return out
 
     def seed(self):
         self.n += 1
@@ -115,25 +143,36 @@ class LinearParams(object):
     def _current_stamp(self):
         return tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in self.pairs)
 
-    def get(self, force=False):
-        stamp = self._current_stamp()
+    def _ensure_storage(self):
         dev = self.pairs[0][0].device
         if self.w is None or self.w.device != dev:
             ld = (self.k + 7) // 8 * 8
             self.w = torch.zeros((self.n, ld), dtype=_BF16, device=dev)[:, :self.k]
-            self.b = torch.empty((self.n,), dtype=_F32, device=dev)
+            self.b = torch.empty((self.n,), dtype=_F32, device=dev) if len(self.pairs) > 1 else None
             self._stamp = None
-        if force or stamp != self._stamp:
-            r = 0
-            for (w, b), n in zip(self.pairs, self.sizes):
-                wd = w.detach()
-                if self.w.stride(0) == self.k:
-                    ops.cast_bf16(wd if wd.is_contiguous() else wd.contiguous(), self.w[r:r + n])
-                else:   # padded leading dimension (k % 8 != 0): plumbing copy, not on the hot path
-                    self.w[r:r + n].copy_(wd)
-                self.b[r:r + n].copy_(b.detach())
-                r += n
-            self._stamp = stamp
+
+    def pending(self, force=False):
+        """(dst, src) copy pairs needed to bring the bf16 operand copy up to date ([] if current)."""
+        self._ensure_storage()
+        stamp = self._current_stamp()
+        if not force and stamp == self._stamp:
+            return []
+        out = []
+        r = 0
+        for (w, b), n in zip(self.pairs, self.sizes):
+            out.append((self.w[r:r + n], w.detach()))
+            if len(self.pairs) > 1:
+                out.append((self.b[r:r + n], b.detach()))
+            r += n
+        if len(self.pairs) == 1:
+            self.b = self.pairs[0][1].detach()      # single layer: use the fp32 master bias in place
+        self._stamp = stamp
+        return out
+
+    def get(self, force=False):
+        todo = self.pending(force)
+        if todo:
+            torch._foreach_copy_([d for d, _ in todo], [s_ for _, s_ in todo])
         return self
 
     def rows(self, i0, i1):
@@ -152,10 +191,9 @@ class GradBuf(object):
         self.lp, self.i0, self.i1 = lp, i0, i1
         self.sizes = lp.sizes[i0:i1]
         n = sum(self.sizes)
-        self.flat = torch.zeros(n * lp.k + n, dtype=_F32, device=lp.w.device)
+        self.flat = rt.zeros(n * lp.k + n, lp.w.device)
         self.w = self.flat[: n * lp.k].view(n, lp.k)
         self.b = self.flat[n * lp.k:]
-        rt.bufs.append(self.flat)
 
     def _range(self, j0, j1):
         r0 = sum(self.lp.sizes[self.i0:j0])
@@ -183,8 +221,38 @@ class Bag(object):
     pass
 
 
+_refresh_scope = [0]     # > 0 while an enclosing module already refreshed every operand copy
+
+
 def _force(rt_training):
-    return ALWAYS_RECAST and rt_training
+    return ALWAYS_RECAST and rt_training and _refresh_scope[0] == 0
+
+
+def refresh_params(lps, force=False):
+    """Brings the bf16 operand copies of many layers up to date with ONE multi-tensor copy
+    (fp32 -> bf16 cast of the weights, concatenation of stacked biases)."""
+    dst, src = [], []
+    for lp in lps:
+        for d, s_ in lp.pending(force):
+            dst.append(d)
+            src.append(s_)
+    if dst:
+        torch._foreach_copy_(dst, src)
+
+
+class refresh_scope(object):
+    """with refresh_scope(lps, training): all operand copies are refreshed once, up front."""
+
+    def __init__(self, lps, training):
+        self.lps, self.training = lps, training
+
+    def __enter__(self):
+        if _refresh_scope[0] == 0:
+            refresh_params(self.lps, ALWAYS_RECAST and self.training)
+        _refresh_scope[0] += 1
+
+    def __exit__(self, *exc):
+        _refresh_scope[0] -= 1
 
 
 # ------------------------------------------------------------------------------------------
@@ -209,8 +277,7 @@ def ln_bwd(rt, norm, dy, s_f32, mean, sigma, p=0.0, seed=0, want_bf=True, dbias=
     dev = s_f32.device
     dx = _empty(rows, h, _F32, dev)
     dxbf = _empty(rows, h, _BF16, dev) if want_bf else None
-    dab = torch.zeros(2 * h, dtype=_F32, device=dev)
-    rt.bufs.append(dab)
+    dab = rt.zeros(2 * h, dev)
     ops.layernorm_bwd(dy, s_f32, mean, sigma, norm.a_2.detach(), norm.eps, dx_f32=dx, dx_bf16=dxbf,
                       dropout_p=p, seed=seed, da2=dab[:h], db2=dab[h:], dbias=dbias)
     return dx, dxbf, dab[:h], dab[h:]
@@ -477,6 +544,11 @@ def mca_ed_fwd(rt, m, x32, y32, B, Sx, Sy, x_mask, y_mask):
     H = m.hidden_size
     L = len(m.dec_list)
     dev = x32.device
+    with refresh_scope(m.all_lps(), rt.p > 0 or torch.is_grad_enabled()):
+        return _mca_ed_fwd(rt, m, x32, y32, B, Sx, Sy, x_mask, y_mask, H, L, dev)
+
+
+def _mca_ed_fwd(rt, m, x32, y32, B, Sx, Sy, x_mask, y_mask, H, L, dev):
     x = act_from_f32(x32)
     y = act_from_f32(y32)
     enc_ctx = []
@@ -507,6 +579,7 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
     B, Sx, Sy = ctx.B, ctx.Sx, ctx.Sy
     dev = dy_out.device
     grads = {}
+    rt.use_arena(sum(p.numel() for p in m.parameters()) + 8 * len(list(m.parameters())) + 64, dev)
     dkv_all = _empty(B * Sx, 2 * H * L, _BF16, dev)
     dy = dy_out
     for i in range(L - 1, -1, -1):
@@ -515,8 +588,7 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
         dy, _, g = sga_bwd(rt, dec, ctx.dec[i], dy, dkv=dkv)
         grads.update(g)
         if after_layer is not None:
-            after_layer(rt.bufs)
-            rt.bufs = []
+            after_layer(rt.drain())
     dx = dx_out
     if L > 0:
         gkv = GradBuf(rt, ctx.lpkv)
@@ -530,14 +602,12 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
             gk[w], gk[b] = gw, gb
         grads.update(gk)
         if after_layer is not None:
-            after_layer(rt.bufs)
-            rt.bufs = []
+            after_layer(rt.drain())
     for i in range(len(m.enc_list) - 1, -1, -1):
         dx, g = sa_bwd(rt, m.enc_list[i], ctx.enc[i], dx)
         grads.update(g)
         if after_layer is not None:
-            after_layer(rt.bufs)
-            rt.bufs = []
+            after_layer(rt.drain())
     return dx, dy, grads
 
 
@@ -585,8 +655,7 @@ def attflat_bwd(rt, af, c, dout, need_dx=True):
     ops.gemm(dout_bf, c.lpm.w, b_layout=1, out_f32=dpooled)
     dx = _empty(B * S, H, _F32, dev)
     dh = _empty(B * S, M, _BF16, dev)
-    gw2 = torch.zeros(G * M + G, dtype=_F32, device=dev)
-    rt.bufs.append(gw2)
+    gw2 = rt.zeros(G * M + G, dev)
     ops.attflat_pool_bwd(dpooled, c.hmid, af.mlp.linear.weight.detach(), c.mask, c.x.f32, c.att_w, batch=B,
                          s=S, h=H, mlp=M, glimpses=G, gate_scale=1.0 / (1.0 - c.p_mid) if c.p_mid > 0 else 1.0,
                          dx=dx, dhmid=dh, dw2=gw2[: G * M], db2=gw2[G * M:])

@@ -7,8 +7,8 @@
 // from the (out,in) weight) and wgrad (both operands read MN-major straight from the
 // activations, split-K with fp32 atomics).  No transposed copies are ever made.
 //
-// CTA = 192 threads:  warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = epilogue (one TMEM lane quarter each).  Pipelines: smem ring full/empty
+// CTA = 320 threads:  warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..9 = epilogue (two warps per TMEM lane quarter, alternating 64-column chunks).  Pipelines: smem ring full/empty
 // (TMA <-> MMA) and a double-buffered TMEM accumulator full/empty (MMA <-> epilogue), so the
 // epilogue of tile i overlaps the main loop of tile i+1.  Grid = min(#work units, #SMs);
 // work unit = (output tile, K split), statically strided over the CTAs.
@@ -29,8 +29,8 @@ namespace mcan {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 192;
-constexpr int kEpilogueWarps = 4;
+constexpr int kEpilogueWarps = 8;   // two warps per TMEM lane quarter, alternating 64-column chunks
+constexpr int kGemmThreads = 64 + 32 * kEpilogueWarps;
 
 struct alignas(64) GemmParams {
     CUtensorMap tma_a[MCAN_MAX_GEMM_SEGMENTS];
@@ -384,7 +384,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         }
     } else {
         // ===================== epilogue: TMEM -> registers -> global =====================
-        const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) belong to this warp
+        const int quad = warp & 3;            // TMEM lanes [32*quad, 32*quad+32) belong to this warp
+        const int chunk_par = (warp - 2) >> 2;  // which of the two warps of this quarter: even / odd chunks
         const uint32_t drop_seed =
             p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
         int acc = 0;
@@ -398,14 +399,23 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             const int nchunks = min(BLOCK_N / kChunkN, (p.n - n0 + kChunkN - 1) / kChunkN);
+            const int last_c = ((nchunks - 1 - chunk_par) & ~1) + chunk_par;   // this warp's last chunk (< 0: none)
+            if (last_c < 0) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_remote(&tmem_empty_bar[acc], 0);
+                    else mbar_arrive(&tmem_empty_bar[acc]);
+                }
+            }
 #pragma unroll 1
-            for (int c = 0; c < nchunks; ++c) {
+            for (int c = chunk_par; c < nchunks; c += 2) {
 #pragma unroll 1
                 for (int hb = 0; hb < 2; ++hb) {
                     uint32_t r[32];
                     tmem_ld_16x256b_x8(taddr + ((uint32_t)(hb * 16) << 16) + (uint32_t)(c * kChunkN), r);
                     tmem_ld_wait();
-                    if (c == nchunks - 1 && hb == 1) {
+                    if (c == last_c && hb == 1) {
                         // accumulator stage fully drained: hand it back to the MMA warp now
                         tc_fence_before();
                         __syncwarp();
