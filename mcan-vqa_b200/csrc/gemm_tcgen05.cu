@@ -18,6 +18,7 @@
 //   MN-major tile [64 k x rows]  : rows/64 boxes {64 mn, 64 k} of 8 KiB; UMMA desc
 //                                  LBO = 8 KiB (next 64 mn), SBO = 1024 B (next 8 k), k-step = +2 KiB
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <unordered_map>
 
@@ -56,6 +57,7 @@ struct alignas(64) GemmParams {
     bf16* out_lo;
     long long ldo_bf16;
     int accumulate;
+    int debug;   // bit0: skip all global stores (profiling experiments only)
 };
 
 // CG = CTAs per MMA (cta_group): 1 = one SM per 128 x BLOCK_N tile, 2 = a CTA pair computes a
@@ -124,16 +126,54 @@ __device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const flo
     }
 }
 
-__device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_t (&r)[32], int lane,
-                                              long long row0, int col0, uint32_t drop_seed) {
+// Residual / gate operands of one fragment, fetched from global memory one fragment AHEAD of
+// their use so that the ~1 us load latency overlaps the previous fragment's work (and, for the
+// first fragment of a tile, the wait for the accumulator).
+struct EpiPrefetch {
+    float2 res[16];    // [8*h + k]
+    uint32_t gt[16];
+};
+
+__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPrefetch& pf, int lane,
+                                                  long long row0, int col0) {
+    if (col0 + kChunkN > p.n || (p.n & 1)) return;   // ragged chunks use the slow path
     const int g = lane >> 2, t = lane & 3;
+    const int col = col0 + 2 * t;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const long long row = row0 + g + 8 * h;
+        if (row < p.m) {
+            if (p.resid != nullptr) {
+                const float2* rp = reinterpret_cast<const float2*>(p.resid + row * p.ldr + col);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pf.res[8 * h + k] = rp[4 * k];
+            }
+            if (p.gate != nullptr) {
+                const uint32_t* gp = reinterpret_cast<const uint32_t*>(p.gate + row * p.ldg + col);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pf.gt[8 * h + k] = __ldg(gp + 4 * k);
+            }
+        }
+    }
+}
+
+template <bool PF>
+__device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_t (&r)[32], int lane,
+                                              long long row0, int col0, uint32_t drop_seed,
+                                              const EpiPrefetch& pf) {
+    const int g = lane >> 2, t = lane & 3;
+    if (col0 + kChunkN > p.n || (p.n & 1)) {
+        // only this copy has its address taken; v[] below must stay in registers (an escaping v[]
+        // made the compiler mirror it to local memory after every pass: +15 us per epilogue stage)
+        float tmp[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tmp[i] = __uint_as_float(r[i]);
+        epilogue_frag_ragged(p, tmp, lane, row0, col0, drop_seed);
+        return;
+    }
     float v[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-    if (col0 + kChunkN > p.n || (p.n & 1)) {
-        epilogue_frag_ragged(p, v, lane, row0, col0, drop_seed);
-        return;
-    }
     const int col = col0 + 2 * t;   // + 8k
     const long long rows[2] = {row0 + g, row0 + g + 8};
     const bool ok[2] = {rows[0] < p.m, rows[1] < p.m};
@@ -163,38 +203,38 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_
             }
         }
     }
-    if (p.gate != nullptr) {
+    if (PF && p.gate != nullptr) {
         const float gs = p.gate_scale;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (ok[h]) {
-                const uint32_t* gp = reinterpret_cast<const uint32_t*>(p.gate + rows[h] * p.ldg + col);
-                uint32_t gt[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) gt[k] = __ldg(gp + 4 * k);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    v[4 * k + 2 * h] = (bf16_lo_to_f(gt[k]) > 0.f) ? v[4 * k + 2 * h] * gs : 0.f;
-                    v[4 * k + 2 * h + 1] = (bf16_hi_to_f(gt[k]) > 0.f) ? v[4 * k + 2 * h + 1] * gs : 0.f;
+                    const uint32_t gt = pf.gt[8 * h + k];
+                    v[4 * k + 2 * h] = (bf16_lo_to_f(gt) > 0.f) ? v[4 * k + 2 * h] * gs : 0.f;
+                    v[4 * k + 2 * h + 1] = (bf16_hi_to_f(gt) > 0.f) ? v[4 * k + 2 * h + 1] * gs : 0.f;
                 }
             }
         }
     }
-    if (p.resid != nullptr) {
+    if (PF && p.resid != nullptr) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (ok[h]) {
-                const float2* rp = reinterpret_cast<const float2*>(p.resid + rows[h] * p.ldr + col);
-                float2 res[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) res[k] = rp[4 * k];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
-                    v[4 * k + 2 * h] += res[k].x;
-                    v[4 * k + 2 * h + 1] += res[k].y;
+                    v[4 * k + 2 * h] += pf.res[8 * h + k].x;
+                    v[4 * k + 2 * h + 1] += pf.res[8 * h + k].y;
                 }
             }
         }
+    }
+    if (p.debug & 1) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += v[i];
+        if (acc == 123.456f) p.out_f32[0] = acc;
+        return;
     }
     if (p.out_f32 != nullptr) {
 #pragma unroll
@@ -231,6 +271,58 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_
                                                 v[4 * k + 2 * h + 1] - bf16_hi_to_f(pk[k]));
                 }
             }
+        }
+    }
+}
+
+// Epilogue of one 128-row output tile for one of the 8 epilogue warps.  PF = the residual / gate
+// operands are prefetched one fragment ahead (separate instantiation so that plain epilogues do
+// not carry the prefetch registers).
+template <int BLOCK_N, int CG, bool PF>
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int chunk_par,
+                                              long long row0, int n0, uint32_t taddr,
+                                              uint64_t* full_bar, uint64_t* empty_bar,
+                                              uint32_t acc_phase, uint32_t drop_seed) {
+    const int nchunks = min(BLOCK_N / kChunkN, (p.n - n0 + kChunkN - 1) / kChunkN);
+    const int last_c = ((nchunks - 1 - chunk_par) & ~1) + chunk_par;   // this warp's last chunk (< 0: none)
+    EpiPrefetch pf_next;
+    if (PF && last_c >= 0)   // operands of the first fragment, before waiting for the MMAs
+        epilogue_prefetch(p, pf_next, lane, row0, n0 + chunk_par * kChunkN);
+    mbar_wait(full_bar, acc_phase);
+    tc_fence_after();
+    if (last_c < 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            if (CG == 2) mbar_arrive_remote(empty_bar, 0);
+            else mbar_arrive(empty_bar);
+        }
+    }
+#pragma unroll 1
+    for (int c = chunk_par; c < nchunks; c += 2) {
+#pragma unroll 1
+        for (int hb = 0; hb < 2; ++hb) {
+            uint32_t r[32];
+            tmem_ld_16x256b_x8(taddr + ((uint32_t)(hb * 16) << 16) + (uint32_t)(c * kChunkN), r);
+            EpiPrefetch pf;
+            if (PF) {
+                pf = pf_next;
+                const int nc = hb ? c + 2 : c, nhb = hb ^ 1;    // next fragment of this tile
+                if (nc < nchunks && row0 + nhb * 16 < p.m)
+                    epilogue_prefetch(p, pf_next, lane, row0 + nhb * 16, n0 + nc * kChunkN);
+            }
+            tmem_ld_wait();
+            if (c == last_c && hb == 1) {
+                // accumulator stage fully drained: hand it back to the MMA warp now
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 2) mbar_arrive_remote(empty_bar, 0);
+                    else mbar_arrive(empty_bar);
+                }
+            }
+            if (row0 + hb * 16 < p.m)
+                epilogue_frag<PF>(p, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed, pf);
         }
     }
 }
@@ -395,39 +487,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             const int m0 = (tile / p.n_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
             const int n0 = (tile % p.n_tiles) * BLOCK_N;
             const long long row0 = m0 + quad * 32;
-            mbar_wait(&tmem_full_bar[acc], acc_phase);
-            tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            const int nchunks = min(BLOCK_N / kChunkN, (p.n - n0 + kChunkN - 1) / kChunkN);
-            const int last_c = ((nchunks - 1 - chunk_par) & ~1) + chunk_par;   // this warp's last chunk (< 0: none)
-            if (last_c < 0) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 2) mbar_arrive_remote(&tmem_empty_bar[acc], 0);
-                    else mbar_arrive(&tmem_empty_bar[acc]);
-                }
-            }
-#pragma unroll 1
-            for (int c = chunk_par; c < nchunks; c += 2) {
-#pragma unroll 1
-                for (int hb = 0; hb < 2; ++hb) {
-                    uint32_t r[32];
-                    tmem_ld_16x256b_x8(taddr + ((uint32_t)(hb * 16) << 16) + (uint32_t)(c * kChunkN), r);
-                    tmem_ld_wait();
-                    if (c == last_c && hb == 1) {
-                        // accumulator stage fully drained: hand it back to the MMA warp now
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) {
-                            if (CG == 2) mbar_arrive_remote(&tmem_empty_bar[acc], 0);
-                            else mbar_arrive(&tmem_empty_bar[acc]);
-                        }
-                    }
-                    if (row0 + hb * 16 < p.m)
-                        epilogue_frag(p, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed);
-                }
-            }
+            if (p.resid != nullptr || p.gate != nullptr)
+                epilogue_tile<BLOCK_N, CG, true>(p, lane, chunk_par, row0, n0, taddr, &tmem_full_bar[acc],
+                                                 &tmem_empty_bar[acc], acc_phase, drop_seed);
+            else
+                epilogue_tile<BLOCK_N, CG, false>(p, lane, chunk_par, row0, n0, taddr, &tmem_full_bar[acc],
+                                                  &tmem_empty_bar[acc], acc_phase, drop_seed);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -692,6 +758,7 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     p.out_lo = reinterpret_cast<bf16*>(a->out_bf16_lo);
     p.ldo_bf16 = a->ldo_bf16;
     p.accumulate = a->accumulate;
+    { const char* d = getenv("MCAN_GEMM_DEBUG"); p.debug = d ? atoi(d) : 0; }
 
     const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
     const int grid = (int)(units < slots ? units : slots) * cg;
