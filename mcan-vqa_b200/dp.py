@@ -26,6 +26,17 @@ def world_size(group=None):
     return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
 
 
+def _all_reduce_sum_async(tensors, group=None):
+    """Async all-reduce(SUM) of a list of tensors; one coalesced NCCL launch on GPUs, one call per
+    tensor on backends without coalescing (gloo, used by the CPU tests).  Returns waitable handles."""
+    if dist.get_backend(group) == "nccl":
+        with dist._coalescing_manager(group, device=tensors[0].device, async_ops=True) as cm:
+            for t in tensors:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return [cm]
+    return [dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=True) for t in tensors]
+
+
 class GradSync(object):
     def __init__(self, model, group=None, overlap=True, backbone_prefix="backbone."):
         self.group = group
@@ -60,10 +71,7 @@ class GradSync(object):
     def _launch(self, tensors):
         if self.world == 1 or not tensors:
             return
-        with dist._coalescing_manager(self.group, device=tensors[0].device, async_ops=True) as cm:
-            for t in tensors:
-                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-        self.pending.append(cm)
+        self.pending.extend(_all_reduce_sum_async(tensors, self.group))
         self.launches += 1
 
     def _ensure_final_callback(self):
@@ -128,8 +136,6 @@ def sync_all_grads(params, group=None):
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return 0
-    with dist._coalescing_manager(group, device=grads[0].device, async_ops=True) as cm:
-        for g in grads:
-            dist.all_reduce(g, op=dist.ReduceOp.SUM, group=group)
-    cm.wait()
+    for w in _all_reduce_sum_async(grads, group):
+        w.wait()
     return len(grads)

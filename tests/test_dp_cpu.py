@@ -1,0 +1,98 @@
+"""Data-parallel gradient exchange (mcan-vqa_b200/dp.py) on 2 gloo ranks, CPU only.
+
+Checks the reference's DataParallel semantics we replace (core/exec.py:62-67): per-rank
+sum-reduced losses + all-reduce(SUM) == single-process gradient of the global batch, for both the
+overlapped mode (layer buffers + post-accumulate hooks + end-of-backward wait) and the at-step
+mode used by the overlay WarmupOptimizer."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+class _LayerFn(torch.autograd.Function):
+    """Stand-in for MCA_ED's backward: produces parameter grads in flat buffers and hands them to dp."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2):
+        ctx.save_for_backward(x, w1, w2)
+        return (x * w1).sum(1, keepdim=True) * w2
+
+    @staticmethod
+    def backward(ctx, g):
+        from mcan_vqa_b200 import dp
+        x, w1, w2 = ctx.saved_tensors
+        s = (x * w1).sum(1, keepdim=True)
+        flat = torch.zeros(w1.numel() + w2.numel())
+        g1 = flat[: w1.numel()].view_as(w1)
+        g2 = flat[w1.numel():].view_as(w2)
+        g1.copy_(((g * w2) * x).sum(0))
+        g2.copy_((g * s).sum(0))
+        hook = dp.layer_hook()
+        if hook is not None:
+            hook([flat])
+        return (g * w2) * w1, g1, g2
+
+
+class _Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(3)
+        self.pre = torch.nn.Linear(6, 5)
+        self.backbone = torch.nn.Module()
+        self.backbone.w1 = torch.nn.Parameter(torch.randn(5, generator=g))
+        self.backbone.w2 = torch.nn.Parameter(torch.randn(1, generator=g))
+        self.post = torch.nn.Linear(1, 3)
+
+    def forward(self, x):
+        h = _LayerFn.apply(self.pre(x), self.backbone.w1, self.backbone.w2)
+        return torch.sigmoid(self.post(h))
+
+
+def _worker(rank, world, port, mode, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from mcan_vqa_b200 import dp
+    torch.manual_seed(0)
+    model = _Toy()
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(8, 6, generator=g)
+    y = torch.rand(8, 3, generator=g)
+    xs, ys = x[rank * 4:(rank + 1) * 4], y[rank * 4:(rank + 1) * 4]
+    loss_fn = torch.nn.BCELoss(reduction="sum")
+    if mode == "overlap":
+        sync = dp.attach(model, overlap=True)
+        loss_fn(model(xs), ys).backward()
+        assert sync.launches >= 2      # layer buffers + hooked parameters went out separately
+    else:
+        dp.attach(model, overlap=False)
+        sys.path.insert(0, ROOT)
+        from core.model.optim import WarmupOptimizer
+        opt = WarmupOptimizer(0.0, torch.optim.SGD(model.parameters(), lr=0.0), 64, 8)
+        loss_fn(model(xs), ys).backward()
+        opt.step()                     # all-reduces inside step()
+    grads = {n: p.grad.clone() for n, p in model.named_parameters()}
+    dp.detach()                        # the single-process reference below must not all-reduce
+    if rank == 0:
+        ref = _Toy()
+        ref.load_state_dict(model.state_dict())
+        loss_fn(ref(x), y).backward()
+        for n, p in ref.named_parameters():
+            assert torch.allclose(grads[n], p.grad, rtol=1e-5, atol=1e-6), n
+        open(out, "w").write("ok")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["overlap", "at_step"])
+def test_two_rank_sum_allreduce_equals_global_batch_gradient(mode, tmp_path):
+    out = str(tmp_path / "ok.txt")
+    port = 29500 + (os.getpid() % 2000) + (0 if mode == "overlap" else 1)
+    mp.spawn(_worker, args=(2, port, mode, out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
