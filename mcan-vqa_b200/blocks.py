@@ -32,9 +32,12 @@ from . import ops
 _BF16 = torch.bfloat16
 _F32 = torch.float32
 
-# When True the bf16 operand copies of the weights are re-cast on every training forward
-# (needed under CUDA-graph replay, where Python cannot observe optimizer updates).
-ALWAYS_RECAST = False
+# The bf16 operand copies of the weights are re-cast on EVERY training forward (grad enabled):
+# optimizer updates cannot be observed reliably from here (fused multi-tensor optimizers do not
+# bump tensor version counters, and under CUDA-graph replay no Python runs at all).  Forwards
+# without grad re-cast only when a master changed (version / storage) or a training forward
+# happened since the last refresh.  Cost: one multi-tensor cast per step (refresh_params).
+ALWAYS_RECAST = True
 
 
 def _mix32(x):
@@ -139,6 +142,7 @@ class LinearParams(object):
         self.w = None
         self.b = None
         self._stamp = None
+        self._dirty = False
 
     def _current_stamp(self):
         return tuple((w.data_ptr(), w._version, b.data_ptr(), b._version) for w, b in self.pairs)
@@ -155,8 +159,9 @@ class LinearParams(object):
         """(dst, src) copy pairs needed to bring the bf16 operand copy up to date ([] if current)."""
         self._ensure_storage()
         stamp = self._current_stamp()
-        if not force and stamp == self._stamp:
+        if not force and not self._dirty and stamp == self._stamp:
             return []
+        self._dirty = bool(force)   # a training forward: the optimizer may change the masters afterwards
         out = []
         r = 0
         for (w, b), n in zip(self.pairs, self.sizes):

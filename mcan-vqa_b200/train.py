@@ -56,7 +56,6 @@ class Trainer(object):
         self.seed_word = torch.zeros(1, dtype=torch.int32, device=device)
         if use_graph:
             ops.set_seed_tensor(self.seed_word)
-            blocks.ALWAYS_RECAST = True
 
     # -- one optimisation step on device-resident tensors -------------------------------------
     def _advance_seed(self):
@@ -102,6 +101,7 @@ class Trainer(object):
         self.opt.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph):
             self.loss = self._raw_step(*self.static)
+        self._step -= 1          # capturing records the step, it does not execute it
         torch.cuda.synchronize()
 
     def step(self, img, ques, ans):
@@ -119,6 +119,5 @@ class Trainer(object):
     def close(self):
         if self.use_graph:
             ops.set_seed_tensor(None)
-            blocks.ALWAYS_RECAST = False
         if self.sync is not None:
             dp.detach()
