@@ -190,6 +190,11 @@ int mcan_attflat_pool_bwd(const float* dpooled, const void* hmid, const float* w
 /* -- small memory-bound helpers -------------------------------------------------------- */
 /* hi = bf16(x); lo (optional) = bf16(x - hi).  n elements. */
 int mcan_cast_bf16(const float* x, int64_t n, void* hi, void* lo, void* stream);
+/* Multi-tensor refresh of GEMM-operand copies in ONE launch.  seg_table_dev: device array of
+ * num_segments entries {const float* src; void* dst; int64 n; int64 first_chunk}, segments laid
+ * out back to back in 4096-element chunks (first_chunk = running chunk index; bit 62 set means
+ * dst is fp32 (plain copy, used to concatenate biases), otherwise dst is bf16). */
+int mcan_cast_multi(const void* seg_table_dev, int32_t num_segments, int64_t total_chunks, void* stream);
 /* out = bf16(act > 0 ? dy * scale : 0): gradient through FC's ReLU + dropout (net_utils.py:28-32)
  * from the saved bf16 activation; n contiguous elements. */
 int mcan_gate_bf16(const float* dy, const void* act, float scale, void* out, int64_t n, void* stream);

@@ -236,13 +236,27 @@ def _force(rt_training):
 def refresh_params(lps, force=False):
     """Brings the bf16 operand copies of many layers up to date with ONE multi-tensor copy
     (fp32 -> bf16 cast of the weights, concatenation of stacked biases)."""
-    dst, src = [], []
+    todo = []
     for lp in lps:
-        for d, s_ in lp.pending(force):
-            dst.append(d)
-            src.append(s_)
-    if dst:
-        torch._foreach_copy_(dst, src)
+        todo += lp.pending(force)
+    if not todo:
+        return
+    fast = [(d, s_) for d, s_ in todo if d.is_contiguous() and s_.is_contiguous() and s_.dtype == _F32]
+    slow = [(d, s_) for d, s_ in todo if not (d.is_contiguous() and s_.is_contiguous() and s_.dtype == _F32)]
+    if fast:
+        key = tuple((d.data_ptr(), s_.data_ptr(), s_.numel()) for d, s_ in fast)
+        entry = _cast_tables.get(key)
+        if entry is None:
+            if len(_cast_tables) > 64:
+                _cast_tables.clear()
+            entry = ops.build_cast_table(fast, fast[0][0].device)
+            _cast_tables[key] = entry
+        ops.cast_multi(*entry)
+    if slow:    # padded leading dimensions (k % 8 != 0): plumbing copies, not on the hot path
+        torch._foreach_copy_([d for d, _ in slow], [s_ for _, s_ in slow])
+
+
+_cast_tables = {}
 
 
 class refresh_scope(object):

@@ -112,6 +112,7 @@ SYMBOLS = {
                                              c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcan_cast_bf16": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "mcan_cast_multi": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_void_p]),
     "mcan_gate_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "mcan_colsum_bf16": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "mcan_colsum_f32": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),

@@ -34,6 +34,54 @@ cast_bf16_kernel(const float* __restrict__ x, long long n, bf16* __restrict__ hi
     }
 }
 
+// Multi-tensor cast/copy: one launch refreshes the bf16 GEMM-operand copies of MANY fp32 master
+// weights (and concatenates the fp32 biases of stacked layers).  The segment table lives in
+// device memory so the launch is CUDA-graph friendly.
+struct CastSeg {
+    const float* src;
+    void* dst;
+    long long n;            // elements
+    long long first_chunk;  // index of this segment's first 4096-element chunk; bit 62 set = fp32 destination
+};
+constexpr long long kCastChunk = 4096;
+constexpr long long kCastF32Flag = 1LL << 62;
+
+__global__ void __launch_bounds__(256)
+cast_multi_kernel(const CastSeg* __restrict__ segs, int nseg, long long total_chunks) {
+    for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
+        int lo = 0, hi = nseg - 1;
+        while (lo < hi) {   // last segment whose first_chunk <= chunk
+            const int mid = (lo + hi + 1) >> 1;
+            if ((segs[mid].first_chunk & ~kCastF32Flag) <= chunk) lo = mid; else hi = mid - 1;
+        }
+        const CastSeg sg = segs[lo];
+        const bool to_f32 = (sg.first_chunk & kCastF32Flag) != 0;
+        const long long off = (chunk - (sg.first_chunk & ~kCastF32Flag)) * kCastChunk;
+        const long long n = min(kCastChunk, sg.n - off);
+        const float* src = sg.src + off;
+        if (to_f32) {
+            float* dst = reinterpret_cast<float*>(sg.dst) + off;
+            for (long long i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        } else {
+            bf16* dst = reinterpret_cast<bf16*>(sg.dst) + off;
+            if ((((uintptr_t)src & 15) | ((uintptr_t)dst & 7)) == 0) {
+                const long long nv = n >> 2;
+                for (long long i = threadIdx.x; i < nv; i += blockDim.x) {
+                    const float4 v = reinterpret_cast<const float4*>(src)[i];
+                    uint2 w;
+                    w.x = pack_bf16x2(v.x, v.y);
+                    w.y = pack_bf16x2(v.z, v.w);
+                    reinterpret_cast<uint2*>(dst)[i] = w;
+                }
+                for (long long i = (nv << 2) + threadIdx.x; i < n; i += blockDim.x)
+                    dst[i] = __float2bfloat16_rn(src[i]);
+            } else {
+                for (long long i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __float2bfloat16_rn(src[i]);
+            }
+        }
+    }
+}
+
 // out = act > 0 ? dy * scale : 0   (backward through ReLU + dropout using the saved activation)
 __global__ void __launch_bounds__(256)
 gate_bf16_kernel(const float* __restrict__ dy, const bf16* __restrict__ act, float scale,
@@ -162,6 +210,18 @@ extern "C" int mcan_gate_bf16(const float* dy, const void* act, float scale, voi
     if (blocks > 16LL * sms) blocks = 16LL * sms;
     gate_bf16_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         dy, reinterpret_cast<const bf16*>(act), scale, reinterpret_cast<bf16*>(out), n);
+    MCAN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mcan_cast_multi(const void* seg_table_dev, int32_t num_segments, int64_t total_chunks,
+                               void* stream) {
+    MCAN_REQUIRE(seg_table_dev && num_segments > 0 && total_chunks > 0, "mcan_cast_multi: bad args");
+    const int sms = device_num_sms();
+    MCAN_REQUIRE(sms > 0, "mcan_cast_multi: no CUDA device");
+    long long blocks = total_chunks < 16LL * sms ? total_chunks : 16LL * sms;
+    cast_multi_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const CastSeg*>(seg_table_dev), num_segments, total_chunks);
     MCAN_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

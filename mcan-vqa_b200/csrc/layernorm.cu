@@ -233,7 +233,7 @@ extern "C" int mcan_layernorm_bwd(const float* dy, const float* x, const float* 
     MCAN_REQUIRE(sms > 0, "mcan_layernorm_bwd: no CUDA device");
     // rows per CTA: 32 when that still gives >= 1 CTA per SM, fewer for short inputs
     int rpc = kLnBwdMaxRows;
-    while (rpc > 4 && (rows + rpc - 1) / rpc < 3LL * sms) rpc >>= 1;
+    while (rpc > 4 && (rows + rpc - 1) / rpc < sms) rpc >>= 1;
     const int grid = (int)((rows + rpc - 1) / rpc);
     const uint32_t thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0;
     const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;

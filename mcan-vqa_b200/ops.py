@@ -226,6 +226,29 @@ def cast_bf16(x, hi, lo=None):
                "mcan_cast_bf16")
 
 
+CAST_CHUNK = 4096
+_CAST_F32_FLAG = 1 << 62
+
+
+def build_cast_table(pairs, device):
+    """pairs = [(dst, src)] with fp32 contiguous src and bf16 (cast) or fp32 (copy) contiguous dst.
+    Returns (int64 table tensor on `device`, num_segments, total_chunks) for cast_multi."""
+    rows, chunk = [], 0
+    for dst, src in pairs:
+        n = src.numel()
+        if not (src.is_contiguous() and dst.is_contiguous() and dst.numel() == n and src.dtype == _F32):
+            raise capi.McanError("cast table: tensors must be contiguous fp32 -> bf16/fp32 of equal size")
+        flag = _CAST_F32_FLAG if dst.dtype == _F32 else 0
+        rows.append([src.data_ptr(), dst.data_ptr(), n, chunk | flag])
+        chunk += (n + CAST_CHUNK - 1) // CAST_CHUNK
+    return torch.tensor(rows, dtype=torch.int64).to(device), len(rows), chunk
+
+
+def cast_multi(table, num_segments, total_chunks):
+    lib = capi.load()
+    capi.check(lib.mcan_cast_multi(table.data_ptr(), num_segments, total_chunks, _stream()), "mcan_cast_multi")
+
+
 def gate_bf16(dy, act, scale, out):
     """out = bf16(act > 0 ? dy * scale : 0) -- backward through ReLU (+dropout) of a saved activation."""
     lib = capi.load()

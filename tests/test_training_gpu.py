@@ -38,7 +38,7 @@ def test_loss_curve_100_steps_matches_oracle():
     T, A, B, steps = 50, 24, 8, 100
     sd = orc.synth_state_dict(cfg, T, A, seed=0)
     batches = [orc.synth_batch(cfg, B, 12, 7, T, A, seed=100 + i, ragged="prefix") for i in range(5)]
-    lr_base, data_size = 2e-3, 25 * B
+    lr_base, data_size = 1e-3, 25 * B
     ref = _oracle_losses(cfg, sd, batches, lr_base, data_size, B, steps)
     tr = Trainer(cfg, T, A, torch.device("cuda"), lr_base=lr_base, data_size=data_size, batch_size=B, state_dict=sd)
     dev_batches = [tuple(t.cuda() for t in b) for b in batches]
