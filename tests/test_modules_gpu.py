@@ -20,6 +20,10 @@ GOLD = os.path.join(ROOT, "tests", "golden")
 TOL_OUT = 1e-2       # relative (max abs err / max abs ref) on activations, bf16 mode
 TOL_GRAD = 6e-2      # relative L2 on weight gradients, bf16 mode (bf16 operands through chained sub-layers)
 TOL_GRAD_1D = 1e-1   # bias / LayerNorm vectors: column sums with cancellation amplify the bf16 noise
+# The per-module golden fixtures use uniform(-0.2, 0.2) weights at H=128 (large pre-LN sums): merely
+# rounding the GEMM operands of the fp64 oracle to bf16 already moves their gradients by 7-12 %
+# (relative L2; measured with the oracle on the CPU), so these fixtures get a wider gradient band.
+TOL_GRAD_FIXTURE = 1.2e-1
 
 
 def _rel_max(got, ref):
@@ -61,7 +65,7 @@ def _module_case(tag):
     return g, params
 
 
-def _check_module(tag, build, call, oracle_call, tol_out=TOL_OUT, tol_grad=TOL_GRAD):
+def _check_module(tag, build, call, oracle_call, tol_out=TOL_OUT, tol_grad=TOL_GRAD_FIXTURE):
     g, params = _module_case(tag)
     cfg = orc.Cfg(dropout_rate=0.0, **orc.TINY)
     mod = _load_params(build(cfg), params).train()       # dropout_rate = 0 -> deterministic
