@@ -99,7 +99,8 @@ class Trainer(object):
         self.graph = torch.cuda.CUDAGraph()
         self._set_lr()
         self.opt.zero_grad(set_to_none=True)
-        with torch.cuda.graph(self.graph):
+        # thread_local: the NCCL watchdog thread polls CUDA events while we capture (data parallel)
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.loss = self._raw_step(*self.static)
         self._step -= 1          # capturing records the step, it does not execute it
         torch.cuda.synchronize()
