@@ -355,8 +355,12 @@ def main():
                                     "sample": "oracle port, %d-sample training steps (fwd+bwd+AdamW, dropout 0.1), 2 timed after 1 warm-up" % args.cpu_batch}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # every collective this rank takes part in is done; skip the NCCL teardown (it can hang
+        # when captured graphs still reference the communicator) and leave immediately
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
