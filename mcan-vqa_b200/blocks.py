@@ -159,7 +159,9 @@ class LinearParams(object):
         """(dst, src) copy pairs needed to bring the bf16 operand copy up to date ([] if current)."""
         self._ensure_storage()
         stamp = self._current_stamp()
-        if not force and not self._dirty and stamp == self._stamp:
+        # inside a refresh_scope the scope entry already brought every copy up to date
+        dirty = self._dirty and _refresh_scope[0] == 0
+        if not force and not dirty and stamp == self._stamp:
             return []
         self._dirty = bool(force)   # a training forward: the optimizer may change the masters afterwards
         out = []
