@@ -89,9 +89,9 @@ __device__ __forceinline__ void stage_rows(bf16* s, const bf16* g, long long ld,
 }
 
 // S = Q_tile K^T for one 16-query tile.  acc[nt] covers keys nt*8..nt*8+7.
-template <int D>
+template <int D, int NT>
 __device__ __forceinline__ void qk_tile(const bf16* sQ, const bf16* sK, int mt, int nkt, int lane,
-                                        float (&acc)[kAttnMaxNT][4]) {
+                                        float (&acc)[NT][4]) {
     constexpr int LDS = D + 8;
     uint32_t qf[D / 16][4];
     {
@@ -102,12 +102,12 @@ __device__ __forceinline__ void qk_tile(const bf16* sQ, const bf16* sK, int mt, 
             ldsm_x4(smem_u32(base + kk * 16), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
     }
 #pragma unroll
-    for (int nt = 0; nt < kAttnMaxNT; ++nt)
+    for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
     const int mi = lane >> 3, r = lane & 7;
 #pragma unroll
-    for (int np = 0; np < kAttnMaxNT / 2; ++np) {
+    for (int np = 0; np < NT / 2; ++np) {
         if (np * 2 < nkt) {  // warp-uniform
             const bf16* kb = sK + (np * 16 + (mi >> 1) * 8 + r) * LDS + (mi & 1) * 8;
 #pragma unroll
@@ -157,13 +157,14 @@ __device__ __forceinline__ void dropout_pair(uint32_t idx, uint32_t seed, uint32
 // In-register masked softmax of the score tile (rows g and g+8 of this thread's quad).
 // Matches: scores/sqrt(d) -> masked_fill(mask, -1e9) -> softmax (mca.py:68-75), evaluated in the
 // log2 domain: p = exp2(s*log2e - max).
-__device__ __forceinline__ void softmax_tile(float (&acc)[kAttnMaxNT][4], uint32_t masked,
+template <int NT>
+__device__ __forceinline__ void softmax_tile(float (&acc)[NT][4], uint32_t masked,
                                              uint32_t valid, int nkt, float scale) {
     const float c = scale * kLog2e;
     const float kMasked = -1e9f * kLog2e;
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < kAttnMaxNT; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
         if (nt < nkt) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -189,7 +190,7 @@ __device__ __forceinline__ void softmax_tile(float (&acc)[kAttnMaxNT][4], uint32
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffU, mx1, 2));
     float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < kAttnMaxNT; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
         if (nt < nkt) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -208,7 +209,7 @@ __device__ __forceinline__ void softmax_tile(float (&acc)[kAttnMaxNT][4], uint32
     sum1 += __shfl_xor_sync(0xffffffffU, sum1, 2);
     const float inv0 = 1.f / sum0, inv1 = 1.f / sum1;
 #pragma unroll
-    for (int nt = 0; nt < kAttnMaxNT; ++nt) {
+    for (int nt = 0; nt < NT; ++nt) {
         if (nt < nkt) {
             acc[nt][0] *= inv0;
             acc[nt][1] *= inv0;
@@ -221,7 +222,8 @@ __device__ __forceinline__ void softmax_tile(float (&acc)[kAttnMaxNT][4], uint32
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
-template <int D>
+// NT = compile-time number of 8-key tiles; EXACT: the runtime tile count equals NT (no guards).
+template <int D, int NT, bool EXACT>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
     constexpr int LDS = D + 8;
     extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -243,15 +245,15 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
-    const int nkt = skp / 8;
+    const int nkt = EXACT ? NT : skp / 8;
     const uint32_t drop_seed =
         p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
     uint32_t kmasked, kvalid;
     key_bits(sMask, nkt, p.sk, lane, kmasked, kvalid);
 
     for (int mt = warp; mt < sqp / 16; mt += nwarps) {
-        float acc[kAttnMaxNT][4];
-        qk_tile<D>(sQ, sK, mt, nkt, lane, acc);
+        float acc[NT][4];
+        qk_tile<D, NT>(sQ, sK, mt, nkt, lane, acc);
         softmax_tile(acc, kmasked, kvalid, nkt, p.scale);
 
         const int row0 = mt * 16 + g, row1 = row0 + 8;
@@ -259,7 +261,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
             const uint32_t base0 = (uint32_t)(((long long)blockIdx.x * p.sq + row0) * p.sk);
             const uint32_t base1 = (uint32_t)(((long long)blockIdx.x * p.sq + row1) * p.sk);
 #pragma unroll
-            for (int nt = 0; nt < kAttnMaxNT; ++nt) {
+            for (int nt = 0; nt < NT; ++nt) {
                 if (nt < nkt) {
                     const uint32_t key = nt * 8 + 2 * t;
                     float k0, k1;
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
             for (int j = 0; j < 4; ++j) o[dn][j] = 0.f;
         const int mi = lane >> 3, r = lane & 7;
 #pragma unroll
-        for (int ks = 0; ks < kAttnMaxNT / 2; ++ks) {
+        for (int ks = 0; ks < NT / 2; ++ks) {
             if (ks * 2 < nkt) {
                 const uint32_t a0 = pack_bf16x2(acc[2 * ks][0], acc[2 * ks][1]);
                 const uint32_t a1 = pack_bf16x2(acc[2 * ks][2], acc[2 * ks][3]);
@@ -310,7 +312,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
-template <int D>
+template <int D, int NT, bool EXACT>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
     constexpr int LDS = D + 8;
     extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
     const int nwarps = blockDim.x >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int mi = lane >> 3, r = lane & 7;
-    const int nkt = skp / 8;
+    const int nkt = EXACT ? NT : skp / 8;
     const uint32_t drop_seed =
         p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
     uint32_t kmasked, kvalid;
@@ -346,13 +348,13 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
 
     // ---- phase 1: per 16-query tile: P, dPd, dS, dQ ----
     for (int mt = warp; mt < sqp / 16; mt += nwarps) {
-        float acc[kAttnMaxNT][4];
-        qk_tile<D>(sQ, sK, mt, nkt, lane, acc);
+        float acc[NT][4];
+        qk_tile<D, NT>(sQ, sK, mt, nkt, lane, acc);
         softmax_tile(acc, kmasked, kvalid, nkt, p.scale);
 
         // dPd = dO V^T (same operand pattern as Q K^T)
-        float dp[kAttnMaxNT][4];
-        qk_tile<D>(sdO, sV, mt, nkt, lane, dp);
+        float dp[NT][4];
+        qk_tile<D, NT>(sdO, sV, mt, nkt, lane, dp);
 
         const int row0 = mt * 16 + g, row1 = row0 + 8;
         const uint32_t base0 = (uint32_t)(((long long)blockIdx.x * p.sq + row0) * p.sk);
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
         // acc = P (undropped); Pd = keep*P goes to smem; dp <- dP = keep * dPd;
         // D_i = sum_j Pd_ij dPd_ij = sum_j P_ij dP_ij
 #pragma unroll
-        for (int nt = 0; nt < kAttnMaxNT; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
             if (nt < nkt) {
                 float pd[4], keep[4] = {1.f, 1.f, 1.f, 1.f};
                 if (p.drop_thr != 0) {
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
         d1 += __shfl_xor_sync(0xffffffffU, d1, 1);
         d1 += __shfl_xor_sync(0xffffffffU, d1, 2);
 #pragma unroll
-        for (int nt = 0; nt < kAttnMaxNT; ++nt) {
+        for (int nt = 0; nt < NT; ++nt) {
             if (nt < nkt) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -406,7 +408,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) o[dn][j] = 0.f;
 #pragma unroll
-        for (int ks = 0; ks < kAttnMaxNT / 2; ++ks) {
+        for (int ks = 0; ks < NT / 2; ++ks) {
             if (ks * 2 < nkt) {
                 const uint32_t a0 = pack_bf16x2(dp[2 * ks][0], dp[2 * ks][1]);
                 const uint32_t a1 = pack_bf16x2(dp[2 * ks][2], dp[2 * ks][3]);
@@ -531,6 +533,33 @@ static int set_smem_once(K kernel, size_t bytes, size_t* configured) {
 
 using namespace mcan;
 
+template <int D, int NT, bool EXACT>
+static int launch_attn_fwd(const AttnParams& p, int grid, int threads, size_t smem, cudaStream_t st) {
+    static size_t configured = 48 * 1024;
+    if (int rc = set_smem_once(attn_fwd_kernel<D, NT, EXACT>, smem, &configured)) return rc;
+    attn_fwd_kernel<D, NT, EXACT><<<grid, threads, smem, st>>>(p);
+    MCAN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+template <int D, int NT, bool EXACT>
+static int launch_attn_bwd(const AttnParams& p, int grid, int threads, size_t smem, cudaStream_t st) {
+    static size_t configured = 48 * 1024;
+    if (int rc = set_smem_once(attn_bwd_kernel<D, NT, EXACT>, smem, &configured)) return rc;
+    attn_bwd_kernel<D, NT, EXACT><<<grid, threads, smem, st>>>(p);
+    MCAN_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+// tile-count specialisations: 2 (<= 16 keys: question), 14 (<= 112 keys: 100 image regions), 16 (any)
+#define MCAN_ATTN_DISPATCH(FN, D)                                                       \
+    do {                                                                                \
+        const int nkt = ((sk + 15) & ~15) / 8;                                          \
+        if (nkt == 2) return FN<D, 2, true>(p, grid, threads, smem, st);                \
+        if (nkt == 14) return FN<D, 14, true>(p, grid, threads, smem, st);              \
+        if (nkt == 16) return FN<D, 16, true>(p, grid, threads, smem, st);              \
+        if (nkt < 8) return FN<D, 8, false>(p, grid, threads, smem, st);                \
+        return FN<D, 16, false>(p, grid, threads, smem, st);                            \
+    } while (0)
+
 extern "C" int mcan_attn_fwd(const mcan_attn_args* a) {
     MCAN_REQUIRE(a != nullptr, "mcan_attn_fwd: null args");
     if (int rc = check_attn(a, "mcan_attn_fwd")) return rc;
@@ -541,17 +570,10 @@ extern "C" int mcan_attn_fwd(const mcan_attn_args* a) {
     const int mtiles = (a->sq + 15) / 16;
     const int threads = 32 * (mtiles < 4 ? mtiles : 4);
     const int grid = a->batch * a->heads;
+    const int sk = a->sk;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
-    static size_t cfg64 = 48 * 1024, cfg128 = 48 * 1024;
-    if (a->head_dim == 64) {
-        if (int rc = set_smem_once(attn_fwd_kernel<64>, smem, &cfg64)) return rc;
-        attn_fwd_kernel<64><<<grid, threads, smem, st>>>(p);
-    } else {
-        if (int rc = set_smem_once(attn_fwd_kernel<128>, smem, &cfg128)) return rc;
-        attn_fwd_kernel<128><<<grid, threads, smem, st>>>(p);
-    }
-    MCAN_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    if (a->head_dim == 64) MCAN_ATTN_DISPATCH(launch_attn_fwd, 64);
+    MCAN_ATTN_DISPATCH(launch_attn_fwd, 128);
 }
 
 extern "C" int mcan_attn_bwd(const mcan_attn_bwd_args* a) {
@@ -575,15 +597,8 @@ extern "C" int mcan_attn_bwd(const mcan_attn_bwd_args* a) {
     const int mx = mtiles > ktiles ? mtiles : ktiles;
     const int threads = 32 * (mx < 8 ? mx : 8);
     const int grid = a->fwd.batch * a->fwd.heads;
+    const int sk = a->fwd.sk;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a->fwd.stream);
-    static size_t cfg64 = 48 * 1024, cfg128 = 48 * 1024;
-    if (a->fwd.head_dim == 64) {
-        if (int rc = set_smem_once(attn_bwd_kernel<64>, smem, &cfg64)) return rc;
-        attn_bwd_kernel<64><<<grid, threads, smem, st>>>(p);
-    } else {
-        if (int rc = set_smem_once(attn_bwd_kernel<128>, smem, &cfg128)) return rc;
-        attn_bwd_kernel<128><<<grid, threads, smem, st>>>(p);
-    }
-    MCAN_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    if (a->fwd.head_dim == 64) MCAN_ATTN_DISPATCH(launch_attn_bwd, 64);
+    MCAN_ATTN_DISPATCH(launch_attn_bwd, 128);
 }
