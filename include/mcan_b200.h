@@ -125,6 +125,12 @@ typedef struct mcan_attn_args {
     float dropout_p;
     uint32_t dropout_seed;
     const uint32_t* dropout_seed_dev; /* optional device word XOR-ed into dropout_seed */
+    /* split precision (forward only): low-order bf16 halves of q/k/v and of the output, same
+     * addressing as the hi pointers; all four or none.  Products become hi*hi + hi*lo + lo*hi. */
+    const void* q_lo;
+    const void* k_lo;
+    const void* v_lo;
+    void* out_lo;
     void* stream;
 } mcan_attn_args;
 
@@ -170,11 +176,12 @@ int mcan_layernorm_bwd(const float* dy, const float* x, const float* mean, const
  *   logit[b,s,g] = hmid[b,s,:] . w2[g,:] + b2[g];  masked_fill(mask, -1e9)
  *   att_w = softmax over s;  pooled[b, g*h : (g+1)*h] = sum_s att_w[b,s,g] * x[b,s,:]
  * pooled is written as fp32 and bf16 (operand of linear_merge).  One CTA per sample.
+ * hmid_lo (optional): low-order bf16 half of hmid (split precision).
  */
-int mcan_attflat_pool_fwd(const void* hmid, const float* w2, const float* b2, const uint8_t* mask,
-                          const float* x, int32_t batch, int32_t s, int32_t h, int32_t mlp,
-                          int32_t glimpses, float* att_w, float* pooled_f32, void* pooled_bf16,
-                          void* stream);
+int mcan_attflat_pool_fwd(const void* hmid, const void* hmid_lo, const float* w2, const float* b2,
+                          const uint8_t* mask, const float* x, int32_t batch, int32_t s, int32_t h,
+                          int32_t mlp, int32_t glimpses, float* att_w, float* pooled_f32,
+                          void* pooled_bf16, void* stream);
 
 /* backward: dpooled fp32 [batch, g*h] ->
  *   dx[b,s,:]  = sum_g att_w[b,s,g] * dpooled[b,g,:]                       (fp32, overwritten)
@@ -191,9 +198,10 @@ int mcan_attflat_pool_bwd(const float* dpooled, const void* hmid, const float* w
 /* hi = bf16(x); lo (optional) = bf16(x - hi).  n elements. */
 int mcan_cast_bf16(const float* x, int64_t n, void* hi, void* lo, void* stream);
 /* Multi-tensor refresh of GEMM-operand copies in ONE launch.  seg_table_dev: device array of
- * num_segments entries {const float* src; void* dst; int64 n; int64 first_chunk}, segments laid
- * out back to back in 4096-element chunks (first_chunk = running chunk index; bit 62 set means
- * dst is fp32 (plain copy, used to concatenate biases), otherwise dst is bf16). */
+ * num_segments entries {const float* src; void* dst; int64 n; int64 first_chunk; void* dst_lo},
+ * segments laid out back to back in 4096-element chunks (first_chunk = running chunk index; bit 62
+ * set means dst is fp32 (plain copy, used to concatenate biases), otherwise dst is bf16 and dst_lo,
+ * if not NULL, receives bf16(x - bf16(x)) for the split-precision mode). */
 int mcan_cast_multi(const void* seg_table_dev, int32_t num_segments, int64_t total_chunks, void* stream);
 /* out = bf16(act > 0 ? dy * scale : 0): gradient through FC's ReLU + dropout (net_utils.py:28-32)
  * from the saved bf16 activation; n contiguous elements. */

@@ -11,4 +11,11 @@ lives in the overlay `core/model/` at the repo root.
 """
 from . import capi  # noqa: F401
 
-__all__ = ["capi"]
+
+def set_precision(mode):
+    """'bf16' (default) or 'fp32' (split-precision inference, see blocks.PRECISION)."""
+    from . import blocks
+    blocks.set_precision(mode)
+
+
+__all__ = ["capi", "set_precision"]

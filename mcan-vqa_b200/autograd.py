@@ -107,13 +107,13 @@ class _MHAttRunner(_Runner):
         H = m.hidden_size
         B, Sq, Sk = q.shape[0], q.shape[1], k.shape[1]
         self.B, self.Sq, self.Sk = B, Sq, Sk
-        qa = blocks.act_from_f32(_as_f32_2d(q, H))
+        qa = blocks.act_from_f32(_as_f32_2d(q, H), self.rt.split)
         mu8 = _mask_u8(mask, B, Sk)
         if self.same_vk and self.same_kq:
             out, self.c = blocks.att_fwd(self.rt, m, qa, B, Sq, key_mask=mu8)
         else:
-            ka = blocks.act_from_f32(_as_f32_2d(k, H))
-            va = None if self.same_vk else blocks.act_from_f32(_as_f32_2d(v, H))
+            ka = blocks.act_from_f32(_as_f32_2d(k, H), self.rt.split)
+            va = None if self.same_vk else blocks.act_from_f32(_as_f32_2d(v, H), self.rt.split)
             out, self.c = blocks.att_fwd(self.rt, m, qa, B, Sq, kv_src=ka, Sk=Sk, key_mask=mu8, v_src=va)
         return out.view(B, Sq, H)
 
@@ -144,7 +144,7 @@ class _MLPRunner(_Runner):
         (x,) = acts
         mlp = self.module
         self.shape = x.shape
-        xa = blocks.act_from_f32(_as_f32_2d(x, mlp.in_size))
+        xa = blocks.act_from_f32(_as_f32_2d(x, mlp.in_size), self.rt.split)
         out, self.c = blocks.mlp_fwd(self.rt, mlp, xa)
         return out.contiguous().view(self.shape[:-1] + (mlp.out_size,))
 
@@ -211,7 +211,7 @@ class _SARunner(_Runner):
         m = self.module
         H = m.hidden_size
         self.B, self.S = x.shape[0], x.shape[1]
-        xa = blocks.act_from_f32(_as_f32_2d(x, H))
+        xa = blocks.act_from_f32(_as_f32_2d(x, H), self.rt.split)
         out, self.c = blocks.sa_fwd(self.rt, m, xa, self.B, self.S, _mask_u8(mask, self.B, self.S))
         return out.f32.view(self.B, self.S, H)
 
@@ -232,8 +232,8 @@ class _SGARunner(_Runner):
         m = self.module
         H = m.hidden_size
         self.B, self.Sx, self.Sy = x.shape[0], x.shape[1], y.shape[1]
-        xa = blocks.act_from_f32(_as_f32_2d(x, H))
-        ya = blocks.act_from_f32(_as_f32_2d(y, H))
+        xa = blocks.act_from_f32(_as_f32_2d(x, H), self.rt.split)
+        ya = blocks.act_from_f32(_as_f32_2d(y, H), self.rt.split)
         out, self.c = blocks.sga_fwd(self.rt, m, xa, ya, self.B, self.Sx, self.Sy,
                                      _mask_u8(x_mask, self.B, self.Sx), _mask_u8(y_mask, self.B, self.Sy))
         return out.f32.view(self.B, self.Sx, H)
@@ -288,7 +288,7 @@ class _SAStackRunner(_Runner):
         H = m.hidden_size
         self.B, self.S = y.shape[0], y.shape[1]
         mu8 = _mask_u8(mask, self.B, self.S)
-        a = blocks.act_from_f32(_as_f32_2d(y, H))
+        a = blocks.act_from_f32(_as_f32_2d(y, H), self.rt.split)
         self.ctxs = []
         for enc in m.enc_list:
             a, c = blocks.sa_fwd(self.rt, enc, a, self.B, self.S, mu8)
@@ -316,7 +316,7 @@ class _AttFlatRunner(_Runner):
         m = self.module
         H = m.hidden_size
         self.B, self.S = x.shape[0], x.shape[1]
-        xa = blocks.act_from_f32(_as_f32_2d(x, H))
+        xa = blocks.act_from_f32(_as_f32_2d(x, H), self.rt.split)
         out, att_w, self.c = blocks.attflat_fwd(self.rt, m, xa, self.B, self.S, _mask_u8(mask, self.B, self.S))
         self.non_differentiable = (att_w,)
         return out, att_w
@@ -339,8 +339,8 @@ class _LinearRunner(_Runner):
         (x,) = acts
         lin = self.module
         self.shape = x.shape
-        lp = lin.lp().get(blocks._force(torch.is_grad_enabled()))
-        out, self.c = blocks.linear_fwd(lp, _as_f32_2d(x, lp.k))
+        lp = lin.lp().get(blocks._force(torch.is_grad_enabled()), self.rt.split)
+        out, self.c = blocks.linear_fwd(lp, _as_f32_2d(x, lp.k), self.rt.split)
         return out.contiguous().view(self.shape[:-1] + (lp.n,)) if out.stride(0) != lp.n else out.view(self.shape[:-1] + (lp.n,))
 
     def backward(self, gouts, needs):

@@ -24,6 +24,7 @@ Per sub-layer launch chain (forward):
     FFN:            GEMM[fc + bias + ReLU + dropout] -> GEMM[out + bias + dropout + residual] -> LayerNorm
 """
 import math
+import os
 
 import torch
 
@@ -38,6 +39,20 @@ _F32 = torch.float32
 # without grad re-cast only when a master changed (version / storage) or a training forward
 # happened since the last refresh.  Cost: one multi-tensor cast per step (refresh_params).
 ALWAYS_RECAST = True
+
+
+# "bf16": bf16 GEMM/attention operands, fp32 accumulation (training and default inference).
+# "fp32": split-precision INFERENCE -- every operand is carried as bf16 hi + lo and every product is
+#         evaluated as hi*hi + hi*lo + lo*hi on the tensor cores (~2e-5 relative, i.e. fp32-grade
+#         logits and identical top-1 answers); applies to forwards without grad, training stays bf16.
+PRECISION = os.environ.get("MCAN_PRECISION", "bf16")
+
+
+def set_precision(mode):
+    global PRECISION
+    if mode not in ("bf16", "fp32"):
+        raise ValueError("precision must be 'bf16' or 'fp32'")
+    PRECISION = mode
 
 
 def _mix32(x):
@@ -62,6 +77,7 @@ class Runtime(object):
         self.base = _mix32((torch.initial_seed() & 0xFFFFFFFF) ^ (_seed_counter[0] * 0x9E3779B9))
         self.n = 0
         self.bufs = []      # loose fp32 gradient buffers produced since the last drain (for dp.py)
+        self.split = (PRECISION == "fp32") and not torch.is_grad_enabled()
         self.arena = None   # one zero-initialised flat buffer all gradients of a backward are carved from
         self.arena_off = 0
         self.arena_mark = 0
@@ -102,17 +118,30 @@ class Runtime(object):
 
 class Act(object):
     """An activation in the formats the kernels consume: fp32 (residual stream) and bf16 (GEMM operand)."""
-    __slots__ = ("f32", "bf")
+    __slots__ = ("f32", "bf", "lo")
 
-    def __init__(self, f32=None, bf=None):
+    def __init__(self, f32=None, bf=None, lo=None):
         self.f32 = f32
         self.bf = bf
+        self.lo = lo        # bf16(x - bf16(x)), split-precision mode only
 
 
-def act_from_f32(x2d):
+def act_from_f32(x2d, split=False):
     bf = torch.empty(x2d.shape, dtype=_BF16, device=x2d.device)
-    ops.cast_bf16(x2d, bf)
-    return Act(x2d, bf)
+    lo = torch.empty(x2d.shape, dtype=_BF16, device=x2d.device) if split else None
+    ops.cast_bf16(x2d, bf, lo)
+    return Act(x2d, bf, lo)
+
+
+def _mm(rt, a, lp, i0, i1, out_bf16=None, out_lo=None, **kw):
+    """GEMM of activation `a` (Act) with stacked members [i0,i1) of `lp`; 3 operand segments in
+    split-precision mode."""
+    w, b = lp.rows(i0, i1)
+    if rt.split:
+        wl = lp.rows_lo(i0, i1)
+        ops.gemm([a.bf, a.bf, a.lo], [w, wl, w], bias=b, out_bf16=out_bf16, out_lo=out_lo, **kw)
+    else:
+        ops.gemm(a.bf, w, bias=b, out_bf16=out_bf16, **kw)
 
 
 def _empty(rows, cols, dtype, device):
@@ -140,6 +169,7 @@ class LinearParams(object):
         self.n = sum(self.sizes)
         self.k = self.pairs[0][0].shape[1]
         self.w = None
+        self.w_lo = None
         self.b = None
         self._stamp = None
         self._dirty = False
@@ -153,11 +183,15 @@ class LinearParams(object):
             ld = (self.k + 7) // 8 * 8
             self.w = torch.zeros((self.n, ld), dtype=_BF16, device=dev)[:, :self.k]
             self.b = torch.empty((self.n,), dtype=_F32, device=dev) if len(self.pairs) > 1 else None
+            self.w_lo = None
             self._stamp = None
 
-    def pending(self, force=False):
-        """(dst, src) copy pairs needed to bring the bf16 operand copy up to date ([] if current)."""
+    def pending(self, force=False, need_lo=False):
+        """(dst, src[, dst_lo]) copy items needed to bring the bf16 operand copy up to date ([] if current)."""
         self._ensure_storage()
+        if need_lo and self.w_lo is None:
+            self.w_lo = torch.zeros((self.n, self.w.stride(0)), dtype=_BF16, device=self.w.device)[:, :self.k]
+            force = True
         stamp = self._current_stamp()
         # inside a refresh_scope the scope entry already brought every copy up to date
         dirty = self._dirty and _refresh_scope[0] == 0
@@ -167,7 +201,10 @@ class LinearParams(object):
         out = []
         r = 0
         for (w, b), n in zip(self.pairs, self.sizes):
-            out.append((self.w[r:r + n], w.detach()))
+            if self.w_lo is not None:
+                out.append((self.w[r:r + n], w.detach(), self.w_lo[r:r + n]))
+            else:
+                out.append((self.w[r:r + n], w.detach()))
             if len(self.pairs) > 1:
                 out.append((self.b[r:r + n], b.detach()))
             r += n
@@ -176,11 +213,14 @@ class LinearParams(object):
         self._stamp = stamp
         return out
 
-    def get(self, force=False):
-        todo = self.pending(force)
-        if todo:
-            torch._foreach_copy_([d for d, _ in todo], [s_ for _, s_ in todo])
+    def get(self, force=False, need_lo=False):
+        refresh_params([self], force, need_lo)
         return self
+
+    def rows_lo(self, i0, i1):
+        r0 = sum(self.sizes[:i0])
+        r1 = sum(self.sizes[:i1])
+        return self.w_lo[r0:r1]
 
     def rows(self, i0, i1):
         """(weight rows, bias) of stacked members i0..i1-1."""
@@ -235,18 +275,22 @@ def _force(rt_training):
     return ALWAYS_RECAST and rt_training and _refresh_scope[0] == 0
 
 
-def refresh_params(lps, force=False):
-    """Brings the bf16 operand copies of many layers up to date with ONE multi-tensor copy
-    (fp32 -> bf16 cast of the weights, concatenation of stacked biases)."""
+def refresh_params(lps, force=False, need_lo=False):
+    """Brings the bf16 operand copies of many layers up to date with ONE multi-tensor cast kernel
+    (fp32 -> bf16 [+ lo] of the weights, concatenation of stacked biases)."""
     todo = []
     for lp in lps:
-        todo += lp.pending(force)
+        todo += lp.pending(force, need_lo)
     if not todo:
         return
-    fast = [(d, s_) for d, s_ in todo if d.is_contiguous() and s_.is_contiguous() and s_.dtype == _F32]
-    slow = [(d, s_) for d, s_ in todo if not (d.is_contiguous() and s_.is_contiguous() and s_.dtype == _F32)]
+
+    def ok(item):
+        return all(t.is_contiguous() for t in item) and item[1].dtype == _F32
+
+    fast = [it for it in todo if ok(it)]
+    slow = [it for it in todo if not ok(it)]
     if fast:
-        key = tuple((d.data_ptr(), s_.data_ptr(), s_.numel()) for d, s_ in fast)
+        key = tuple(tuple(t.data_ptr() for t in it) + (it[1].numel(),) for it in fast)
         entry = _cast_tables.get(key)
         if entry is None:
             if len(_cast_tables) > 64:
@@ -254,8 +298,10 @@ def refresh_params(lps, force=False):
             entry = ops.build_cast_table(fast, fast[0][0].device)
             _cast_tables[key] = entry
         ops.cast_multi(*entry)
-    if slow:    # padded leading dimensions (k % 8 != 0): plumbing copies, not on the hot path
-        torch._foreach_copy_([d for d, _ in slow], [s_ for _, s_ in slow])
+    for it in slow:    # padded leading dimensions (k % 8 != 0): plumbing copies, not on the hot path
+        it[0].copy_(it[1])
+        if len(it) > 2:
+            it[2].copy_(it[1] - it[0].float())
 
 
 _cast_tables = {}
@@ -269,7 +315,8 @@ class refresh_scope(object):
 
     def __enter__(self):
         if _refresh_scope[0] == 0:
-            refresh_params(self.lps, ALWAYS_RECAST and self.training)
+            need_lo = (PRECISION == "fp32") and not torch.is_grad_enabled()
+            refresh_params(self.lps, ALWAYS_RECAST and self.training, need_lo)
         _refresh_scope[0] += 1
 
     def __exit__(self, *exc):
@@ -279,17 +326,18 @@ class refresh_scope(object):
 # ------------------------------------------------------------------------------------------
 # LayerNorm
 # ------------------------------------------------------------------------------------------
-def ln_fwd(norm, s_f32, want_bf=True):
-    """s_f32 [rows, h] fp32 -> (Act(y_f32, y_bf), mean, sigma)."""
+def ln_fwd(norm, s_f32, want_bf=True, split=False):
+    """s_f32 [rows, h] fp32 -> (Act(y_f32, y_bf[, y_lo]), mean, sigma)."""
     rows, h = s_f32.shape
     dev = s_f32.device
     y32 = _empty(rows, h, _F32, dev)
     ybf = _empty(rows, h, _BF16, dev) if want_bf else None
+    ylo = _empty(rows, h, _BF16, dev) if (want_bf and split) else None
     mean = torch.empty(rows, dtype=_F32, device=dev)
     sigma = torch.empty(rows, dtype=_F32, device=dev)
-    ops.layernorm_fwd(s_f32, norm.a_2.detach(), norm.b_2.detach(), norm.eps, y_f32=y32, y_bf16=ybf,
+    ops.layernorm_fwd(s_f32, norm.a_2.detach(), norm.b_2.detach(), norm.eps, y_f32=y32, y_bf16=ybf, y_lo=ylo,
                       mean=mean, sigma=sigma)
-    return Act(y32, ybf), mean, sigma
+    return Act(y32, ybf, ylo), mean, sigma
 
 
 def ln_bwd(rt, norm, dy, s_f32, mean, sigma, p=0.0, seed=0, want_bf=True, dbias=None):
@@ -321,51 +369,61 @@ def att_fwd(rt, mh, x, B, Sq, kv_src=None, Sk=None, key_mask=None, kv=None, norm
     M = B * Sq
     c = Bag()
     c.B, c.Sq, c.mask = B, Sq, key_mask
-    lp = mh.lp_qkv().get(_force(rt.p > 0 or torch.is_grad_enabled()))
+    lp = mh.lp_qkv().get(_force(rt.p > 0 or torch.is_grad_enabled()), rt.split)
     c.lp = lp
     c.x_bf = x.bf
     c.mode = "self" if (kv_src is None and kv is None) else ("kv" if kv is not None else "cross")
+    sp = rt.split
+    q_lo = k_lo = v_lo = None
     if c.mode == "self":
         Sk = Sq
-        w, b = lp.rows(0, 3)
         qkv = _empty(M, 3 * H, _BF16, dev)
-        ops.gemm(x.bf, w, bias=b, out_bf16=qkv)
+        qkv_lo = _empty(M, 3 * H, _BF16, dev) if sp else None
+        _mm(rt, x, lp, 0, 3, out_bf16=qkv, out_lo=qkv_lo)
         q, k, v = qkv[:, :H], qkv[:, H:2 * H], qkv[:, 2 * H:]
+        if sp:
+            q_lo, k_lo, v_lo = qkv_lo[:, :H], qkv_lo[:, H:2 * H], qkv_lo[:, 2 * H:]
     else:
-        w, b = lp.rows(0, 1)
         q = _empty(M, H, _BF16, dev)
-        ops.gemm(x.bf, w, bias=b, out_bf16=q)
+        q_lo = _empty(M, H, _BF16, dev) if sp else None
+        _mm(rt, x, lp, 0, 1, out_bf16=q, out_lo=q_lo)
         if c.mode == "kv":
-            k, v = kv
+            if sp:
+                k, v, k_lo, v_lo = kv
+            else:
+                k, v = kv[0], kv[1]
         else:
             kvb = _empty(B * Sk, 2 * H, _BF16, dev)
+            kvl = _empty(B * Sk, 2 * H, _BF16, dev) if sp else None
             k, v = kvb[:, :H], kvb[:, H:]
+            if sp:
+                k_lo, v_lo = kvl[:, :H], kvl[:, H:]
             if v_src is None:
-                w, b = lp.rows(1, 3)
-                ops.gemm(kv_src.bf, w, bias=b, out_bf16=kvb)
+                _mm(rt, kv_src, lp, 1, 3, out_bf16=kvb, out_lo=kvl)
             else:
-                w, b = lp.rows(1, 2)
-                ops.gemm(kv_src.bf, w, bias=b, out_bf16=k)
-                w, b = lp.rows(2, 3)
-                ops.gemm(v_src.bf, w, bias=b, out_bf16=v)
+                _mm(rt, kv_src, lp, 1, 2, out_bf16=k, out_lo=k_lo)
+                _mm(rt, v_src, lp, 2, 3, out_bf16=v, out_lo=v_lo)
                 c.v_bf = v_src.bf
             c.kv_bf = kv_src.bf
     c.Sk = Sk
     c.q, c.k, c.v = q, k, v
     att = _empty(M, H, _BF16, dev)
+    att_lo = _empty(M, H, _BF16, dev) if sp else None
     c.seed_att = rt.seed()
     ops.attn_fwd(q, k, v, key_mask, att, batch=B, heads=heads, sq=Sq, sk=Sk, head_dim=d,
-                 scale=1.0 / math.sqrt(d), dropout_p=rt.p, seed=c.seed_att)
+                 scale=1.0 / math.sqrt(d), dropout_p=rt.p, seed=c.seed_att,
+                 q_lo=q_lo, k_lo=k_lo, v_lo=v_lo, out_lo=att_lo)
     c.att = att
-    lpm = mh.lp_merge().get(_force(rt.p > 0 or torch.is_grad_enabled()))
+    lpm = mh.lp_merge().get(_force(rt.p > 0 or torch.is_grad_enabled()), rt.split)
     c.lpm = lpm
     s = _empty(M, H, _F32, dev)
+    atta = Act(None, att, att_lo)
     if norm is None:
-        ops.gemm(att, lpm.w, bias=lpm.b, out_f32=s)
+        _mm(rt, atta, lpm, 0, 1, out_f32=s)
         return s, c
     c.seed_out = rt.seed()
-    ops.gemm(att, lpm.w, bias=lpm.b, dropout_p=rt.p, seed=c.seed_out, resid=x.f32, out_f32=s)
-    out, c.mean, c.sigma = ln_fwd(norm, s)
+    _mm(rt, atta, lpm, 0, 1, dropout_p=rt.p, seed=c.seed_out, resid=x.f32, out_f32=s)
+    out, c.mean, c.sigma = ln_fwd(norm, s, split=rt.split)
     c.s = s
     return out, c
 
@@ -456,28 +514,29 @@ def mlp_fwd(rt, mlp, x, norm=None):
     M = x.bf.shape[0]
     c = Bag()
     force = _force(rt.p > 0 or torch.is_grad_enabled())
-    lp1 = mlp.lp_fc().get(force)
-    lp2 = mlp.lp_out().get(force)
+    lp1 = mlp.lp_fc().get(force, rt.split)
+    lp2 = mlp.lp_out().get(force, rt.split)
     c.lp1, c.lp2, c.x_bf = lp1, lp2, x.bf
     p_mid = rt.p if mlp.fc.dropout_r > 0 else 0.0
     c.p_mid = p_mid
     hmid = _empty(M, lp1.n, _BF16, dev)
+    hlo = _empty(M, lp1.n, _BF16, dev) if rt.split else None
     c.seed_mid = rt.seed()
-    ops.gemm(x.bf, lp1.w, bias=lp1.b, relu=mlp.fc.use_relu, dropout_p=p_mid, seed=c.seed_mid, out_bf16=hmid)
+    _mm(rt, x, lp1, 0, 1, relu=mlp.fc.use_relu, dropout_p=p_mid, seed=c.seed_mid, out_bf16=hmid, out_lo=hlo)
     c.hmid = hmid
+    ha = Act(None, hmid, hlo)
     if norm is None:
         if lp2.n % 8 == 0:
             out = _empty(M, lp2.n, _F32, dev)
-            ops.gemm(hmid, lp2.w, bias=lp2.b, out_f32=out)
         else:   # narrow head (e.g. AttFlat glimpses): padded fp32 output buffer
             ldp = (lp2.n + 3) // 4 * 4
             out = torch.empty((M, ldp), dtype=_F32, device=dev)[:, :lp2.n]
-            ops.gemm(hmid, lp2.w, bias=lp2.b, out_f32=out)
+        _mm(rt, ha, lp2, 0, 1, out_f32=out)
         return out, c
     s = _empty(M, lp2.n, _F32, dev)
     c.seed_out = rt.seed()
-    ops.gemm(hmid, lp2.w, bias=lp2.b, dropout_p=rt.p, seed=c.seed_out, resid=x.f32, out_f32=s)
-    out, c.mean, c.sigma = ln_fwd(norm, s)
+    _mm(rt, ha, lp2, 0, 1, dropout_p=rt.p, seed=c.seed_out, resid=x.f32, out_f32=s)
+    out, c.mean, c.sigma = ln_fwd(norm, s, split=rt.split)
     c.s = s
     return out, c
 
@@ -570,20 +629,23 @@ def mca_ed_fwd(rt, m, x32, y32, B, Sx, Sy, x_mask, y_mask):
 
 
 def _mca_ed_fwd(rt, m, x32, y32, B, Sx, Sy, x_mask, y_mask, H, L, dev):
-    x = act_from_f32(x32)
-    y = act_from_f32(y32)
+    x = act_from_f32(x32, rt.split)
+    y = act_from_f32(y32, rt.split)
     enc_ctx = []
     for enc in m.enc_list:
         x, c = sa_fwd(rt, enc, x, B, Sx, x_mask)
         enc_ctx.append(c)
     # K/V of the final encoder output for all decoder layers: one GEMM [B*Sx, H] x [H, L*2H]
-    lpkv = m.lp_kv_all().get(_force(rt.p > 0 or torch.is_grad_enabled()))
+    lpkv = m.lp_kv_all().get(_force(rt.p > 0 or torch.is_grad_enabled()), rt.split)
     kv_all = _empty(B * Sx, 2 * H * L, _BF16, dev)
+    kv_lo = _empty(B * Sx, 2 * H * L, _BF16, dev) if rt.split else None
     if L > 0:
-        ops.gemm(x.bf, lpkv.w, bias=lpkv.b, out_bf16=kv_all)
+        _mm(rt, x, lpkv, 0, len(lpkv.sizes), out_bf16=kv_all, out_lo=kv_lo)
     dec_ctx = []
     for i, dec in enumerate(m.dec_list):
         kv = (kv_all[:, 2 * H * i: 2 * H * i + H], kv_all[:, 2 * H * i + H: 2 * H * (i + 1)])
+        if rt.split:
+            kv = kv + (kv_lo[:, 2 * H * i: 2 * H * i + H], kv_lo[:, 2 * H * i + H: 2 * H * (i + 1)])
         y, c = sga_fwd(rt, dec, y, x, B, Sy, Sx, y_mask, x_mask, kv=kv)
         dec_ctx.append(c)
     ctx = Bag()
@@ -641,22 +703,29 @@ def attflat_fwd(rt, af, x, B, S, mask):
     dev = x.bf.device
     c = Bag()
     force = _force(rt.p > 0 or torch.is_grad_enabled())
-    lp1 = af.mlp.lp_fc().get(force)
-    lpm = af.lp_merge().get(force)
+    lp1 = af.mlp.lp_fc().get(force, rt.split)
+    lpm = af.lp_merge().get(force, rt.split)
     c.lp1, c.lpm, c.x, c.B, c.S, c.mask = lp1, lpm, x, B, S, mask
     p_mid = rt.p if af.mlp.fc.dropout_r > 0 else 0.0
     c.p_mid = p_mid
     hmid = _empty(B * S, M, _BF16, dev)
+    hlo = _empty(B * S, M, _BF16, dev) if rt.split else None
     c.seed_mid = rt.seed()
-    ops.gemm(x.bf, lp1.w, bias=lp1.b, relu=True, dropout_p=p_mid, seed=c.seed_mid, out_bf16=hmid)
+    _mm(rt, x, lp1, 0, 1, relu=True, dropout_p=p_mid, seed=c.seed_mid, out_bf16=hmid, out_lo=hlo)
     att_w = torch.empty((B, S, G), dtype=_F32, device=dev)
     pooled = _empty(B, G * H, _BF16, dev)
     w2 = af.mlp.linear.weight.detach()
     b2 = af.mlp.linear.bias.detach()
-    ops.attflat_pool_fwd(hmid, w2, b2, mask, x.f32, batch=B, s=S, h=H, mlp=M, glimpses=G, att_w=att_w,
-                         pooled_bf16=pooled)
     out = _empty(B, lpm.n, _F32, dev)
-    ops.gemm(pooled, lpm.w, bias=lpm.b, out_f32=out)
+    if rt.split:
+        p32 = _empty(B, G * H, _F32, dev)
+        ops.attflat_pool_fwd(hmid, w2, b2, mask, x.f32, batch=B, s=S, h=H, mlp=M, glimpses=G, att_w=att_w,
+                             pooled_f32=p32, hmid_lo=hlo)
+        _mm(rt, act_from_f32(p32, True), lpm, 0, 1, out_f32=out)
+    else:
+        ops.attflat_pool_fwd(hmid, w2, b2, mask, x.f32, batch=B, s=S, h=H, mlp=M, glimpses=G, att_w=att_w,
+                             pooled_bf16=pooled)
+        ops.gemm(pooled, lpm.w, bias=lpm.b, out_f32=out)
     c.hmid, c.att_w, c.pooled = hmid, att_w, pooled
     return out, att_w, c
 
@@ -695,18 +764,24 @@ def attflat_bwd(rt, af, c, dout, need_dx=True):
 # ------------------------------------------------------------------------------------------
 # plain linear on the tcgen05 GEMM (img_feat_linear / proj: the rows next to the hot path)
 # ------------------------------------------------------------------------------------------
-def linear_fwd(lp, x32):
+def linear_fwd(lp, x32, split=False):
     dev = x32.device
     M = x32.shape[0]
     c = Bag()
     xbf = _bf_padded(M, lp.k, dev)
+    xlo = _bf_padded(M, lp.k, dev) if split else None
     if xbf.stride(0) == lp.k:
-        ops.cast_bf16(x32.contiguous(), xbf)
+        ops.cast_bf16(x32.contiguous(), xbf, xlo)
     else:
         xbf.copy_(x32)
+        if split:
+            xlo.copy_(x32 - xbf.float())
     ldo = (lp.n + 3) // 4 * 4
     out = torch.empty((M, ldo), dtype=_F32, device=dev)[:, :lp.n]
-    ops.gemm(xbf, lp.w, bias=lp.b, out_f32=out)
+    if split:
+        ops.gemm([xbf, xbf, xlo], [lp.w, lp.w_lo, lp.w], bias=lp.b, out_f32=out)
+    else:
+        ops.gemm(xbf, lp.w, bias=lp.b, out_f32=out)
     c.xbf, c.lp = xbf, lp
     return out, c
 

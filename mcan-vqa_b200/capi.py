@@ -74,6 +74,10 @@ class AttnArgs(ctypes.Structure):
         ("dropout_p", c_float),
         ("dropout_seed", c_uint32),
         ("dropout_seed_dev", c_void_p),
+        ("q_lo", c_void_p),
+        ("k_lo", c_void_p),
+        ("v_lo", c_void_p),
+        ("out_lo", c_void_p),
         ("stream", c_void_p),
     ]
 
@@ -105,7 +109,7 @@ SYMBOLS = {
     "mcan_layernorm_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                           c_int64, c_int64, c_void_p, c_void_p, c_float, c_uint32,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "mcan_attflat_pool_fwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+    "mcan_attflat_pool_fwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                              c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                              c_void_p, c_void_p]),
     "mcan_attflat_pool_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -24,6 +24,10 @@ struct AttnParams {
     const bf16* q;
     const bf16* k;
     const bf16* v;
+    const bf16* q_lo;   // split precision ("bf16x3"): low-order halves, same addressing as q/k/v/out
+    const bf16* k_lo;
+    const bf16* v_lo;
+    bf16* out_lo;
     long long ldq, ldk, ldv;
     const uint8_t* mask;
     bf16* out;
@@ -89,7 +93,7 @@ __device__ __forceinline__ void stage_rows(bf16* s, const bf16* g, long long ld,
 }
 
 // S = Q_tile K^T for one 16-query tile.  acc[nt] covers keys nt*8..nt*8+7.
-template <int D, int NT>
+template <int D, int NT, bool ZERO = true>
 __device__ __forceinline__ void qk_tile(const bf16* sQ, const bf16* sK, int mt, int nkt, int lane,
                                         float (&acc)[NT][4]) {
     constexpr int LDS = D + 8;
@@ -101,10 +105,12 @@ __device__ __forceinline__ void qk_tile(const bf16* sQ, const bf16* sK, int mt, 
         for (int kk = 0; kk < D / 16; ++kk)
             ldsm_x4(smem_u32(base + kk * 16), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
     }
+    if (ZERO) {
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt)
+        for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+            for (int j = 0; j < 4; ++j) acc[nt][j] = 0.f;
+    }
     const int mi = lane >> 3, r = lane & 7;
 #pragma unroll
     for (int np = 0; np < NT / 2; ++np) {
@@ -312,6 +318,105 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
+// forward, split precision: every bf16 operand comes as hi + lo and every product is evaluated as
+// hi*hi + hi*lo + lo*hi (fp32 accumulate), which reproduces the fp32 reference to ~2e-5.
+// Used by the "fp32" inference mode (north star: 1e-4 logits, identical top-1 answers).
+// ------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(128) attn_fwd_split_kernel(const AttnParams p) {
+    constexpr int LDS = D + 8;
+    constexpr int NT = kAttnMaxNT;
+    extern __shared__ __align__(16) uint8_t smem_attn[];
+    const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
+    const int sqp = (p.sq + 15) & ~15, skp = (p.sk + 15) & ~15;
+    bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
+    bf16* sQl = sQ + sqp * LDS;
+    bf16* sK = sQl + sqp * LDS;
+    bf16* sKl = sK + skp * LDS;
+    bf16* sV = sKl + skp * LDS;
+    bf16* sVl = sV + skp * LDS;
+    uint8_t* sMask = reinterpret_cast<uint8_t*>(sVl + skp * LDS);
+    const long long qo = (long long)b * p.sq * p.ldq + h * D;
+    const long long ko = (long long)b * p.sk * p.ldk + h * D;
+    const long long vo = (long long)b * p.sk * p.ldv + h * D;
+    stage_rows<D>(sQ, p.q + qo, p.ldq, p.sq, sqp);
+    stage_rows<D>(sQl, p.q_lo + qo, p.ldq, p.sq, sqp);
+    stage_rows<D>(sK, p.k + ko, p.ldk, p.sk, skp);
+    stage_rows<D>(sKl, p.k_lo + ko, p.ldk, p.sk, skp);
+    stage_rows<D>(sV, p.v + vo, p.ldv, p.sk, skp);
+    stage_rows<D>(sVl, p.v_lo + vo, p.ldv, p.sk, skp);
+    for (int i = threadIdx.x; i < skp; i += blockDim.x)
+        sMask[i] = (p.mask != nullptr && i < p.sk) ? p.mask[(long long)b * p.sk + i] : 0;
+    cp_async_wait_all();
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int nkt = skp / 8;
+    uint32_t kmasked, kvalid;
+    key_bits(sMask, nkt, p.sk, lane, kmasked, kvalid);
+
+    for (int mt = warp; mt < sqp / 16; mt += nwarps) {
+        float acc[NT][4];
+        qk_tile<D, NT, true>(sQ, sK, mt, nkt, lane, acc);
+        qk_tile<D, NT, false>(sQ, sKl, mt, nkt, lane, acc);
+        qk_tile<D, NT, false>(sQl, sK, mt, nkt, lane, acc);
+        softmax_tile(acc, kmasked, kvalid, nkt, p.scale);
+
+        float o[D / 8][4];
+#pragma unroll
+        for (int dn = 0; dn < D / 8; ++dn)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[dn][j] = 0.f;
+        const int mi = lane >> 3, r = lane & 7;
+#pragma unroll
+        for (int ks = 0; ks < NT / 2; ++ks) {
+            if (ks * 2 < nkt) {
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float x0 = acc[2 * ks + (q >> 1)][2 * (q & 1)], x1 = acc[2 * ks + (q >> 1)][2 * (q & 1) + 1];
+                    ah[q] = pack_bf16x2(x0, x1);
+                    al[q] = pack_bf16x2(x0 - bf16_lo_to_f(ah[q]), x1 - bf16_hi_to_f(ah[q]));
+                }
+                const int voff = (ks * 16 + (mi & 1) * 8 + r) * LDS + (mi >> 1) * 8;
+#pragma unroll
+                for (int dp = 0; dp < D / 16; ++dp) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4_t(smem_u32(sV + voff + dp * 16), b0, b1, b2, b3);
+                    mma_bf16(o[dp * 2], ah[0], ah[1], ah[2], ah[3], b0, b1);
+                    mma_bf16(o[dp * 2 + 1], ah[0], ah[1], ah[2], ah[3], b2, b3);
+                    mma_bf16(o[dp * 2], al[0], al[1], al[2], al[3], b0, b1);
+                    mma_bf16(o[dp * 2 + 1], al[0], al[1], al[2], al[3], b2, b3);
+                    ldsm_x4_t(smem_u32(sVl + voff + dp * 16), b0, b1, b2, b3);
+                    mma_bf16(o[dp * 2], ah[0], ah[1], ah[2], ah[3], b0, b1);
+                    mma_bf16(o[dp * 2 + 1], ah[0], ah[1], ah[2], ah[3], b2, b3);
+                }
+            }
+        }
+        const int row0 = mt * 16 + g, row1 = row0 + 8;
+        const long long o0 = ((long long)b * p.sq + row0) * p.ldo + h * D + 2 * t;
+        const long long o1 = ((long long)b * p.sq + row1) * p.ldo + h * D + 2 * t;
+#pragma unroll
+        for (int dn = 0; dn < D / 8; ++dn) {
+            if (row0 < p.sq) {
+                const uint32_t hi = pack_bf16x2(o[dn][0], o[dn][1]);
+                *reinterpret_cast<uint32_t*>(p.out + o0 + dn * 8) = hi;
+                *reinterpret_cast<uint32_t*>(p.out_lo + o0 + dn * 8) =
+                    pack_bf16x2(o[dn][0] - bf16_lo_to_f(hi), o[dn][1] - bf16_hi_to_f(hi));
+            }
+            if (row1 < p.sq) {
+                const uint32_t hi = pack_bf16x2(o[dn][2], o[dn][3]);
+                *reinterpret_cast<uint32_t*>(p.out + o1 + dn * 8) = hi;
+                *reinterpret_cast<uint32_t*>(p.out_lo + o1 + dn * 8) =
+                    pack_bf16x2(o[dn][2] - bf16_lo_to_f(hi), o[dn][3] - bf16_hi_to_f(hi));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 template <int D, int NT, bool EXACT>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
     constexpr int LDS = D + 8;
@@ -508,6 +613,10 @@ static void fill_attn_params(AttnParams& p, const mcan_attn_args* a) {
     p.q = reinterpret_cast<const bf16*>(a->q);
     p.k = reinterpret_cast<const bf16*>(a->k);
     p.v = reinterpret_cast<const bf16*>(a->v);
+    p.q_lo = reinterpret_cast<const bf16*>(a->q_lo);
+    p.k_lo = reinterpret_cast<const bf16*>(a->k_lo);
+    p.v_lo = reinterpret_cast<const bf16*>(a->v_lo);
+    p.out_lo = reinterpret_cast<bf16*>(a->out_lo);
     p.ldq = a->ldq; p.ldk = a->ldk; p.ldv = a->ldv;
     p.mask = a->key_mask;
     p.out = reinterpret_cast<bf16*>(a->out);
@@ -572,6 +681,23 @@ extern "C" int mcan_attn_fwd(const mcan_attn_args* a) {
     const int grid = a->batch * a->heads;
     const int sk = a->sk;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
+    if (a->q_lo || a->k_lo || a->v_lo || a->out_lo) {
+        MCAN_REQUIRE(a->q_lo && a->k_lo && a->v_lo && a->out_lo, "mcan_attn_fwd: split precision needs all four lo pointers");
+        MCAN_REQUIRE(a->dropout_p == 0.f, "mcan_attn_fwd: split precision is an inference mode (no dropout)");
+        MCAN_REQUIRE((((uintptr_t)a->q_lo | (uintptr_t)a->k_lo | (uintptr_t)a->v_lo) & 15) == 0 &&
+                         ((uintptr_t)a->out_lo & 3) == 0, "mcan_attn_fwd: lo alignment");
+        const size_t smem2 = 2 * (smem - 16) + 16;
+        static size_t cfg64 = 48 * 1024, cfg128 = 48 * 1024;
+        if (a->head_dim == 64) {
+            if (int rc = set_smem_once(attn_fwd_split_kernel<64>, smem2, &cfg64)) return rc;
+            attn_fwd_split_kernel<64><<<grid, threads, smem2, st>>>(p);
+        } else {
+            if (int rc = set_smem_once(attn_fwd_split_kernel<128>, smem2, &cfg128)) return rc;
+            attn_fwd_split_kernel<128><<<grid, threads, smem2, st>>>(p);
+        }
+        MCAN_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (a->head_dim == 64) MCAN_ATTN_DISPATCH(launch_attn_fwd, 64);
     MCAN_ATTN_DISPATCH(launch_attn_fwd, 128);
 }

@@ -15,7 +15,8 @@ constexpr int kFlatMaxSeq = 128;
 constexpr int kFlatMaxGlimpses = 8;
 
 __global__ void __launch_bounds__(kFlatThreads)
-attflat_pool_fwd_kernel(const bf16* __restrict__ hmid, const float* __restrict__ w2,
+attflat_pool_fwd_kernel(const bf16* __restrict__ hmid, const bf16* __restrict__ hmid_lo,
+                        const float* __restrict__ w2,
                         const float* __restrict__ b2, const uint8_t* __restrict__ mask,
                         const float* __restrict__ x, int S, int H, int M, int G,
                         float* __restrict__ att_w, float* __restrict__ pooled32,
@@ -39,6 +40,13 @@ attflat_pool_fwd_kernel(const bf16* __restrict__ hmid, const float* __restrict__
                        bf16_lo_to_f(hv.y) * w0.z + bf16_hi_to_f(hv.y) * w0.w +
                        bf16_lo_to_f(hv.z) * w1.x + bf16_hi_to_f(hv.z) * w1.y +
                        bf16_lo_to_f(hv.w) * w1.z + bf16_hi_to_f(hv.w) * w1.w;
+                if (hmid_lo != nullptr) {
+                    const uint4 lv = *reinterpret_cast<const uint4*>(hmid_lo + ((long long)b * S + s) * M + c);
+                    acc += bf16_lo_to_f(lv.x) * w0.x + bf16_hi_to_f(lv.x) * w0.y +
+                           bf16_lo_to_f(lv.y) * w0.z + bf16_hi_to_f(lv.y) * w0.w +
+                           bf16_lo_to_f(lv.z) * w1.x + bf16_hi_to_f(lv.z) * w1.y +
+                           bf16_lo_to_f(lv.w) * w1.z + bf16_hi_to_f(lv.w) * w1.w;
+                }
             }
             acc = warp_sum(acc);
             if (lane == 0) s_att[s * G + g] = masked ? -1e9f : acc + b2[g];
@@ -233,17 +241,19 @@ static int check_flat(int batch, int s, int h, int mlp, int g, const char* who) 
 
 using namespace mcan;
 
-extern "C" int mcan_attflat_pool_fwd(const void* hmid, const float* w2, const float* b2,
-                                     const uint8_t* mask, const float* x, int32_t batch, int32_t s,
-                                     int32_t h, int32_t mlp, int32_t glimpses, float* att_w,
-                                     float* pooled_f32, void* pooled_bf16, void* stream) {
+extern "C" int mcan_attflat_pool_fwd(const void* hmid, const void* hmid_lo, const float* w2,
+                                     const float* b2, const uint8_t* mask, const float* x,
+                                     int32_t batch, int32_t s, int32_t h, int32_t mlp,
+                                     int32_t glimpses, float* att_w, float* pooled_f32,
+                                     void* pooled_bf16, void* stream) {
     MCAN_REQUIRE(hmid && w2 && b2 && x && att_w, "mcan_attflat_pool_fwd: null input");
     if (int rc = check_flat(batch, s, h, mlp, glimpses, "mcan_attflat_pool_fwd")) return rc;
     MCAN_REQUIRE((((uintptr_t)hmid | (uintptr_t)w2 | (uintptr_t)x | (uintptr_t)pooled_f32) & 15) == 0 &&
                      ((uintptr_t)pooled_bf16 & 7) == 0,
                  "mcan_attflat_pool_fwd: alignment");
     attflat_pool_fwd_kernel<<<batch, kFlatThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const bf16*>(hmid), w2, b2, mask, x, s, h, mlp, glimpses, att_w, pooled_f32,
+        reinterpret_cast<const bf16*>(hmid), reinterpret_cast<const bf16*>(hmid_lo), w2, b2, mask, x, s, h, mlp,
+        glimpses, att_w, pooled_f32,
         reinterpret_cast<bf16*>(pooled_bf16));
     MCAN_CHECK_CUDA(cudaGetLastError());
     return 0;

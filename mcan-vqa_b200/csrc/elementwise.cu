@@ -42,6 +42,7 @@ struct CastSeg {
     void* dst;
     long long n;            // elements
     long long first_chunk;  // index of this segment's first 4096-element chunk; bit 62 set = fp32 destination
+    void* dst_lo;           // optional bf16(x - bf16(x)) destination (split precision)
 };
 constexpr long long kCastChunk = 4096;
 constexpr long long kCastF32Flag = 1LL << 62;
@@ -64,7 +65,14 @@ cast_multi_kernel(const CastSeg* __restrict__ segs, int nseg, long long total_ch
             for (long long i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
         } else {
             bf16* dst = reinterpret_cast<bf16*>(sg.dst) + off;
-            if ((((uintptr_t)src & 15) | ((uintptr_t)dst & 7)) == 0) {
+            if (sg.dst_lo != nullptr) {
+                bf16* dlo = reinterpret_cast<bf16*>(sg.dst_lo) + off;
+                for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+                    const bf16 hi = __float2bfloat16_rn(src[i]);
+                    dst[i] = hi;
+                    dlo[i] = __float2bfloat16_rn(src[i] - __bfloat162float(hi));
+                }
+            } else if ((((uintptr_t)src & 15) | ((uintptr_t)dst & 7)) == 0) {
                 const long long nv = n >> 2;
                 for (long long i = threadIdx.x; i < nv; i += blockDim.x) {
                     const float4 v = reinterpret_cast<const float4*>(src)[i];

@@ -141,13 +141,20 @@ def _attn_args(q, k, v, key_mask, batch, heads, sq, sk, head_dim, scale, dropout
     return args
 
 
-def attn_fwd(q, k, v, key_mask, out, *, batch, heads, sq, sk, head_dim, scale, dropout_p=0.0, seed=0):
+def attn_fwd(q, k, v, key_mask, out, *, batch, heads, sq, sk, head_dim, scale, dropout_p=0.0, seed=0,
+             q_lo=None, k_lo=None, v_lo=None, out_lo=None):
     """out[b*sq+s, h*d:(h+1)*d] = softmax(mask(Q K^T scale)) V per (batch, head).  q/k/v/out are
     bf16 [rows, >=heads*d] views (column offset already applied by slicing)."""
     lib = capi.load()
     args = _attn_args(q, k, v, key_mask, batch, heads, sq, sk, head_dim, scale, dropout_p, seed)
     _req2d(out, _BF16, "attn out")
     args.out, args.ldo = out.data_ptr(), out.stride(0)
+    if q_lo is not None:    # split precision: lo halves share the hi tensors' strides
+        for hi, lo, nm in ((q, q_lo, "q_lo"), (k, k_lo, "k_lo"), (v, v_lo, "v_lo"), (out, out_lo, "out_lo")):
+            _req2d(lo, _BF16, "attn " + nm)
+            if lo.stride(0) != hi.stride(0):
+                raise capi.McanError("attn %s must share the leading dimension of its hi tensor" % nm)
+        args.q_lo, args.k_lo, args.v_lo, args.out_lo = q_lo.data_ptr(), k_lo.data_ptr(), v_lo.data_ptr(), out_lo.data_ptr()
     capi.check(lib.mcan_attn_fwd(ctypes.byref(args)), "mcan_attn_fwd")
 
 
@@ -193,14 +200,14 @@ def layernorm_bwd(dy, x, mean, sigma, a2, eps, *, dx_f32=None, dx_bf16=None, dro
 
 
 def attflat_pool_fwd(hmid, w2, b2, mask, x, *, batch, s, h, mlp, glimpses, att_w, pooled_f32=None,
-                     pooled_bf16=None):
+                     pooled_bf16=None, hmid_lo=None):
     lib = capi.load()
     _req(hmid, _BF16, "attflat hmid")
     _req(x, _F32, "attflat x")
     _req(w2, _F32, "attflat w2")
     if mask is not None:
         _req(mask, torch.uint8, "attflat mask")
-    capi.check(lib.mcan_attflat_pool_fwd(hmid.data_ptr(), w2.data_ptr(), b2.data_ptr(), _ptr(mask),
+    capi.check(lib.mcan_attflat_pool_fwd(hmid.data_ptr(), _ptr(hmid_lo), w2.data_ptr(), b2.data_ptr(), _ptr(mask),
                                          x.data_ptr(), batch, s, h, mlp, glimpses, att_w.data_ptr(),
                                          _ptr(pooled_f32), _ptr(pooled_bf16), _stream()),
                "mcan_attflat_pool_fwd")
@@ -231,15 +238,18 @@ _CAST_F32_FLAG = 1 << 62
 
 
 def build_cast_table(pairs, device):
-    """pairs = [(dst, src)] with fp32 contiguous src and bf16 (cast) or fp32 (copy) contiguous dst.
+    """pairs = [(dst, src)] or [(dst, src, dst_lo)] with fp32 contiguous src and bf16 (cast) or fp32
+    (copy) contiguous dst; dst_lo (optional bf16) receives the low-order half.
     Returns (int64 table tensor on `device`, num_segments, total_chunks) for cast_multi."""
     rows, chunk = [], 0
-    for dst, src in pairs:
+    for item in pairs:
+        dst, src = item[0], item[1]
+        lo = item[2] if len(item) > 2 else None
         n = src.numel()
         if not (src.is_contiguous() and dst.is_contiguous() and dst.numel() == n and src.dtype == _F32):
             raise capi.McanError("cast table: tensors must be contiguous fp32 -> bf16/fp32 of equal size")
         flag = _CAST_F32_FLAG if dst.dtype == _F32 else 0
-        rows.append([src.data_ptr(), dst.data_ptr(), n, chunk | flag])
+        rows.append([src.data_ptr(), dst.data_ptr(), n, chunk | flag, 0 if lo is None else lo.data_ptr()])
         chunk += (n + CAST_CHUNK - 1) // CAST_CHUNK
     return torch.tensor(rows, dtype=torch.int64).to(device), len(rows), chunk
 

@@ -247,3 +247,32 @@ def test_dropout_statistics_and_determinism():
     c, d = m(x, xm), m(x, xm)
     assert torch.equal(c, d)
     assert _rel_max(a, c) < 1.0 and torch.isfinite(a).all()
+
+
+@pytest.mark.parametrize("model,B", [("small", 48), ("large", 12)])
+def test_net_fp32_mode_logits_and_top1(model, B):
+    """Split-precision inference mode (north star: logits within 1e-4 at fp32, identical top-1 answers).
+    Every tensor-core product is hi*hi + hi*lo + lo*hi on bf16 halves; compared with the fp64 oracle."""
+    import mcan_vqa_b200
+    from core.model.net import Net
+    cfgd = orc.SMALL if model == "small" else orc.LARGE
+    cfg = orc.Cfg(dropout_rate=0.1, **cfgd)
+    token_size, answer_size = 1000, 3129
+    sd = orc.synth_state_dict(cfg, token_size, answer_size, seed=0)
+    v, q, _ = orc.synth_batch(cfg, B, 100, 14, token_size, answer_size, seed=4321, ragged="random")
+    with torch.no_grad():
+        ref = orc.net_forward({k: t.double() for k, t in sd.items()}, v.double(), q, cfg)[0]
+    net = _load_params(Net(cfg, None, token_size, answer_size), sd).eval()
+    mcan_vqa_b200.set_precision("fp32")
+    try:
+        with torch.no_grad():
+            out = net(v.cuda(), q.cuda())[0].cpu().double()
+    finally:
+        mcan_vqa_b200.set_precision("bf16")
+    rel = ((out - ref).abs() / ref.abs().clamp_min(1e-9)).max().item()
+    assert rel < 1e-4, rel
+    assert (out.argmax(1) == ref.argmax(1)).all()          # identical top-1 on every sample
+    with torch.no_grad():
+        bf = net(v.cuda(), q.cuda())[0].cpu().double()
+    agree = (bf.argmax(1) == ref.argmax(1)).double().mean().item()
+    print("fp32-mode max rel err %.2e; bf16-mode top-1 agreement %.3f" % (rel, agree))

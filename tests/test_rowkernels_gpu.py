@@ -127,7 +127,8 @@ def _make_attn(batch, heads, sq, sk, d, kind, seed=0):
 
 
 def _heads(t, batch, s, heads, d):
-    return t.float().reshape(batch, s, heads, d).transpose(1, 2)
+    t = t if t.dtype == torch.float64 else t.float()
+    return t.reshape(batch, s, heads, d).transpose(1, 2)
 
 
 @pytest.mark.parametrize("batch,heads,sq,sk,d,kind", ATTN_CASES)
@@ -244,3 +245,31 @@ def test_cast_and_colsum():
     torch.cuda.synchronize()
     assert (out - y.sum(0)).abs().max() < 1e-2
     assert (out2 - ybf[:, 512:1024].float().sum(0)).abs().max() < 1e-2
+
+
+@pytest.mark.parametrize("batch,heads,sq,sk,d", [(2, 8, 100, 100, 64), (2, 4, 100, 14, 64), (2, 2, 60, 60, 128)])
+def test_attention_fwd_split_precision(batch, heads, sq, sk, d):
+    """hi/lo operands: the kernel must reproduce fp32 attention to ~1e-5, far below bf16 rounding."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    H = heads * d
+    q32 = torch.randn(batch * sq, H, generator=g).cuda()
+    k32 = torch.randn(batch * sk, H, generator=g).cuda()
+    v32 = torch.randn(batch * sk, H, generator=g).cuda()
+    mask = (torch.rand(batch, sk, generator=g) < 0.3).cuda()
+    parts = {}
+    for nm, t in (("q", q32), ("k", k32), ("v", v32)):
+        hi = torch.empty_like(t, dtype=torch.bfloat16); lo = torch.empty_like(t, dtype=torch.bfloat16)
+        ops.cast_bf16(t, hi, lo)
+        parts[nm] = (hi, lo)
+    out = torch.empty(batch * sq, H, device="cuda", dtype=torch.bfloat16)
+    out_lo = torch.empty_like(out)
+    ops.attn_fwd(parts["q"][0], parts["k"][0], parts["v"][0], mask.to(torch.uint8).contiguous(), out, batch=batch,
+                 heads=heads, sq=sq, sk=sk, head_dim=d, scale=1.0 / math.sqrt(d),
+                 q_lo=parts["q"][1], k_lo=parts["k"][1], v_lo=parts["v"][1], out_lo=out_lo)
+    ref = _attn_ref(_heads(q32.double(), batch, sq, heads, d).double(), _heads(k32.double(), batch, sk, heads, d).double(),
+                    _heads(v32.double(), batch, sk, heads, d).double(), mask, 1.0 / math.sqrt(d))
+    torch.cuda.synchronize()
+    got = _heads(out, batch, sq, heads, d).double() + _heads(out_lo, batch, sq, heads, d).double()
+    err = (got - ref).abs().max().item() / ref.abs().max().item()
+    assert err < 5e-5, err
