@@ -15,6 +15,7 @@ from core.model.mca import MCA_ED, MCAClassifier
 from core.model.net_utils import FC, MLP, LayerNorm, TCLinear  # noqa: F401
 from mcan_vqa_b200 import autograd as _ag
 from mcan_vqa_b200.autograd import cfg_get
+from mcan_vqa_b200 import blocks as _blocks
 from mcan_vqa_b200.blocks import LinearParams, refresh_scope
 
 
@@ -79,7 +80,12 @@ class _VQABase(nn.Module):
     def _features_impl(self, v, ques_ix):
         q_mask = _make_mask(ques_ix.unsqueeze(2))
         v_mask = _make_mask(v)
-        q, _ = self.lstm(self.embedding(ques_ix))
+        if _blocks.PRECISION == "fp32" and not torch.is_grad_enabled():
+            # fp32-grade inference: cuDNN's RNN GEMMs default to TF32 (1e-3); switch that off
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                q, _ = self.lstm(self.embedding(ques_ix))
+        else:
+            q, _ = self.lstm(self.embedding(ques_ix))
         v = self.img_feat_linear(v)
         q, v = self.backbone(q, v, q_mask, v_mask)
         lang, q_w = self.attflat_lang(q, q_mask)
