@@ -276,3 +276,32 @@ def test_net_fp32_mode_logits_and_top1(model, B):
         bf = net(v.cuda(), q.cuda())[0].cpu().double()
     agree = (bf.argmax(1) == ref.argmax(1)).double().mean().item()
     print("fp32-mode max rel err %.2e; bf16-mode top-1 agreement %.3f" % (rel, agree))
+
+
+def test_top1_agreement_1024_samples_small():
+    """North star: identical top-1 answer indices on >= 99.9 % of samples (fp32 mode), MCAN-small,
+    ragged inputs, vs the fp32 oracle (the reference's own precision)."""
+    import mcan_vqa_b200
+    from core.model.net import Net
+    cfg = orc.Cfg(dropout_rate=0.1, **orc.SMALL)
+    token_size, answer_size, B, nb = 1000, 3129, 64, 16
+    sd = orc.synth_state_dict(cfg, token_size, answer_size, seed=0)
+    net = _load_params(Net(cfg, None, token_size, answer_size), sd).eval()
+    same32 = same16 = total = 0
+    for i in range(nb):
+        v, q, _ = orc.synth_batch(cfg, B, 100, 14, token_size, answer_size, seed=9000 + i,
+                                  ragged="prefix" if i % 2 else "random")
+        with torch.no_grad():
+            ref = orc.net_forward(sd, v, q, cfg)[0].argmax(1)
+            bf = net(v.cuda(), q.cuda())[0].argmax(1).cpu()
+            mcan_vqa_b200.set_precision("fp32")
+            try:
+                hi = net(v.cuda(), q.cuda())[0].argmax(1).cpu()
+            finally:
+                mcan_vqa_b200.set_precision("bf16")
+        same32 += int((hi == ref).sum())
+        same16 += int((bf == ref).sum())
+        total += B
+    print("top-1 agreement over %d samples: fp32 mode %.4f, bf16 mode %.4f" % (total, same32 / total, same16 / total))
+    assert same32 / total >= 0.999
+    assert same16 / total >= 0.95
