@@ -220,13 +220,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the MCAN hot path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    reserve = int(os.environ.get("MCAN_DP_RESERVE_SMS", "8"))
     if world > 1:
+        # the overlapped gradient all-reduce gets `reserve` SMs of its own (see mcan_set_sm_limit)
+        if reserve > 0:
+            os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
         dist.init_process_group("nccl", device_id=dev)
 
     import __graft_entry__
     __graft_entry__.build()
-    from mcan_vqa_b200 import capi
+    from mcan_vqa_b200 import capi, ops
     from mcan_vqa_b200.train import Trainer
+    if world > 1 and reserve > 0:
+        ops.set_sm_limit(ops.num_sms() - reserve)
 
     cfg = Cfg(MODELS[args.model])
     torch.manual_seed(0)           # identical random-init replicas on every rank
@@ -337,6 +343,7 @@ def main():
             "config": {"workload": "MCAN-%s full training step (Net fwd + BCE(sum) + bwd + AdamW), batch %d per GPU, "
                                    "100x2048 region feats, 14 tokens, 3129 answers, dropout 0.1, random init" % (args.model, BATCH),
                        "global_batch": BATCH * world, "parallelism": "dp%d" % world, "launch": graph_note,
+                       "sms_reserved_for_nccl": reserve if world > 1 else 0,
                        "l2": "working set per step (fp32 masters + bf16 copies + activations, > 1 GB) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -42,6 +42,10 @@ int mcan_version(void);
 const char* mcan_last_error(void);
 /* number of SMs of the current device (persistent kernels size their grids with it) */
 int mcan_num_sms(void);
+/* Persistent kernels use at most `sms` SMs (0 = all).  Data-parallel training leaves a few SMs to
+ * the NCCL all-reduce that overlaps the backward pass: the statically scheduled GEMM would
+ * otherwise wait a whole extra wave for the SMs NCCL occupies. */
+int mcan_set_sm_limit(int sms);
 
 /* -- G1/G2/G3: tcgen05 GEMM with fused epilogue --------------------------------------
  * D[M,N] = epilogue( sum_{s<num_seg} A_s[M,K] * B_s[N,K]^T )         (fp32 accumulate in TMEM)

@@ -101,6 +101,7 @@ SYMBOLS = {
     "mcan_version": (ctypes.c_int, []),
     "mcan_last_error": (ctypes.c_char_p, []),
     "mcan_num_sms": (ctypes.c_int, []),
+    "mcan_set_sm_limit": (ctypes.c_int, [ctypes.c_int]),
     "mcan_gemm": (ctypes.c_int, [ctypes.POINTER(GemmArgs)]),
     "mcan_attn_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs)]),
     "mcan_attn_bwd": (ctypes.c_int, [ctypes.POINTER(AttnBwdArgs)]),

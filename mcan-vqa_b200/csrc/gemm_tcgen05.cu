@@ -588,7 +588,16 @@ static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t
     return 0;
 }
 
+static int g_sm_limit = 0;   // 0 = use every SM (set through mcan_set_sm_limit)
+
+int device_num_sms_raw();
+
 int device_num_sms() {
+    const int raw = device_num_sms_raw();
+    return (g_sm_limit > 0 && g_sm_limit < raw) ? g_sm_limit : raw;
+}
+
+int device_num_sms_raw() {
     static int sms[64] = {0};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
@@ -672,6 +681,12 @@ static int pick_splits(int64_t tiles, int kblocks, int slots) {
 }  // namespace mcan
 
 using namespace mcan;
+
+extern "C" int mcan_set_sm_limit(int sms) {
+    MCAN_REQUIRE(sms >= 0, "mcan_set_sm_limit: %d", sms);
+    mcan::g_sm_limit = sms & ~1;   // keep it even: CTA pairs
+    return 0;
+}
 
 extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     MCAN_REQUIRE(a != nullptr, "mcan_gemm: null args");

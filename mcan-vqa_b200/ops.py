@@ -56,6 +56,11 @@ def num_sms():
     return capi.load().mcan_num_sms()
 
 
+def set_sm_limit(sms):
+    """Persistent kernels use at most `sms` SMs (0 = all); see include/mcan_b200.h."""
+    capi.check(capi.load().mcan_set_sm_limit(int(sms)), "mcan_set_sm_limit")
+
+
 def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, seed=0, gate=None,
          gate_scale=1.0, resid=None, out_f32=None, out_bf16=None, out_lo=None, accumulate=False,
          split_k=0, block_n=0, cta_group=0):
