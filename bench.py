@@ -158,9 +158,12 @@ def run_reference(args):
 
 def gemm_roofline(trainer, batch_dev, peaks):
     """One instrumented training step: CUDA events around every tcgen05 GEMM launch (on the launching
-    stream).  achieved = sum of algorithmic FLOPs / sum of launch durations."""
+    stream).  achieved = sum of algorithmic FLOPs / sum of launch durations.  A 40 ms single-CTA spin
+    kernel is queued first so that the host runs ahead of the device: otherwise an eager step is
+    launch-bound and every event pair would also time the host gap in front of its kernel."""
     import torch
-    from mcan_vqa_b200 import ops
+    from mcan_vqa_b200 import capi, ops
+    lib = capi.load()
     records = []
     real = ops.gemm
 
@@ -180,6 +183,7 @@ def gemm_roofline(trainer, batch_dev, peaks):
     try:
         for _ in range(2):
             records.clear()
+            capi.check(lib.mcan_debug_hog(1, int(0.040 * 1.9e9), 1024, torch.cuda.current_stream().cuda_stream), "hog")
             trainer._raw_step(*batch_dev)
             torch.cuda.synchronize()
     finally:
@@ -220,9 +224,12 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (the MCAN hot path has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    reserve = int(os.environ.get("MCAN_DP_RESERVE_SMS", "8"))
+    # Data parallel: the gradient all-reduce overlaps the backward pass and takes a few SMs away from
+    # the persistent GEMMs.  Default: dynamic tile schedule (an occupied SM just claims fewer tiles).
+    # Alternative (MCAN_DP_RESERVE_SMS=n): static schedule on #SMs - n, NCCL capped at n CTAs.
+    reserve = int(os.environ.get("MCAN_DP_RESERVE_SMS", "0"))
+    dynamic = world > 1 and reserve == 0 and os.environ.get("MCAN_GEMM_DYNAMIC", "1") != "0"
     if world > 1:
-        # the overlapped gradient all-reduce gets `reserve` SMs of its own (see mcan_set_sm_limit)
         if reserve > 0:
             os.environ.setdefault("NCCL_MAX_CTAS", str(reserve))
         dist.init_process_group("nccl", device_id=dev)
@@ -233,6 +240,7 @@ def main():
     from mcan_vqa_b200.train import Trainer
     if world > 1 and reserve > 0:
         ops.set_sm_limit(ops.num_sms() - reserve)
+    ops.set_gemm_schedule(dynamic)
 
     cfg = Cfg(MODELS[args.model])
     torch.manual_seed(0)           # identical random-init replicas on every rank
@@ -344,6 +352,7 @@ def main():
                                    "100x2048 region feats, 14 tokens, 3129 answers, dropout 0.1, random init" % (args.model, BATCH),
                        "global_batch": BATCH * world, "parallelism": "dp%d" % world, "launch": graph_note,
                        "sms_reserved_for_nccl": reserve if world > 1 else 0,
+                       "gemm_tile_schedule": "dynamic" if dynamic else "static",
                        "l2": "working set per step (fp32 masters + bf16 copies + activations, > 1 GB) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

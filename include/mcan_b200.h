@@ -46,6 +46,15 @@ int mcan_num_sms(void);
  * the NCCL all-reduce that overlaps the backward pass: the statically scheduled GEMM would
  * otherwise wait a whole extra wave for the SMs NCCL occupies. */
 int mcan_set_sm_limit(int sms);
+/* Tile schedule of the persistent GEMM.  0 (default): static round robin -- no atomics on the
+ * critical path, best when the GEMM owns the GPU.  1: dynamic -- CTAs claim work units from a
+ * global counter, so an SM that a co-running kernel (the overlapped NCCL all-reduce of
+ * data-parallel training) holds simply claims fewer units instead of stalling a whole wave. */
+int mcan_set_gemm_schedule(int dynamic);
+/* Programmatic dependent launch between consecutive kernels of the library (default on): the next
+ * kernel's launch latency and prologue overlap the previous kernel's tail; every kernel waits for
+ * its predecessors' completion (griddepcontrol.wait) before touching global memory. */
+int mcan_set_pdl(int enabled);
 
 /* -- G1/G2/G3: tcgen05 GEMM with fused epilogue --------------------------------------
  * D[M,N] = epilogue( sum_{s<num_seg} A_s[M,K] * B_s[N,K]^T )         (fp32 accumulate in TMEM)
@@ -216,6 +225,9 @@ int mcan_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64_t ld, floa
 /* out[c] += sum_r x[r,c]   (x fp32) */
 int mcan_colsum_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out,
                     void* stream);
+
+/* experiment helper (tools/contention_bench.py): keep `ctas` SMs busy for `cycles` clocks */
+int mcan_debug_hog(int32_t ctas, int64_t cycles, int32_t smem_bytes, void* stream);
 
 #ifdef __cplusplus
 }

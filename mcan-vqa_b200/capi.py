@@ -102,6 +102,8 @@ SYMBOLS = {
     "mcan_last_error": (ctypes.c_char_p, []),
     "mcan_num_sms": (ctypes.c_int, []),
     "mcan_set_sm_limit": (ctypes.c_int, [ctypes.c_int]),
+    "mcan_set_gemm_schedule": (ctypes.c_int, [ctypes.c_int]),
+    "mcan_set_pdl": (ctypes.c_int, [ctypes.c_int]),
     "mcan_gemm": (ctypes.c_int, [ctypes.POINTER(GemmArgs)]),
     "mcan_attn_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs)]),
     "mcan_attn_bwd": (ctypes.c_int, [ctypes.POINTER(AttnBwdArgs)]),
@@ -118,6 +120,7 @@ SYMBOLS = {
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcan_cast_bf16": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "mcan_cast_multi": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_void_p]),
+    "mcan_debug_hog": (ctypes.c_int, [c_int32, c_int64, c_int32, c_void_p]),
     "mcan_gate_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "mcan_colsum_bf16": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
     "mcan_colsum_f32": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),
@@ -144,6 +147,8 @@ def load():
         fn = getattr(lib, name)  # AttributeError here = header/library mismatch
         fn.restype = restype
         fn.argtypes = argtypes
+    if os.environ.get("MCAN_PDL", "1") == "0":      # debugging / A-B timing: plain stream-ordered launches
+        lib.mcan_set_pdl(0)
     _lib = lib
     return lib
 

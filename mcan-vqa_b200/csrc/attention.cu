@@ -231,6 +231,8 @@ __device__ __forceinline__ void softmax_tile(float (&acc)[NT][4], uint32_t maske
 // NT = compile-time number of 8-key tiles; EXACT: the runtime tile count equals NT (no guards).
 template <int D, int NT, bool EXACT>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int LDS = D + 8;
     extern __shared__ __align__(16) uint8_t smem_attn[];
     const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
@@ -324,6 +326,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 // ------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(128) attn_fwd_split_kernel(const AttnParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int LDS = D + 8;
     constexpr int NT = kAttnMaxNT;
     extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -419,6 +423,8 @@ __global__ void __launch_bounds__(128) attn_fwd_split_kernel(const AttnParams p)
 // ------------------------------------------------------------------------------------------
 template <int D, int NT, bool EXACT>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     constexpr int LDS = D + 8;
     extern __shared__ __align__(16) uint8_t smem_attn[];
     const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
@@ -646,16 +652,14 @@ template <int D, int NT, bool EXACT>
 static int launch_attn_fwd(const AttnParams& p, int grid, int threads, size_t smem, cudaStream_t st) {
     static size_t configured = 48 * 1024;
     if (int rc = set_smem_once(attn_fwd_kernel<D, NT, EXACT>, smem, &configured)) return rc;
-    attn_fwd_kernel<D, NT, EXACT><<<grid, threads, smem, st>>>(p);
-    MCAN_CHECK_CUDA(cudaGetLastError());
+    MCAN_CHECK_CUDA(launch_kernel(attn_fwd_kernel<D, NT, EXACT>, dim3(grid), dim3(threads), smem, st, p));
     return 0;
 }
 template <int D, int NT, bool EXACT>
 static int launch_attn_bwd(const AttnParams& p, int grid, int threads, size_t smem, cudaStream_t st) {
     static size_t configured = 48 * 1024;
     if (int rc = set_smem_once(attn_bwd_kernel<D, NT, EXACT>, smem, &configured)) return rc;
-    attn_bwd_kernel<D, NT, EXACT><<<grid, threads, smem, st>>>(p);
-    MCAN_CHECK_CUDA(cudaGetLastError());
+    MCAN_CHECK_CUDA(launch_kernel(attn_bwd_kernel<D, NT, EXACT>, dim3(grid), dim3(threads), smem, st, p));
     return 0;
 }
 // tile-count specialisations: 2 (<= 16 keys: question), 14 (<= 112 keys: 100 image regions), 16 (any)
@@ -690,10 +694,10 @@ extern "C" int mcan_attn_fwd(const mcan_attn_args* a) {
         static size_t cfg64 = 48 * 1024, cfg128 = 48 * 1024;
         if (a->head_dim == 64) {
             if (int rc = set_smem_once(attn_fwd_split_kernel<64>, smem2, &cfg64)) return rc;
-            attn_fwd_split_kernel<64><<<grid, threads, smem2, st>>>(p);
+            MCAN_CHECK_CUDA(launch_kernel(attn_fwd_split_kernel<64>, dim3(grid), dim3(threads), smem2, st, p));
         } else {
             if (int rc = set_smem_once(attn_fwd_split_kernel<128>, smem2, &cfg128)) return rc;
-            attn_fwd_split_kernel<128><<<grid, threads, smem2, st>>>(p);
+            MCAN_CHECK_CUDA(launch_kernel(attn_fwd_split_kernel<128>, dim3(grid), dim3(threads), smem2, st, p));
         }
         MCAN_CHECK_CUDA(cudaGetLastError());
         return 0;

@@ -21,6 +21,8 @@ attflat_pool_fwd_kernel(const bf16* __restrict__ hmid, const bf16* __restrict__ 
                         const float* __restrict__ x, int S, int H, int M, int G,
                         float* __restrict__ att_w, float* __restrict__ pooled32,
                         bf16* __restrict__ pooledbf) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float s_att[kFlatMaxSeq * kFlatMaxGlimpses];
     const int b = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -116,6 +118,8 @@ attflat_pool_bwd_kernel(const float* __restrict__ dpooled, const bf16* __restric
                         int M, int G, float gate_scale, float* __restrict__ dx,
                         bf16* __restrict__ dhmid, float* __restrict__ dw2,
                         float* __restrict__ db2) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float s_att[kFlatMaxSeq * kFlatMaxGlimpses];
     __shared__ float s_dl[kFlatMaxSeq * kFlatMaxGlimpses];  // d att_w, then d logit
     const int b = blockIdx.x;
@@ -251,11 +255,10 @@ extern "C" int mcan_attflat_pool_fwd(const void* hmid, const void* hmid_lo, cons
     MCAN_REQUIRE((((uintptr_t)hmid | (uintptr_t)w2 | (uintptr_t)x | (uintptr_t)pooled_f32) & 15) == 0 &&
                      ((uintptr_t)pooled_bf16 & 7) == 0,
                  "mcan_attflat_pool_fwd: alignment");
-    attflat_pool_fwd_kernel<<<batch, kFlatThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const bf16*>(hmid), reinterpret_cast<const bf16*>(hmid_lo), w2, b2, mask, x, s, h, mlp,
-        glimpses, att_w, pooled_f32,
-        reinterpret_cast<bf16*>(pooled_bf16));
-    MCAN_CHECK_CUDA(cudaGetLastError());
+    MCAN_CHECK_CUDA(launch_kernel(attflat_pool_fwd_kernel, dim3(batch), dim3(kFlatThreads), 0,
+                                  reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const bf16*>(hmid),
+                                  reinterpret_cast<const bf16*>(hmid_lo), w2, b2, mask, x, s, h, mlp, glimpses,
+                                  att_w, pooled_f32, reinterpret_cast<bf16*>(pooled_bf16)));
     return 0;
 }
 
@@ -269,9 +272,9 @@ extern "C" int mcan_attflat_pool_bwd(const float* dpooled, const void* hmid, con
     MCAN_REQUIRE((((uintptr_t)dpooled | (uintptr_t)hmid | (uintptr_t)w2 | (uintptr_t)x | (uintptr_t)dx |
                    (uintptr_t)dhmid) & 15) == 0,
                  "mcan_attflat_pool_bwd: alignment");
-    attflat_pool_bwd_kernel<<<batch, kFlatThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dpooled, reinterpret_cast<const bf16*>(hmid), w2, mask, x, att_w, s, h, mlp, glimpses,
-        gate_scale, dx, reinterpret_cast<bf16*>(dhmid), dw2, db2);
-    MCAN_CHECK_CUDA(cudaGetLastError());
+    MCAN_CHECK_CUDA(launch_kernel(attflat_pool_bwd_kernel, dim3(batch), dim3(kFlatThreads), 0,
+                                  reinterpret_cast<cudaStream_t>(stream), dpooled,
+                                  reinterpret_cast<const bf16*>(hmid), w2, mask, x, att_w, s, h, mlp, glimpses,
+                                  gate_scale, dx, reinterpret_cast<bf16*>(dhmid), dw2, db2));
     return 0;
 }

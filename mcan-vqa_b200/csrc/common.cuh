@@ -41,6 +41,40 @@ void set_last_error(const char* fmt, ...);
     } while (0)
 
 // ---------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library
+//   * calls pdl_launch_dependents() first: once all CTAs of a grid have done so, the NEXT kernel
+//     of the stream may start being scheduled onto SMs as they drain -- its launch latency and
+//     prologue (barrier init, TMEM allocation, descriptor prefetch) hide behind this grid's tail;
+//   * calls pdl_wait() before its first access to global memory: it returns when all
+//     prerequisite grids have COMPLETED and their writes are visible, so no data hazard is
+//     introduced (completion is transitive because every kernel waits before it finishes).
+// Both are no-ops for a kernel launched without the attribute (mcan_set_pdl(0)).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();   // c_api.cu
+
+// <<<>>> replacement: launches `kernel` with the PDL attribute when enabled.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------
 // dropout: counter-based hash, 16 random bits per element.
 //   keep(idx) <=> u16(idx) >= thr,   thr = round(p * 65536)
 // Forward epilogues and backward kernels regenerate the same mask from
@@ -289,6 +323,54 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
         "}\n" ::"r"(smem_u32(bar)),
         "r"(cta)
         : "memory");
+}
+
+// cluster-scope release / acquire variants: used where DATA written to a peer CTA's shared memory
+// must be visible to the thread that wakes up on the barrier (dynamic tile scheduler)
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(cta)
+        : "memory");
+}
+__device__ __forceinline__ void st_shared_remote_u32(uint32_t* local_addr, uint32_t cta, uint32_t val) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "st.shared::cluster.u32 [ra], %2;\n"
+        "}\n" ::"r"(smem_u32(local_addr)),
+        "r"(cta), "r"(val)
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_acq_cluster(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_acq_cluster(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait_acq_cluster(bar, parity)) return;
+    long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait_acq_cluster(bar, parity)) {
+        if ((++spins & 0x3FFU) == 0 && (clock64() - t0) > 4000000000LL) {
+            printf("mcan: scheduler mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
+                   (int)threadIdx.x);
+            __trap();
+        }
+    }
 }
 
 // ---- UMMA descriptors (sm_100 "version 1" shared-memory matrix descriptor) ----

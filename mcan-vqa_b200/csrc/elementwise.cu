@@ -10,6 +10,8 @@ int device_num_sms();
 __global__ void __launch_bounds__(256)
 cast_bf16_kernel(const float* __restrict__ x, long long n, bf16* __restrict__ hi,
                  bf16* __restrict__ lo) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long nv = n >> 2;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
@@ -49,6 +51,8 @@ constexpr long long kCastF32Flag = 1LL << 62;
 
 __global__ void __launch_bounds__(256)
 cast_multi_kernel(const CastSeg* __restrict__ segs, int nseg, long long total_chunks) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long chunk = blockIdx.x; chunk < total_chunks; chunk += gridDim.x) {
         int lo = 0, hi = nseg - 1;
         while (lo < hi) {   // last segment whose first_chunk <= chunk
@@ -90,10 +94,22 @@ cast_multi_kernel(const CastSeg* __restrict__ segs, int nseg, long long total_ch
     }
 }
 
+// Debug / experiment helper: occupies `gridDim.x` SMs (one CTA each, large dynamic smem) for
+// `cycles` clock cycles.  Used by tools/contention_bench.py to emulate a co-running collective.
+__global__ void hog_kernel(long long cycles, int* sink) {
+    extern __shared__ uint8_t hog_smem[];
+    const long long t0 = clock64();
+    int x = 0;
+    while (clock64() - t0 < cycles) x += hog_smem[threadIdx.x & 63];
+    if (x == 123456789) *sink = x;
+}
+
 // out = act > 0 ? dy * scale : 0   (backward through ReLU + dropout using the saved activation)
 __global__ void __launch_bounds__(256)
 gate_bf16_kernel(const float* __restrict__ dy, const bf16* __restrict__ act, float scale,
                  bf16* __restrict__ out, long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         out[i] = __float2bfloat16_rn(__bfloat162float(act[i]) > 0.f ? dy[i] * scale : 0.f);
@@ -104,6 +120,8 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ x, long long rows, long long cols, long long ld,
               float* __restrict__ out, int vec_ok) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float s_part[8][32 * VEC + 1];
     const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
     const long long c0 = ((long long)blockIdx.x * 32 + cg) * VEC;
@@ -175,9 +193,9 @@ static int launch_colsum(const T* x, int64_t rows, int64_t cols, int64_t ld, flo
     const long long maxy = (rows + 63) / 64;
     if (gy > maxy) gy = maxy;
     if (gy < 1) gy = 1;
-    colsum_kernel<T, VEC><<<dim3(gx, (unsigned)gy), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, rows, cols, ld, out, vec_ok);
-    MCAN_CHECK_CUDA(cudaGetLastError());
+    MCAN_CHECK_CUDA(launch_kernel(colsum_kernel<T, VEC>, dim3(gx, (unsigned)gy), dim3(256), 0,
+                                  reinterpret_cast<cudaStream_t>(stream), x, (long long)rows, (long long)cols,
+                                  (long long)ld, out, vec_ok));
     return 0;
 }
 
@@ -193,9 +211,9 @@ extern "C" int mcan_cast_bf16(const float* x, int64_t n, void* hi, void* lo, voi
     long long blocks = ((n >> 2) + 255) / 256;
     if (blocks > 8LL * sms) blocks = 8LL * sms;
     if (blocks < 1) blocks = 1;
-    cast_bf16_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        x, n, reinterpret_cast<bf16*>(hi), reinterpret_cast<bf16*>(lo));
-    MCAN_CHECK_CUDA(cudaGetLastError());
+    MCAN_CHECK_CUDA(launch_kernel(cast_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0,
+                                  reinterpret_cast<cudaStream_t>(stream), x, (long long)n,
+                                  reinterpret_cast<bf16*>(hi), reinterpret_cast<bf16*>(lo)));
     return 0;
 }
 
@@ -216,9 +234,9 @@ extern "C" int mcan_gate_bf16(const float* dy, const void* act, float scale, voi
     MCAN_REQUIRE(sms > 0, "mcan_gate_bf16: no CUDA device");
     long long blocks = (n + 255) / 256;
     if (blocks > 16LL * sms) blocks = 16LL * sms;
-    gate_bf16_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        dy, reinterpret_cast<const bf16*>(act), scale, reinterpret_cast<bf16*>(out), n);
-    MCAN_CHECK_CUDA(cudaGetLastError());
+    MCAN_CHECK_CUDA(launch_kernel(gate_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0,
+                                  reinterpret_cast<cudaStream_t>(stream), dy, reinterpret_cast<const bf16*>(act),
+                                  scale, reinterpret_cast<bf16*>(out), (long long)n));
     return 0;
 }
 
@@ -228,8 +246,22 @@ extern "C" int mcan_cast_multi(const void* seg_table_dev, int32_t num_segments, 
     const int sms = device_num_sms();
     MCAN_REQUIRE(sms > 0, "mcan_cast_multi: no CUDA device");
     long long blocks = total_chunks < 16LL * sms ? total_chunks : 16LL * sms;
-    cast_multi_kernel<<<(int)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const CastSeg*>(seg_table_dev), num_segments, total_chunks);
+    MCAN_CHECK_CUDA(launch_kernel(cast_multi_kernel, dim3((unsigned)blocks), dim3(256), 0,
+                                  reinterpret_cast<cudaStream_t>(stream),
+                                  reinterpret_cast<const CastSeg*>(seg_table_dev), (int)num_segments,
+                                  (long long)total_chunks));
+    return 0;
+}
+
+extern "C" int mcan_debug_hog(int32_t ctas, int64_t cycles, int32_t smem_bytes, void* stream) {
+    static int* sink = nullptr;
+    if (!sink) MCAN_CHECK_CUDA(cudaMalloc(&sink, sizeof(int)));
+    static int configured = 0;
+    if (smem_bytes > configured) {
+        MCAN_CHECK_CUDA(cudaFuncSetAttribute(hog_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        configured = smem_bytes;
+    }
+    hog_kernel<<<ctas, 64, smem_bytes, reinterpret_cast<cudaStream_t>(stream)>>>(cycles, sink);
     MCAN_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

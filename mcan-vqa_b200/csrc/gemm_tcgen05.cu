@@ -11,12 +11,17 @@
 // warps 2..9 = epilogue (two warps per TMEM lane quarter, alternating 64-column chunks).  Pipelines: smem ring full/empty
 // (TMA <-> MMA) and a double-buffered TMEM accumulator full/empty (MMA <-> epilogue), so the
 // epilogue of tile i overlaps the main loop of tile i+1.  Grid = min(#work units, #SMs);
-// work unit = (output tile, K split), statically strided over the CTAs.
+// work unit = (output tile, K split), claimed DYNAMICALLY from a global counter by the leader's
+// producer thread and broadcast to every role (of both CTAs of a pair) through a small smem ring:
+// a CTA that starts late -- because a co-running kernel, e.g. the NCCL all-reduce that overlaps
+// the backward pass, holds its SM -- simply claims fewer units.  (A static round-robin schedule
+// made every GEMM 1.5x slower as soon as another kernel pinned 4 SMs.)
 //
 // Tile 128 x BLOCK_N (128 | 256) x 64.  Operand tiles are TMA boxes with the 128-byte swizzle:
 //   K-major  tile [rows x 64 k]  : one box {64, rows}; UMMA desc SBO = 1024 B, k-step = +32 B
 //   MN-major tile [64 k x rows]  : rows/64 boxes {64 mn, 64 k} of 8 KiB; UMMA desc
 //                                  LBO = 8 KiB (next 64 mn), SBO = 1024 B (next 8 k), k-step = +2 KiB
+#include <atomic>
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
@@ -30,6 +35,7 @@ namespace mcan {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
+constexpr int kSchedStages = 4;      // depth of the work-unit broadcast ring (dynamic tile scheduler)
 constexpr int kEpilogueWarps = 8;   // two warps per TMEM lane quarter, alternating 64-column chunks
 constexpr int kGemmThreads = 64 + 32 * kEpilogueWarps;
 
@@ -58,6 +64,7 @@ struct alignas(64) GemmParams {
     long long ldo_bf16;
     int accumulate;
     int debug;   // bit0: skip all global stores (profiling experiments only)
+    int* tile_counter;   // dynamic tile scheduler: next unclaimed work unit (0 at launch, reset by the last claim)
 };
 
 // CG = CTAs per MMA (cta_group): 1 = one SM per 128 x BLOCK_N tile, 2 = a CTA pair computes a
@@ -71,7 +78,7 @@ struct GemmCfg {
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (192 * 1024) / kStageBytes;
     static constexpr uint32_t kTmemCols = 2 * BLOCK_N;
-    static constexpr uint32_t kBarrierBytes = (2 * kStages + 4) * 8 + 16;
+    static constexpr uint32_t kBarrierBytes = (2 * kStages + 4 + 2 * kSchedStages) * 8 + 16 + 4 * kSchedStages;
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarrierBytes;
 };
 
@@ -338,6 +345,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     // dynamic window starts at the (1024-aligned) base of the CTA's shared memory.
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw;
+    pdl_launch_dependents();   // the next kernel's launch + prologue may overlap this grid (see common.cuh)
     if ((smem_u32(smem) & 1023U) != 0) {
         if (threadIdx.x == 0) printf("mcan gemm: dynamic smem base not 1024-byte aligned\n");
         __trap();
@@ -346,7 +354,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full_bar = empty_bar + kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* sched_full = tmem_empty_bar + 2;
+    uint64_t* sched_empty = sched_full + kSchedStages;
+    uint32_t* sched_unit = reinterpret_cast<uint32_t*>(sched_empty + kSchedStages);
+    uint32_t* tmem_slot = sched_unit + kSchedStages;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -369,6 +380,11 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                 mbar_init(&tmem_full_bar[s], 1);
                 mbar_init(&tmem_empty_bar[s], kEpilogueWarps * CG);   // CG==2: leader's, both CTAs arrive
             }
+            for (int s = 0; s < kSchedStages; ++s) {
+                mbar_init(&sched_full[s], 1);
+                // consumers: MMA thread + epilogue warps of the leader, producer + epilogue warps of the peer
+                mbar_init(&sched_empty[s], (1 + kEpilogueWarps) * CG);
+            }
             fence_mbar_init();
         }
         __syncwarp();
@@ -384,17 +400,78 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail;
+    // from here on global memory is touched: wait for the prerequisite grids to complete
+    pdl_wait();
 
     const int tiles = p.m_tiles * p.n_tiles;      // m_tiles counts (128*CG)-row tiles
     const int units = tiles * p.splits;
-    const int first_unit = blockIdx.x / CG, unit_stride = gridDim.x / CG;
+    const int nclusters = gridDim.x / CG;
+    // p.tile_counter == nullptr: static schedule (cluster c takes units c, c + nclusters, ...), no
+    // atomics and no broadcast on the critical path -- the default when nothing else shares the GPU.
+    const bool dyn = p.tile_counter != nullptr;
+    int sunit = (int)blockIdx.x / CG;
+    int sslot = 0;            // position in the work-unit ring (every role walks it in lock step)
+    uint32_t sphase = 0;
+    // consumer side of the ring: returns the next work unit (>= units: no more work)
+    auto next_unit = [&]() -> int {
+        if (!dyn) {
+            const int u = sunit;
+            sunit += nclusters;
+            return u;
+        }
+        // the leader's own consumers see a local write (CTA scope is enough and much cheaper);
+        // the peer's consumers need cluster-scope acquire / release
+        if (CG == 2 && !leader) mbar_wait_acq_cluster(&sched_full[sslot], sphase);
+        else mbar_wait(&sched_full[sslot], sphase);
+        const int u = (int)*reinterpret_cast<volatile uint32_t*>(&sched_unit[sslot]);
+        if (CG == 2 && !leader) mbar_arrive_release_cluster(&sched_empty[sslot], 0);
+        else mbar_arrive(&sched_empty[sslot]);
+        if (++sslot == kSchedStages) { sslot = 0; sphase ^= 1; }
+        return u;
+    };
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int unit = first_unit; unit < units; unit += unit_stride) {
+            // Scheduler (leader only): claims run one tile ahead of their publication and publications
+            // one tile ahead of their use, so neither the atomic's round trip to L2 nor the
+            // cross-CTA broadcast latency ever stalls a tile.  Exactly one failing claim per cluster.
+            auto publish = [&](int unit) {
+                if (unit == units + nclusters - 1) atomicExch(p.tile_counter, 0);   // the very last claim
+                mbar_wait(&sched_empty[sslot], sphase ^ 1);
+                sched_unit[sslot] = (uint32_t)unit;
+                if (CG == 2) {
+                    st_shared_remote_u32(&sched_unit[sslot], 1, (uint32_t)unit);
+                    mbar_arrive_release_cluster(&sched_full[sslot], 1);
+                    mbar_arrive_release_cluster(&sched_full[sslot], 0);
+                } else {
+                    mbar_arrive(&sched_full[sslot]);
+                }
+                if (++sslot == kSchedStages) { sslot = 0; sphase ^= 1; }
+            };
+            int c0 = 0, c1 = 0;
+            if (dyn && leader) {
+                c0 = atomicAdd(p.tile_counter, 1);
+                publish(c0);
+                c1 = (c0 < units) ? atomicAdd(p.tile_counter, 1) : c0;
+            }
+            while (true) {
+                int unit;
+                if (dyn && leader) {
+                    unit = c0;
+                    if (unit < units) {
+                        publish(c1);                                        // the tile after this one (or the end marker)
+                        const int c2 = (c1 < units) ? atomicAdd(p.tile_counter, 1) : c1;
+                        c0 = c1;
+                        c1 = c2;
+                    }
+                } else {
+                    unit = next_unit();
+                }
+                if (unit >= units) break;
                 const int tile = unit % tiles, split = unit / tiles;
                 const int m0 = (tile / p.n_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
                 const int n0 = (tile % p.n_tiles) * BLOCK_N + (int)rank * kBRows;
@@ -442,7 +519,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int unit = first_unit; unit < units; unit += unit_stride) {
+            int unit = next_unit();
+            while (unit < units) {
+                // units are published one tile ahead: fetch the next one now, off the critical path
+                const int unit_after = next_unit();
                 const int split = unit / tiles;
                 const int kb0 = (int)((long long)p.kblocks * split / p.splits);
                 const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.splits);
@@ -472,6 +552,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                 // accumulator ready for the epilogue warps (of both CTAs)
                 if (CG == 2) umma_commit_cg2(&tmem_full_bar[acc], 3); else umma_commit(&tmem_full_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                unit = unit_after;
             }
         }
     } else {
@@ -482,7 +563,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int unit = first_unit; unit < units; unit += unit_stride) {
+        int unit = 0;
+        if (lane == 0) unit = next_unit();
+        unit = __shfl_sync(0xffffffffU, unit, 0);
+        while (unit < units) {
+            int unit_after = 0;
+            if (lane == 0) unit_after = next_unit();     // published one tile ahead
+            unit_after = __shfl_sync(0xffffffffU, unit_after, 0);
             const int tile = unit % tiles;
             const int m0 = (tile / p.n_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
             const int n0 = (tile % p.n_tiles) * BLOCK_N;
@@ -495,6 +582,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                 epilogue_tile<BLOCK_N, CG, false>(p, lane, chunk_par, row0, n0, taddr, &tmem_full_bar[acc],
                                                   &tmem_empty_bar[acc], acc_phase, drop_seed);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            unit = unit_after;
         }
     }
 
@@ -609,6 +697,27 @@ int device_num_sms_raw() {
     return sms[dev];
 }
 
+// 0: static round-robin tile schedule, 1: dynamic (work-unit counter).  See mcan_set_gemm_schedule.
+static std::atomic<int> g_dynamic_schedule{0};
+
+// Pool of zero-initialised work-unit counters (one per in-flight launch; each kernel resets its own
+// counter with its last claim).  The only device memory the library owns besides nothing else.
+static int next_tile_counter(int** out) {
+    constexpr int kPool = 256;
+    static int* pool[64] = {nullptr};
+    static unsigned next[64] = {0};
+    int dev = 0;
+    MCAN_CHECK_CUDA(cudaGetDevice(&dev));
+    MCAN_REQUIRE(dev >= 0 && dev < 64, "device index %d", dev);
+    if (pool[dev] == nullptr) {
+        MCAN_CHECK_CUDA(cudaMalloc(&pool[dev], kPool * sizeof(int)));
+        MCAN_CHECK_CUDA(cudaMemset(pool[dev], 0, kPool * sizeof(int)));
+        MCAN_CHECK_CUDA(cudaDeviceSynchronize());
+    }
+    *out = pool[dev] + (next[dev]++ % kPool);
+    return 0;
+}
+
 template <int BLOCK_N, int A_MN, int B_MN, int CG>
 static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
     using Cfg = GemmCfg<BLOCK_N, CG>;
@@ -627,13 +736,15 @@ static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MCAN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
     return 0;
 }
@@ -685,6 +796,11 @@ using namespace mcan;
 extern "C" int mcan_set_sm_limit(int sms) {
     MCAN_REQUIRE(sms >= 0, "mcan_set_sm_limit: %d", sms);
     mcan::g_sm_limit = sms & ~1;   // keep it even: CTA pairs
+    return 0;
+}
+
+extern "C" int mcan_set_gemm_schedule(int dynamic) {
+    mcan::g_dynamic_schedule.store(dynamic ? 1 : 0, std::memory_order_relaxed);
     return 0;
 }
 
@@ -773,6 +889,10 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     p.out_lo = reinterpret_cast<bf16*>(a->out_bf16_lo);
     p.ldo_bf16 = a->ldo_bf16;
     p.accumulate = a->accumulate;
+    p.tile_counter = nullptr;
+    if (g_dynamic_schedule.load(std::memory_order_relaxed)) {
+        if (int rc = next_tile_counter(&p.tile_counter)) return rc;
+    }
     { const char* d = getenv("MCAN_GEMM_DEBUG"); p.debug = d ? atoi(d) : 0; }
 
     const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.splits;

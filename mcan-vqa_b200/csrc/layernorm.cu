@@ -33,6 +33,8 @@ ln_fwd_kernel(const float* __restrict__ x, long long rows, int h, const float* _
               const float* __restrict__ b2, float eps, float* __restrict__ y32,
               bf16* __restrict__ ybf, bf16* __restrict__ ylo, float* __restrict__ mean_out,
               float* __restrict__ sigma_out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long row = (long long)blockIdx.x * kLnWarps + warp;
     if (row >= rows) return;
@@ -101,6 +103,8 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
               float* __restrict__ dx32, bf16* __restrict__ dxbf, uint32_t drop_thr,
               float drop_scale, uint32_t drop_seed_in, const uint32_t* __restrict__ drop_seed_dev,
               float* __restrict__ da2, float* __restrict__ db2, float* __restrict__ dbias) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float s_mean[kLnBwdMaxRows], s_invs[kLnBwdMaxRows], s_mg[kLnBwdMaxRows], s_k2[kLnBwdMaxRows];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = h >> 2;
@@ -206,7 +210,7 @@ extern "C" int mcan_layernorm_fwd(const float* x, int64_t rows, int64_t h, const
     const int grid = (int)((rows + kLnWarps - 1) / kLnWarps);
     bf16* ybf = reinterpret_cast<bf16*>(y_bf16);
     bf16* ylo = reinterpret_cast<bf16*>(y_bf16_lo);
-#define LN_FWD(MV) ln_fwd_kernel<MV><<<grid, kLnWarps * 32, 0, st>>>(x, rows, (int)h, a2, b2, eps, y_f32, ybf, ylo, mean, sigma)
+#define LN_FWD(MV) MCAN_CHECK_CUDA(launch_kernel(ln_fwd_kernel<MV>, dim3(grid), dim3(kLnWarps * 32), 0, st, x, (long long)rows, (int)h, a2, b2, eps, y_f32, ybf, ylo, mean, sigma))
     if (h <= 512) LN_FWD(4);
     else if (h <= 1024) LN_FWD(8);
     else LN_FWD(16);
@@ -237,9 +241,8 @@ extern "C" int mcan_layernorm_bwd(const float* dy, const float* x, const float* 
     const int grid = (int)((rows + rpc - 1) / rpc);
     const uint32_t thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0;
     const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
-    ln_bwd_kernel<<<grid, kLnBwdThreads, 0, st>>>(dy, x, mean, sigma, a2, eps, rows, (int)h, rpc, dx_f32,
-                                                reinterpret_cast<bf16*>(dx_bf16), thr, scale, dropout_seed,
-                                                dropout_seed_dev, da2, db2, dbias);
-    MCAN_CHECK_CUDA(cudaGetLastError());
+    MCAN_CHECK_CUDA(launch_kernel(ln_bwd_kernel, dim3(grid), dim3(kLnBwdThreads), 0, st, dy, x, mean, sigma, a2,
+                                  eps, (long long)rows, (int)h, rpc, dx_f32, reinterpret_cast<bf16*>(dx_bf16), thr,
+                                  scale, dropout_seed, dropout_seed_dev, da2, db2, dbias));
     return 0;
 }

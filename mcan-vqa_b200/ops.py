@@ -61,6 +61,16 @@ def set_sm_limit(sms):
     capi.check(capi.load().mcan_set_sm_limit(int(sms)), "mcan_set_sm_limit")
 
 
+def set_gemm_schedule(dynamic):
+    """Static (False, default) or dynamic (True) tile schedule of the GEMM; see include/mcan_b200.h."""
+    capi.check(capi.load().mcan_set_gemm_schedule(1 if dynamic else 0), "mcan_set_gemm_schedule")
+
+
+def set_pdl(enabled):
+    """Programmatic dependent launch between the library's kernels (default on)."""
+    capi.check(capi.load().mcan_set_pdl(1 if enabled else 0), "mcan_set_pdl")
+
+
 def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, seed=0, gate=None,
          gate_scale=1.0, resid=None, out_f32=None, out_bf16=None, out_lo=None, accumulate=False,
          split_k=0, block_n=0, cta_group=0):

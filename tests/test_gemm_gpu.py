@@ -159,3 +159,29 @@ def test_gemm_strided_views_qkv():
     ref = x.float() @ wqkv[h:2 * h].float().t()
     _close(out[:, h:2 * h], ref, 6e-3, "strided out")
     assert (out[:, :h] == 0).all() and (out[:, 2 * h:] == 0).all()
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (6400, 1024, 1024), (6400, 4096, 1024), (100, 512, 512), (42, 136, 64)])
+@pytest.mark.parametrize("cta_group,block_n", [(1, 128), (1, 256), (2, 128), (2, 256), (0, 0)])
+def test_gemm_dynamic_schedule_matches_static(m, n, k, cta_group, block_n):
+    """The dynamic tile schedule (work-unit counter, used under data parallelism) computes the same
+    tiles as the static one: results are bit-identical, also over repeated launches (the counter
+    must reset itself)."""
+    ops = _ops()
+    a, w = _rand((m, k), 21), _rand((n, k), 22, 0.05)
+    ref = torch.full((m, n), float("nan"), device="cuda")
+    ops.gemm(a, w, out_f32=ref, block_n=block_n, cta_group=cta_group)
+    try:
+        ops.set_gemm_schedule(True)
+        for _ in range(3):
+            out = torch.full((m, n), float("nan"), device="cuda")
+            ops.gemm(a, w, out_f32=out, block_n=block_n, cta_group=cta_group)
+            torch.cuda.synchronize()
+            assert torch.equal(out, ref)
+        acc = torch.zeros((n, k), device="cuda")
+        ops.gemm(_rand((m, n), 23, 0.1), a, a_layout=1, b_layout=1, out_f32=acc, accumulate=True, split_k=3,
+                 block_n=block_n, cta_group=cta_group)
+        torch.cuda.synchronize()
+        _close(acc, _rand((m, n), 23, 0.1).float().t() @ a.float(), 5e-5, "dynamic wgrad split-K")
+    finally:
+        ops.set_gemm_schedule(False)
