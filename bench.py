@@ -177,7 +177,8 @@ def gemm_roofline(trainer, batch_dev, peaks):
         s.record()
         real(a, b, **kw)
         e.record()
-        records.append((2.0 * m * n * k * nseg, s, e))
+        records.append((2.0 * m * n * k * nseg, s, e, (m, n, k, kw.get("a_layout", 0), kw.get("b_layout", 0),
+                                                     sorted(x for x in kw if kw[x] is not None and x not in ("a_layout", "b_layout")))))
 
     ops.gemm = timed
     try:
@@ -190,6 +191,10 @@ def gemm_roofline(trainer, batch_dev, peaks):
         ops.gemm = real
     flops = sum(r[0] for r in records)
     secs = sum(r[1].elapsed_time(r[2]) for r in records) * 1e-3
+    if os.environ.get("MCAN_BENCH_DUMP"):
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", os.environ["MCAN_BENCH_DUMP"]), "w") as f:
+            json.dump([{"shape": r[3], "us": r[1].elapsed_time(r[2]) * 1e3, "flops": r[0]} for r in records], f)
     achieved = flops / secs / 1e12
     peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

@@ -226,6 +226,19 @@ int mcan_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64_t ld, floa
 int mcan_colsum_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out,
                     void* stream);
 
+/* -- fused multi-tensor AdamW (reference core/model/optim.py:58-64) -----------------
+ * One launch updates every fp32 master parameter with torch.optim.AdamW semantics (decoupled weight
+ * decay, bias correction with the step count t) and re-emits, in the same pass, the operand copy
+ * the next forward's GEMMs read.  seg_table_dev: device array of `num_segments` records of seven
+ * 64-bit words {p, g, m, v, shadow, n, first_chunk}: fp32 pointers p (in/out), g (in), m, v (in/out);
+ * shadow = optional copy of the updated p (bf16, or fp32 when bit 62 of first_chunk is set; 0 = none);
+ * n elements; first_chunk = running index of the segment's first 4096-element chunk.
+ * lr_dev / step_dev: device scalars (fp32) holding the learning rate and t >= 1, so a captured CUDA
+ * graph replays with new values. */
+int mcan_adamw_multi(const void* seg_table_dev, int32_t num_segments, int64_t total_chunks,
+                     const float* lr_dev, const float* step_dev, float beta1, float beta2, float eps,
+                     float weight_decay, void* stream);
+
 /* experiment helper (tools/contention_bench.py): keep `ctas` SMs busy for `cycles` clocks */
 int mcan_debug_hog(int32_t ctas, int64_t cycles, int32_t smem_bytes, void* stream);
 

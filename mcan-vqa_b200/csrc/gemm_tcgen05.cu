@@ -7,15 +7,20 @@
 // from the (out,in) weight) and wgrad (both operands read MN-major straight from the
 // activations, split-K with fp32 atomics).  No transposed copies are ever made.
 //
-// CTA = 320 threads:  warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..9 = epilogue (two warps per TMEM lane quarter, alternating 64-column chunks).  Pipelines: smem ring full/empty
-// (TMA <-> MMA) and a double-buffered TMEM accumulator full/empty (MMA <-> epilogue), so the
-// epilogue of tile i overlaps the main loop of tile i+1.  Grid = min(#work units, #SMs);
-// work unit = (output tile, K split), claimed DYNAMICALLY from a global counter by the leader's
-// producer thread and broadcast to every role (of both CTAs of a pair) through a small smem ring:
-// a CTA that starts late -- because a co-running kernel, e.g. the NCCL all-reduce that overlaps
-// the backward pass, holds its SM -- simply claims fewer units.  (A static round-robin schedule
-// made every GEMM 1.5x slower as soon as another kernel pinned 4 SMs.)
+// CTA = 352 threads:  warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..9 = epilogue (two warps per TMEM lane quarter, alternating 64-column chunks), warp 10 =
+// tile scheduler.  Pipelines: smem ring full/empty (TMA <-> MMA) and a double-buffered TMEM
+// accumulator full/empty (MMA <-> epilogue), so the epilogue of tile i overlaps the main loop of
+// tile i+1.  Grid = min(#work units, #SMs); work unit = (output tile, K split).
+// Two schedules (mcan_set_gemm_schedule):
+//   static  -- cluster c takes units c, c + #clusters, ...: nothing on the critical path; used
+//              when the GEMM owns the GPU;
+//   dynamic -- the scheduler warp of the leader CTA claims units from a global counter and
+//              broadcasts them to every role (of both CTAs of a pair) through a 2-slot smem ring,
+//              one unit ahead of the producer: a CTA whose SM is held by a co-running kernel
+//              (the NCCL all-reduce overlapping the backward pass) simply claims fewer units.
+//              Under the static schedule every GEMM ran 1.5x slower as soon as another kernel
+//              pinned 4 SMs (tools/contention_bench.py).
 //
 // Tile 128 x BLOCK_N (128 | 256) x 64.  Operand tiles are TMA boxes with the 128-byte swizzle:
 //   K-major  tile [rows x 64 k]  : one box {64, rows}; UMMA desc SBO = 1024 B, k-step = +32 B
@@ -35,9 +40,10 @@ namespace mcan {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int UMMA_K = 16;
-constexpr int kSchedStages = 4;      // depth of the work-unit broadcast ring (dynamic tile scheduler)
+constexpr int kSchedStages = 2;      // depth of the work-unit broadcast ring (dynamic tile scheduler)
 constexpr int kEpilogueWarps = 8;   // two warps per TMEM lane quarter, alternating 64-column chunks
-constexpr int kGemmThreads = 64 + 32 * kEpilogueWarps;
+constexpr int kSchedWarp = 2 + kEpilogueWarps;   // last warp: tile scheduler (idle under the static schedule)
+constexpr int kGemmThreads = 32 * (kSchedWarp + 1);
 
 struct alignas(64) GemmParams {
     CUtensorMap tma_a[MCAN_MAX_GEMM_SEGMENTS];
@@ -382,8 +388,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             }
             for (int s = 0; s < kSchedStages; ++s) {
                 mbar_init(&sched_full[s], 1);
-                // consumers: MMA thread + epilogue warps of the leader, producer + epilogue warps of the peer
-                mbar_init(&sched_empty[s], (1 + kEpilogueWarps) * CG);
+                // readers: producer + MMA thread + epilogue warps of the leader, producer + epilogue warps of the peer
+                mbar_init(&sched_empty[s], (2 + kEpilogueWarps) + (CG == 2 ? 1 + kEpilogueWarps : 0));
             }
             fence_mbar_init();
         }
@@ -436,41 +442,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            // Scheduler (leader only): claims run one tile ahead of their publication and publications
-            // one tile ahead of their use, so neither the atomic's round trip to L2 nor the
-            // cross-CTA broadcast latency ever stalls a tile.  Exactly one failing claim per cluster.
-            auto publish = [&](int unit) {
-                if (unit == units + nclusters - 1) atomicExch(p.tile_counter, 0);   // the very last claim
-                mbar_wait(&sched_empty[sslot], sphase ^ 1);
-                sched_unit[sslot] = (uint32_t)unit;
-                if (CG == 2) {
-                    st_shared_remote_u32(&sched_unit[sslot], 1, (uint32_t)unit);
-                    mbar_arrive_release_cluster(&sched_full[sslot], 1);
-                    mbar_arrive_release_cluster(&sched_full[sslot], 0);
-                } else {
-                    mbar_arrive(&sched_full[sslot]);
-                }
-                if (++sslot == kSchedStages) { sslot = 0; sphase ^= 1; }
-            };
-            int c0 = 0, c1 = 0;
-            if (dyn && leader) {
-                c0 = atomicAdd(p.tile_counter, 1);
-                publish(c0);
-                c1 = (c0 < units) ? atomicAdd(p.tile_counter, 1) : c0;
-            }
             while (true) {
-                int unit;
-                if (dyn && leader) {
-                    unit = c0;
-                    if (unit < units) {
-                        publish(c1);                                        // the tile after this one (or the end marker)
-                        const int c2 = (c1 < units) ? atomicAdd(p.tile_counter, 1) : c1;
-                        c0 = c1;
-                        c1 = c2;
-                    }
-                } else {
-                    unit = next_unit();
-                }
+                const int unit = next_unit();
                 if (unit >= units) break;
                 const int tile = unit % tiles, split = unit / tiles;
                 const int m0 = (tile / p.n_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
@@ -553,6 +526,31 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                 if (CG == 2) umma_commit_cg2(&tmem_full_bar[acc], 3); else umma_commit(&tmem_full_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 unit = unit_after;
+            }
+        }
+    } else if (warp == kSchedWarp) {
+        // ===================== tile scheduler (dynamic schedule, leader CTA only) =====================
+        // Claims work units from the global counter and publishes them to every role of the CTA
+        // (pair) through the ring; runs kSchedStages units ahead of the slowest reader, so the
+        // atomic's round trip to L2 and the cross-CTA broadcast never stall a tile.  Exactly one
+        // failing claim per cluster; the very last claim of the grid resets the counter.
+        if (dyn && leader && lane == 0) {
+            int slot = 0;
+            uint32_t ph = 0;
+            while (true) {
+                const int unit = atomicAdd(p.tile_counter, 1);
+                if (unit == units + nclusters - 1) atomicExch(p.tile_counter, 0);
+                mbar_wait(&sched_empty[slot], ph ^ 1);
+                sched_unit[slot] = (uint32_t)unit;
+                if (CG == 2) {
+                    st_shared_remote_u32(&sched_unit[slot], 1, (uint32_t)unit);
+                    mbar_arrive_release_cluster(&sched_full[slot], 1);
+                    mbar_arrive_release_cluster(&sched_full[slot], 0);
+                } else {
+                    mbar_arrive(&sched_full[slot]);
+                }
+                if (++slot == kSchedStages) { slot = 0; ph ^= 1; }
+                if (unit >= units) break;
             }
         }
     } else {

@@ -88,105 +88,134 @@ ln_fwd_kernel(const float* __restrict__ x, long long rows, int h, const float* _
 // Backward.  ghat = dy*a_2, c = x-mean, s = sigma+eps:
 //   dx = (ghat - mean(ghat))/s - c * sum(ghat*c) / (s^2 * sigma * (N-1))
 //   da_2 += dy*c/s ; db_2 += dy ; dbias += gated dx
-// A CTA owns a block of up to 32 consecutive rows.  Pass A (warp per row, streaming, a handful
-// of registers) reduces the two row statistics into shared memory.  Pass B re-reads the block
-// from L1/L2 with the threads laid out along the columns: each thread owns one float4 column
-// group for all rows of the block, so the a_2 / b_2 / bias column sums are 12 registers and
-// every global access is a coalesced 16-byte vector; one atomicAdd per column per CTA.
-constexpr int kLnBwdMaxRows = 32;
-constexpr int kLnBwdThreads = 256;
+// Single pass over HBM (x and dy are read exactly once): a warp owns one row at a time, the row
+// lives in registers (like the forward), the two row statistics are warp shuffles.  The three
+// column sums (a_2, b_2, bias of the producing layer) are accumulated in a PRIVATE shared-memory
+// slice per warp (plain vector load/add/store, no atomics), summed over the warps of the CTA at
+// the end and added to global memory with one atomicAdd per column per CTA.  The grid is
+// persistent (2 CTAs per SM for h <= 1024), warps stride over the rows.
+constexpr int kLnBwdWarps = 8;
+constexpr int kLnBwdThreads = kLnBwdWarps * 32;
 
+template <int MAXV>
 __global__ void __launch_bounds__(kLnBwdThreads)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
               const float* __restrict__ mean_in, const float* __restrict__ sigma_in,
-              const float* __restrict__ a2, float eps, long long rows, int h, int rows_per_cta,
+              const float* __restrict__ a2, float eps, long long rows, int h,
               float* __restrict__ dx32, bf16* __restrict__ dxbf, uint32_t drop_thr,
               float drop_scale, uint32_t drop_seed_in, const uint32_t* __restrict__ drop_seed_dev,
               float* __restrict__ da2, float* __restrict__ db2, float* __restrict__ dbias) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ float s_mean[kLnBwdMaxRows], s_invs[kLnBwdMaxRows], s_mg[kLnBwdMaxRows], s_k2[kLnBwdMaxRows];
+    extern __shared__ __align__(16) float s_ln[];   // [warp][3][h]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = h >> 2;
-    const long long row_base = (long long)blockIdx.x * rows_per_cta;
-    const int nrows = (int)min((long long)rows_per_cta, rows - row_base);
     const uint32_t drop_seed =
         drop_seed_in ^ ((drop_thr != 0 && drop_seed_dev != nullptr) ? __ldg(drop_seed_dev) : 0U);
     const float4* ar = reinterpret_cast<const float4*>(a2);
-
-    // ---- pass A: row statistics ----
-    for (int r = warp; r < nrows; r += kLnBwdThreads / 32) {
-        const long long row = row_base + r;
-        const float mean = mean_in[row], sigma = sigma_in[row];
+    float4* acc_a = reinterpret_cast<float4*>(s_ln + (size_t)warp * 3 * h);
+    float4* acc_b = acc_a + nv;
+    float4* acc_bias = acc_b + nv;
+    const bool want_ab = da2 != nullptr || db2 != nullptr;
+    const bool want_bias = dbias != nullptr;
+    bool first = true;
+    const long long wstride = (long long)gridDim.x * kLnBwdWarps;
+    for (long long row = (long long)blockIdx.x * kLnBwdWarps + warp; row < rows; row += wstride) {
         const float4* xr = reinterpret_cast<const float4*>(x + row * h);
         const float4* gr = reinterpret_cast<const float4*>(dy + row * h);
+        float4 c[MAXV], g[MAXV];
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int i = lane + 32 * j;
+            c[j] = (i < nv) ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int i = lane + 32 * j;
+            g[j] = (i < nv) ? gr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float mean = mean_in[row], sigma = sigma_in[row];
+        const float s = sigma + eps, inv_s = 1.f / s;
         float sum_g = 0.f, sum_gc = 0.f;
-        for (int i = lane; i < nv; i += 32) {
-            const float4 xv = xr[i], gv = gr[i], a = __ldg(ar + i);
-            const float g0 = gv.x * a.x, g1 = gv.y * a.y, g2 = gv.z * a.z, g3 = gv.w * a.w;
-            sum_g += (g0 + g1) + (g2 + g3);
-            sum_gc += (g0 * (xv.x - mean) + g1 * (xv.y - mean)) + (g2 * (xv.z - mean) + g3 * (xv.w - mean));
-        }
-        sum_g = warp_sum(sum_g);
-        sum_gc = warp_sum(sum_gc);
-        if (lane == 0) {
-            const float s = sigma + eps;
-            s_mean[r] = mean;
-            s_invs[r] = 1.f / s;
-            s_mg[r] = sum_g / (float)h;
-            // sigma == 0: the reference's autograd gives NaN; emit the finite limit instead.
-            s_k2[r] = (sigma > 0.f) ? sum_gc / (s * s * sigma * (float)(h - 1)) : 0.f;
-        }
-    }
-    __syncthreads();
-
-    // ---- pass B: dx and the column sums ----
-    for (int c = threadIdx.x; c < nv; c += kLnBwdThreads) {
-        const float4 a = __ldg(ar + c);
-        float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f), acc_b = acc_a, acc_bias = acc_a;
-#pragma unroll 4
-        for (int r = 0; r < nrows; ++r) {
-            const long long row = row_base + r;
-            const float4 xv = reinterpret_cast<const float4*>(x + row * h)[c];
-            const float4 gv = reinterpret_cast<const float4*>(dy + row * h)[c];
-            const float mean = s_mean[r], inv_s = s_invs[r], mg = s_mg[r], k2 = s_k2[r];
-            const float cx = xv.x - mean, cy = xv.y - mean, cz = xv.z - mean, cw = xv.w - mean;
-            float4 d;
-            d.x = (gv.x * a.x - mg) * inv_s - cx * k2;
-            d.y = (gv.y * a.y - mg) * inv_s - cy * k2;
-            d.z = (gv.z * a.z - mg) * inv_s - cz * k2;
-            d.w = (gv.w * a.w - mg) * inv_s - cw * k2;
-            acc_a.x += gv.x * cx * inv_s; acc_a.y += gv.y * cy * inv_s;
-            acc_a.z += gv.z * cz * inv_s; acc_a.w += gv.w * cw * inv_s;
-            acc_b.x += gv.x; acc_b.y += gv.y; acc_b.z += gv.z; acc_b.w += gv.w;
-            if (dx32) reinterpret_cast<float4*>(dx32 + row * h)[c] = d;
-            if (dxbf != nullptr || dbias != nullptr) {
-                float4 gd = d;
-                if (drop_thr != 0) {
-                    const uint32_t base = (uint32_t)(row * h + 4 * c);  // multiple of 4
-                    const uint32_t r0 = dropout_bits_pair(base >> 1, drop_seed);
-                    const uint32_t r1 = dropout_bits_pair((base >> 1) + 1, drop_seed);
-                    gd.x = ((r0 & 0xFFFFU) >= drop_thr) ? d.x * drop_scale : 0.f;
-                    gd.y = ((r0 >> 16) >= drop_thr) ? d.y * drop_scale : 0.f;
-                    gd.z = ((r1 & 0xFFFFU) >= drop_thr) ? d.z * drop_scale : 0.f;
-                    gd.w = ((r1 >> 16) >= drop_thr) ? d.w * drop_scale : 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int i = lane + 32 * j;
+            if (i < nv) {
+                const float4 a = __ldg(ar + i);
+                c[j].x -= mean; c[j].y -= mean; c[j].z -= mean; c[j].w -= mean;
+                if (want_ab) {
+                    float4 ta, tb;
+                    ta.x = g[j].x * c[j].x * inv_s; ta.y = g[j].y * c[j].y * inv_s;
+                    ta.z = g[j].z * c[j].z * inv_s; ta.w = g[j].w * c[j].w * inv_s;
+                    tb = g[j];
+                    if (!first) {
+                        const float4 pa = acc_a[i], pb = acc_b[i];
+                        ta.x += pa.x; ta.y += pa.y; ta.z += pa.z; ta.w += pa.w;
+                        tb.x += pb.x; tb.y += pb.y; tb.z += pb.z; tb.w += pb.w;
+                    }
+                    acc_a[i] = ta;
+                    acc_b[i] = tb;
                 }
-                if (dxbf) store_bf16x4(dxbf + row * h + 4 * c, gd.x, gd.y, gd.z, gd.w);
-                acc_bias.x += gd.x; acc_bias.y += gd.y; acc_bias.z += gd.z; acc_bias.w += gd.w;
+                g[j].x *= a.x; g[j].y *= a.y; g[j].z *= a.z; g[j].w *= a.w;     // ghat
+                sum_g += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+                sum_gc += (g[j].x * c[j].x + g[j].y * c[j].y) + (g[j].z * c[j].z + g[j].w * c[j].w);
             }
         }
-        if (da2) {
-            atomicAdd(da2 + 4 * c + 0, acc_a.x); atomicAdd(da2 + 4 * c + 1, acc_a.y);
-            atomicAdd(da2 + 4 * c + 2, acc_a.z); atomicAdd(da2 + 4 * c + 3, acc_a.w);
+        const float mg = warp_sum(sum_g) / (float)h;
+        // sigma == 0: the reference's autograd gives NaN; emit the finite limit instead.
+        const float sgc = warp_sum(sum_gc);
+        const float k2 = (sigma > 0.f) ? sgc / (s * s * sigma * (float)(h - 1)) : 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXV; ++j) {
+            const int i = lane + 32 * j;
+            if (i < nv) {
+                float4 d;
+                d.x = (g[j].x - mg) * inv_s - c[j].x * k2;
+                d.y = (g[j].y - mg) * inv_s - c[j].y * k2;
+                d.z = (g[j].z - mg) * inv_s - c[j].z * k2;
+                d.w = (g[j].w - mg) * inv_s - c[j].w * k2;
+                if (dx32) reinterpret_cast<float4*>(dx32 + row * h)[i] = d;
+                if (dxbf != nullptr || want_bias) {
+                    if (drop_thr != 0) {
+                        const uint32_t base = (uint32_t)(row * h + 4 * i);  // multiple of 4
+                        const uint32_t r0 = dropout_bits_pair(base >> 1, drop_seed);
+                        const uint32_t r1 = dropout_bits_pair((base >> 1) + 1, drop_seed);
+                        d.x = ((r0 & 0xFFFFU) >= drop_thr) ? d.x * drop_scale : 0.f;
+                        d.y = ((r0 >> 16) >= drop_thr) ? d.y * drop_scale : 0.f;
+                        d.z = ((r1 & 0xFFFFU) >= drop_thr) ? d.z * drop_scale : 0.f;
+                        d.w = ((r1 >> 16) >= drop_thr) ? d.w * drop_scale : 0.f;
+                    }
+                    if (dxbf) store_bf16x4(dxbf + row * h + 4 * i, d.x, d.y, d.z, d.w);
+                    if (want_bias) {
+                        if (!first) {
+                            const float4 pb = acc_bias[i];
+                            d.x += pb.x; d.y += pb.y; d.z += pb.z; d.w += pb.w;
+                        }
+                        acc_bias[i] = d;
+                    }
+                }
+            }
         }
-        if (db2) {
-            atomicAdd(db2 + 4 * c + 0, acc_b.x); atomicAdd(db2 + 4 * c + 1, acc_b.y);
-            atomicAdd(db2 + 4 * c + 2, acc_b.z); atomicAdd(db2 + 4 * c + 3, acc_b.w);
+        first = false;
+    }
+    if (!want_ab && !want_bias) return;
+    // a warp that processed no row contributes zeros
+    if (first) {
+        for (int i = lane; i < 3 * nv; i += 32) acc_a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < h; col += kLnBwdThreads) {
+        float ta = 0.f, tb = 0.f, tc = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnBwdWarps; ++w) {
+            const float* base = s_ln + (size_t)w * 3 * h;
+            ta += base[col];
+            tb += base[h + col];
+            tc += base[2 * h + col];
         }
-        if (dbias) {
-            atomicAdd(dbias + 4 * c + 0, acc_bias.x); atomicAdd(dbias + 4 * c + 1, acc_bias.y);
-            atomicAdd(dbias + 4 * c + 2, acc_bias.z); atomicAdd(dbias + 4 * c + 3, acc_bias.w);
-        }
+        if (da2) atomicAdd(da2 + col, ta);
+        if (db2) atomicAdd(db2 + col, tb);
+        if (want_bias) atomicAdd(dbias + col, tc);
     }
 }
 
@@ -235,14 +264,28 @@ extern "C" int mcan_layernorm_bwd(const float* dy, const float* x, const float* 
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int sms = device_num_sms();
     MCAN_REQUIRE(sms > 0, "mcan_layernorm_bwd: no CUDA device");
-    // rows per CTA: 32 when that still gives >= 1 CTA per SM, fewer for short inputs
-    int rpc = kLnBwdMaxRows;
-    while (rpc > 4 && (rows + rpc - 1) / rpc < sms) rpc >>= 1;
-    const int grid = (int)((rows + rpc - 1) / rpc);
     const uint32_t thr = dropout_p > 0.f ? dropout_threshold(dropout_p) : 0;
     const float scale = dropout_p > 0.f ? 1.f / (1.f - dropout_p) : 1.f;
-    MCAN_CHECK_CUDA(launch_kernel(ln_bwd_kernel, dim3(grid), dim3(kLnBwdThreads), 0, st, dy, x, mean, sigma, a2,
-                                  eps, (long long)rows, (int)h, rpc, dx_f32, reinterpret_cast<bf16*>(dx_bf16), thr,
-                                  scale, dropout_seed, dropout_seed_dev, da2, db2, dbias));
+    const size_t smem = (size_t)kLnBwdWarps * 3 * (size_t)h * sizeof(float);
+    const int per_sm = h <= 1024 ? 2 : 1;
+    long long grid = (rows + kLnBwdWarps - 1) / kLnBwdWarps;
+    if (grid > (long long)per_sm * sms) grid = (long long)per_sm * sms;
+#define LN_BWD(MV)                                                                                          \
+    do {                                                                                                    \
+        static size_t configured = 48 * 1024;                                                               \
+        if (smem > configured) {                                                                            \
+            MCAN_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                                 (int)smem));                                               \
+            configured = smem;                                                                              \
+        }                                                                                                   \
+        MCAN_CHECK_CUDA(launch_kernel(ln_bwd_kernel<MV>, dim3((unsigned)grid), dim3(kLnBwdThreads), smem, st, dy, x, \
+                                      mean, sigma, a2, eps, (long long)rows, (int)h, dx_f32,                \
+                                      reinterpret_cast<bf16*>(dx_bf16), thr, scale, dropout_seed,           \
+                                      dropout_seed_dev, da2, db2, dbias));                                  \
+    } while (0)
+    if (h <= 512) LN_BWD(4);
+    else if (h <= 1024) LN_BWD(8);
+    else LN_BWD(16);
+#undef LN_BWD
     return 0;
 }
