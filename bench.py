@@ -241,7 +241,7 @@ def main():
 
     import __graft_entry__
     __graft_entry__.build()
-    from mcan_vqa_b200 import capi, ops
+    from mcan_vqa_b200 import blocks, capi, ops
     from mcan_vqa_b200.train import Trainer
     if world > 1 and reserve > 0:
         ops.set_sm_limit(ops.num_sms() - reserve)
@@ -358,6 +358,8 @@ def main():
                        "global_batch": BATCH * world, "parallelism": "dp%d" % world, "launch": graph_note,
                        "sms_reserved_for_nccl": reserve if world > 1 else 0,
                        "gemm_tile_schedule": "dynamic" if dynamic else "static",
+                       "optimizer": "fused multi-tensor AdamW (library kernel, emits the bf16 operand copies)",
+                       "decoder_wgrads": "second stream, next to the encoder backward" if blocks.OVERLAP_WGRAD else "inline",
                        "l2": "working set per step (fp32 masters + bf16 copies + activations, > 1 GB) exceeds the 126 MB L2; no explicit flush"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -5,6 +5,8 @@ when torch.distributed is initialised, step() first all-reduces (SUM) every grad
 ranks -- the one-process-per-GPU replacement of the reference's nn.DataParallel gradient
 reduction (core/exec.py:62-63) that works with core/exec.py unchanged, for any grad_accu_steps.
 """
+import os
+
 import torch
 from torch.optim import AdamW
 
@@ -44,9 +46,21 @@ class WarmupOptimizer(object):
 
 
 def get_optim(opt, model, data_size, lr_base=None):
+    """reference optim.py:51-67.  On the GPU the AdamW is the library's fused multi-tensor kernel
+    (same update rule; it also keeps the bf16 GEMM-operand copies of the weights current);
+    MCAN_FUSED_ADAMW=0 or CPU parameters select torch.optim.AdamW."""
     lr_base = opt.lr_base if lr_base is None else lr_base
     params = [p for p in model.parameters() if p.requires_grad]
-    return WarmupOptimizer(lr_base, AdamW(params, lr=0, weight_decay=1e-4), data_size, opt.batch_size)
+    inner = None
+    if params and all(p.is_cuda for p in params) and os.environ.get("MCAN_FUSED_ADAMW", "1") != "0":
+        from mcan_vqa_b200.optim import FusedAdamW
+        inner = FusedAdamW(params, lr=0, weight_decay=1e-4)
+        net = model.module if hasattr(model, "module") else model
+        if hasattr(net, "all_lps"):
+            inner.attach_shadows(net.all_lps())
+    if inner is None:
+        inner = AdamW(params, lr=0, weight_decay=1e-4)
+    return WarmupOptimizer(lr_base, inner, data_size, opt.batch_size)
 
 
 def adjust_lr(optim, decay_r):

@@ -26,10 +26,13 @@ struct AdamSeg {
     float* v;
     void* shadow;           // optional copy kept in sync with p: bf16, or fp32 when bit 62 of first_chunk is set
     long long n;            // elements
-    long long first_chunk;  // index of this segment's first chunk (bits 0..61)
+    long long first_chunk;  // index of this segment's first chunk (bits 0..60)
+    void* shadow2;          // optional second copy (a weight can sit in two stacked operand buffers); fp32 flag = bit 61
 };
 constexpr long long kAdamChunk = 4096;
 constexpr long long kAdamF32Flag = 1LL << 62;
+constexpr long long kAdamF32Flag2 = 1LL << 61;
+constexpr long long kAdamChunkMask = ~(kAdamF32Flag | kAdamF32Flag2);
 
 struct AdamCoef {
     float lr_wd;   // 1 - lr * wd
@@ -68,11 +71,12 @@ adamw_multi_kernel(const AdamSeg* __restrict__ segs, int nseg, long long total_c
         int lo = 0, hi = nseg - 1;
         while (lo < hi) {   // last segment whose first_chunk <= chunk
             const int mid = (lo + hi + 1) >> 1;
-            if ((segs[mid].first_chunk & ~kAdamF32Flag) <= chunk) lo = mid; else hi = mid - 1;
+            if ((segs[mid].first_chunk & kAdamChunkMask) <= chunk) lo = mid; else hi = mid - 1;
         }
         const AdamSeg sg = segs[lo];
         const bool shadow_f32 = (sg.first_chunk & kAdamF32Flag) != 0;
-        const long long off = (chunk - (sg.first_chunk & ~kAdamF32Flag)) * kAdamChunk;
+        const bool shadow2_f32 = (sg.first_chunk & kAdamF32Flag2) != 0;
+        const long long off = (chunk - (sg.first_chunk & kAdamChunkMask)) * kAdamChunk;
         const long long n = min(kAdamChunk, sg.n - off);
         float* p = sg.p + off;
         const float* g = sg.g + off;
@@ -80,8 +84,10 @@ adamw_multi_kernel(const AdamSeg* __restrict__ segs, int nseg, long long total_c
         float* v = sg.v + off;
         float* sh32 = (sg.shadow != nullptr && shadow_f32) ? reinterpret_cast<float*>(sg.shadow) + off : nullptr;
         bf16* sh16 = (sg.shadow != nullptr && !shadow_f32) ? reinterpret_cast<bf16*>(sg.shadow) + off : nullptr;
-        const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)sh32) & 15) == 0) &&
-                         (((uintptr_t)sh16 & 7) == 0);
+        float* sh32b = (sg.shadow2 != nullptr && shadow2_f32) ? reinterpret_cast<float*>(sg.shadow2) + off : nullptr;
+        bf16* sh16b = (sg.shadow2 != nullptr && !shadow2_f32) ? reinterpret_cast<bf16*>(sg.shadow2) + off : nullptr;
+        const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)sh32 | (uintptr_t)sh32b) & 15) == 0) &&
+                         ((((uintptr_t)sh16 | (uintptr_t)sh16b) & 7) == 0);
         long long done = 0;
         if (vec) {
             const long long nv = n >> 2;
@@ -97,13 +103,15 @@ adamw_multi_kernel(const AdamSeg* __restrict__ segs, int nseg, long long total_c
                 reinterpret_cast<float4*>(p)[i] = pv;
                 reinterpret_cast<float4*>(m)[i] = mv;
                 reinterpret_cast<float4*>(v)[i] = vv;
-                if (sh16) {
+                if (sh16 || sh16b) {
                     uint2 w;
                     w.x = pack_bf16x2(pv.x, pv.y);
                     w.y = pack_bf16x2(pv.z, pv.w);
-                    reinterpret_cast<uint2*>(sh16)[i] = w;
+                    if (sh16) reinterpret_cast<uint2*>(sh16)[i] = w;
+                    if (sh16b) reinterpret_cast<uint2*>(sh16b)[i] = w;
                 }
                 if (sh32) reinterpret_cast<float4*>(sh32)[i] = pv;
+                if (sh32b) reinterpret_cast<float4*>(sh32b)[i] = pv;
             }
             done = nv << 2;
         }
@@ -115,6 +123,8 @@ adamw_multi_kernel(const AdamSeg* __restrict__ segs, int nseg, long long total_c
             v[i] = vv;
             if (sh16) sh16[i] = __float2bfloat16_rn(pn);
             if (sh32) sh32[i] = pn;
+            if (sh16b) sh16b[i] = __float2bfloat16_rn(pn);
+            if (sh32b) sh32b[i] = pn;
         }
     }
 }

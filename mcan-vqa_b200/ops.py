@@ -56,14 +56,52 @@ def num_sms():
     return capi.load().mcan_num_sms()
 
 
+_raw_sms = [0]
+
+
+def num_sms_physical():
+    """SM count of the device, regardless of set_sm_limit."""
+    if _raw_sms[0] == 0:
+        saved = _state["sm_limit"]
+        if saved:
+            capi.load().mcan_set_sm_limit(0)
+        _raw_sms[0] = capi.load().mcan_num_sms()
+        if saved:
+            capi.load().mcan_set_sm_limit(saved)
+    return _raw_sms[0]
+
+
+_state = {"sm_limit": 0, "dynamic": False}
+
+
 def set_sm_limit(sms):
     """Persistent kernels use at most `sms` SMs (0 = all); see include/mcan_b200.h."""
     capi.check(capi.load().mcan_set_sm_limit(int(sms)), "mcan_set_sm_limit")
+    _state["sm_limit"] = int(sms)
 
 
 def set_gemm_schedule(dynamic):
     """Static (False, default) or dynamic (True) tile schedule of the GEMM; see include/mcan_b200.h."""
     capi.check(capi.load().mcan_set_gemm_schedule(1 if dynamic else 0), "mcan_set_gemm_schedule")
+    _state["dynamic"] = bool(dynamic)
+
+
+class launch_config(object):
+    """with launch_config(sm_limit=..., dynamic=...): GEMM launches inside use these settings."""
+
+    def __init__(self, sm_limit=None, dynamic=None):
+        self.want = (sm_limit, dynamic)
+
+    def __enter__(self):
+        self.saved = (_state["sm_limit"], _state["dynamic"])
+        if self.want[0] is not None:
+            set_sm_limit(self.want[0])
+        if self.want[1] is not None:
+            set_gemm_schedule(self.want[1])
+
+    def __exit__(self, *exc):
+        set_sm_limit(self.saved[0])
+        set_gemm_schedule(self.saved[1])
 
 
 def set_pdl(enabled):

@@ -1,0 +1,186 @@
+"""Fused multi-tensor AdamW on the library's `mcan_adamw_multi` kernel (SURVEY 8f "next" #3).
+
+Semantics = torch.optim.AdamW as the reference builds it (core/model/optim.py:58-64: lr set per
+step by WarmupOptimizer, betas (0.9, 0.999), eps 1e-8, weight_decay 1e-4): decoupled weight decay,
+bias-corrected moments.  ONE kernel per step updates every parameter and re-emits the bf16
+GEMM-operand copies ("shadows") that the next forward reads, so the separate fp32 -> bf16 refresh
+pass over all weights disappears.  Learning rate and step count are device scalars: a captured
+CUDA graph replays the step with new values.
+
+Differences from torch.optim.AdamW, all deliberate: one global step counter (parameters that never
+receive a gradient are skipped, as in torch, but a parameter that only sometimes receives one
+shares the counter); no amsgrad / maximize / foreach options.  `state_dict()` uses torch's layout,
+so checkpoints written by core/exec.py:237-244 load into either optimiser.
+"""
+import torch
+
+from . import capi, ops
+
+_F32 = torch.float32
+_CHUNK = 4096
+_F32_FLAG = 1 << 62
+_F32_FLAG2 = 1 << 61
+_WORDS = 8
+
+
+class FusedAdamW(object):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FusedAdamW: no parameters")
+        dev = self.params[0].device
+        if dev.type != "cuda":
+            raise capi.McanError("FusedAdamW needs CUDA parameters (the MCAN hot path has no CPU fallback)")
+        for p in self.params:
+            if p.device != dev or p.dtype != _F32 or not p.is_contiguous():
+                raise capi.McanError("FusedAdamW: parameters must be contiguous fp32 tensors on one device")
+        self.defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay)
+        self.param_groups = [dict(self.defaults, params=self.params)]
+        self.device = dev
+        self.lr_t = torch.zeros((), dtype=_F32, device=dev)
+        self.step_t = torch.zeros((), dtype=_F32, device=dev)
+        # flat moment buffers; every parameter's slice starts 16-byte aligned
+        self._off, tot = [], 0
+        for p in self.params:
+            self._off.append(tot)
+            tot += (p.numel() + 3) // 4 * 4
+        self._m = torch.zeros(tot, dtype=_F32, device=dev)
+        self._v = torch.zeros(tot, dtype=_F32, device=dev)
+        self._shadow = {}       # id(param) -> up to two contiguous bf16 / fp32 tensors of the same numel
+        self._managed = []      # LinearParams whose operand copies this optimiser keeps current
+        self._tables = {}
+        # pinned staging for the segment tables, allocated up front: a table built while a CUDA graph is
+        # being captured must not allocate host memory, and the captured upload re-reads its buffer
+        # on every replay, so buffers are never recycled
+        self._pinned = [torch.empty((len(self.params), _WORDS), dtype=torch.int64).pin_memory() for _ in range(8)]
+        self.epoch = 0          # bumped on every step (and by note_replay): low-order copies go stale
+
+    # -- operand copies ------------------------------------------------------------------------
+    def attach_shadows(self, lps):
+        """Keep the bf16 operand copies of these blocks.LinearParams in sync with the masters."""
+        by_id = {id(p): p for p in self.params}
+        for lp in lps:
+            if lp.managed is self:
+                continue
+            items = lp.shadow_items()
+            if items is None or any(id(src) not in by_id for _, src in items):
+                continue
+            if any(len(self._shadow.get(id(src), ())) >= 2 for _, src in items):
+                continue        # the kernel writes at most two copies per parameter
+            for dst, src in items:
+                self._shadow.setdefault(id(src), []).append(dst)
+            lp.managed = self
+            self._managed.append(lp)
+        self._tables.clear()
+
+    def note_replay(self):
+        """A captured graph containing step() was replayed (no Python ran)."""
+        self.epoch += 1
+
+    # -- torch.optim.Optimizer surface used by core/exec.py and WarmupOptimizer ---------------------
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if p.grad is None:
+                continue
+            if set_to_none:
+                p.grad = None
+            else:
+                p.grad.detach_()
+                p.grad.zero_()
+
+    def _table(self, active):
+        key = tuple((i, self.params[i].data_ptr(), g.data_ptr()) for i, g in active)
+        entry = self._tables.get(key)
+        if entry is not None:
+            return entry
+        if len(self._tables) > 16:
+            self._tables.clear()
+        rows, chunk = [], 0
+        for i, g in active:
+            p = self.params[i]
+            n, o = p.numel(), self._off[i]
+            sh = self._shadow.get(id(p), [])
+            flag = (_F32_FLAG if (len(sh) > 0 and sh[0].dtype == _F32) else 0) | \
+                   (_F32_FLAG2 if (len(sh) > 1 and sh[1].dtype == _F32) else 0)
+            rows.append([p.data_ptr(), g.data_ptr(), self._m.data_ptr() + 4 * o, self._v.data_ptr() + 4 * o,
+                         sh[0].data_ptr() if len(sh) > 0 else 0, n, chunk | flag,
+                         sh[1].data_ptr() if len(sh) > 1 else 0])
+            chunk += (n + _CHUNK - 1) // _CHUNK
+        host = self._pinned.pop() if self._pinned else torch.empty((len(self.params), _WORDS), dtype=torch.int64).pin_memory()
+        host = host[:len(rows)]
+        host.copy_(torch.tensor(rows, dtype=torch.int64))
+        table = torch.empty(host.shape, dtype=torch.int64, device=self.device)
+        table.copy_(host, non_blocking=True)      # captured with the step when a graph is being recorded
+        entry = (table, host, len(rows), chunk)
+        self._tables[key] = entry
+        return entry
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise capi.McanError("FusedAdamW.step: closures are not supported")
+        g0 = self.param_groups[0]
+        lr = g0["lr"]
+        if torch.is_tensor(lr):
+            self.lr_t.copy_(lr.detach().reshape(()).to(_F32), non_blocking=True)
+        else:
+            self.lr_t.fill_(float(lr))
+        active = []
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is None:
+                continue
+            if g.dtype != _F32 or not g.is_contiguous():
+                g = g.to(_F32).contiguous()
+            active.append((i, g))
+        if not active:
+            return None
+        self.step_t.add_(1.0)
+        table, _host, nseg, chunks = self._table(active)
+        b1, b2 = g0["betas"]
+        lib = capi.load()
+        capi.check(lib.mcan_adamw_multi(table.data_ptr(), nseg, chunks, self.lr_t.data_ptr(), self.step_t.data_ptr(),
+                                        float(b1), float(b2), float(g0["eps"]), float(g0["weight_decay"]),
+                                        ops._stream()), "mcan_adamw_multi")
+        self.epoch += 1
+        return None
+
+    # -- checkpoints (torch.optim layout) --------------------------------------------------------
+    def _views(self, i):
+        p, o = self.params[i], self._off[i]
+        n = p.numel()
+        return self._m[o:o + n].view_as(p), self._v[o:o + n].view_as(p)
+
+    def state_dict(self):
+        step = self.step_t.detach().clone().cpu()
+        state = {}
+        if float(step) > 0:
+            for i in range(len(self.params)):
+                m, v = self._views(i)
+                state[i] = {"step": step.clone(), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+        g0 = self.param_groups[0]
+        group = {k: v for k, v in g0.items() if k != "params"}
+        group.update(amsgrad=False, maximize=False, foreach=None, capturable=False, differentiable=False, fused=None)
+        group["params"] = list(range(len(self.params)))
+        return {"state": state, "param_groups": [group]}
+
+    def load_state_dict(self, sd):
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError("FusedAdamW.load_state_dict: parameter groups do not match")
+        for k in ("lr", "betas", "eps", "weight_decay"):
+            if k in groups[0]:
+                self.param_groups[0][k] = tuple(groups[0][k]) if k == "betas" else groups[0][k]
+        order = groups[0]["params"]
+        steps = [0.0]
+        for pos, idx in enumerate(order):
+            st = sd["state"].get(idx)
+            m, v = self._views(pos)
+            if st is None:
+                m.zero_()
+                v.zero_()
+                continue
+            m.copy_(st["exp_avg"])
+            v.copy_(st["exp_avg_sq"])
+            steps.append(float(st["step"]))
+        self.step_t.fill_(max(steps))

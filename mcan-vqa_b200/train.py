@@ -17,6 +17,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from . import blocks, dp, ops  # noqa: E402
+from .optim import FusedAdamW  # noqa: E402
 
 
 def warmup_rate(step, lr_base, data_size, batch_size):
@@ -30,7 +31,8 @@ def warmup_rate(step, lr_base, data_size, batch_size):
 
 class Trainer(object):
     def __init__(self, cfg, token_size, answer_size, device, lr_base=1e-4, data_size=64 * 1000,
-                 batch_size=64, state_dict=None, use_graph=False, data_parallel=False, net_cls=None):
+                 batch_size=64, state_dict=None, use_graph=False, data_parallel=False, net_cls=None,
+                 fused_optimizer=True):
         from core.model.net import Net
         self.device = device
         self.cfg = cfg
@@ -44,8 +46,13 @@ class Trainer(object):
         self.use_graph = use_graph
         self.lr_t = torch.zeros((), dtype=torch.float32, device=device)
         params = [p for p in self.net.parameters() if p.requires_grad]
-        self.opt = torch.optim.AdamW(params, lr=self.lr_t if use_graph else 0.0, weight_decay=1e-4,
-                                     fused=True, capturable=use_graph)
+        if fused_optimizer:
+            # the library's multi-tensor AdamW: one kernel per step that also re-emits the bf16 operand copies
+            self.opt = FusedAdamW(params, lr=self.lr_t if use_graph else 0.0, weight_decay=1e-4)
+            self.opt.attach_shadows(self.net.all_lps())
+        else:
+            self.opt = torch.optim.AdamW(params, lr=self.lr_t if use_graph else 0.0, weight_decay=1e-4,
+                                         fused=True, capturable=use_graph)
         self.loss_fn = torch.nn.BCELoss(reduction="sum")
         self.sync = dp.attach(self.net, overlap=True) if data_parallel else None
         self.graph = None
@@ -114,6 +121,8 @@ class Trainer(object):
                 self.static[1].copy_(ques, non_blocking=True)
                 self.static[2].copy_(ans, non_blocking=True)
             self.graph.replay()
+            if isinstance(self.opt, FusedAdamW):
+                self.opt.note_replay()
             return self.loss
         return self._raw_step(img, ques, ans)
 

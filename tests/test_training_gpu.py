@@ -168,3 +168,37 @@ def test_full_size_properties(model):
     loss.backward()
     for n, p in net.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
+
+
+def test_deferred_weight_gradients_on_second_stream_match_inline():
+    """MCA_ED's backward runs the decoder wgrads on a second stream next to the encoder backward
+    (blocks.OVERLAP_WGRAD); every parameter gradient must equal the single-stream result."""
+    from core.model.net import Net
+    from mcan_vqa_b200 import blocks
+    cfg = orc.Cfg(dropout_rate=0.1, **orc.TINY)
+    T, A, B = 50, 24, 8
+    sd = orc.synth_state_dict(cfg, T, A, seed=11)
+    v, q, a = (t.cuda() for t in orc.synth_batch(cfg, B, 12, 7, T, A, seed=12, ragged="prefix"))
+    got = {}
+    saved = blocks.OVERLAP_WGRAD
+    try:
+        for mode in (False, True):
+            blocks.OVERLAP_WGRAD = mode
+            torch.manual_seed(3)
+            blocks._seed_counter[0] = 0
+            net = Net(cfg, None, T, A)
+            net.load_state_dict(sd)
+            net = net.cuda().train()
+            for _ in range(3):      # repeated use of the side stream
+                net.zero_grad(set_to_none=True)
+                loss = torch.nn.BCELoss(reduction="sum")(net(v, q)[0], a)
+                loss.backward()
+            torch.cuda.synchronize()
+            got[mode] = {n: p.grad.clone() for n, p in net.named_parameters() if p.grad is not None}
+    finally:
+        blocks.OVERLAP_WGRAD = saved
+    assert got[True].keys() == got[False].keys()
+    for n in got[True]:
+        ref = got[False][n]
+        err = (got[True][n] - ref).abs().max().item()
+        assert err <= 1e-5 * (ref.abs().max().item() + 1e-12) + 1e-7, (n, err)
