@@ -694,6 +694,10 @@ def _mca_ed_fwd(rt, m, x32, y32, B, Sx, Sy, x_mask, y_mask, H, L, dev):
 # bound by L2 -> shared-memory operand traffic, not by SM count, so sharing the GPU buys nothing.
 OVERLAP_WGRAD = os.environ.get("MCAN_OVERLAP_WGRAD", "0") != "0"
 WGRAD_SMS = int(os.environ.get("MCAN_WGRAD_SMS", "108"))
+# Data parallel: hand the decoder layers' gradients to the all-reduce only once the whole decoder
+# backward is enqueued (one large exchange next to the latency-bound encoder backward) instead of
+# layer by layer next to the decoder's large GEMMs.
+DP_DELAY_DECODER = os.environ.get("MCAN_DP_DELAY_DECODER", "0") != "0"
 _side_streams = {}
 
 
@@ -729,7 +733,7 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
         if overlap:
             pending.append((rt.deferred, rt.drain()))
             rt.deferred = None
-        elif after_layer is not None:
+        elif after_layer is not None and not DP_DELAY_DECODER:
             after_layer(rt.drain())
     dx = dx_out
     if L > 0:

@@ -280,6 +280,17 @@ __device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMa
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
+// Same, multicast: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and
+// each destination's bytes are signalled on the mbarrier of the leader of ITS pair.
+__device__ __forceinline__ void tma_load_2d_cg2_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar,
+                                                   int32_t c0, int32_t c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        ".multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "h"(cta_mask), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t* slot_in_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(slot_in_smem)),

@@ -295,7 +295,7 @@ template <int BLOCK_N, int CG, bool PF>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int chunk_par,
                                               long long row0, int n0, uint32_t taddr,
                                               uint64_t* full_bar, uint64_t* empty_bar,
-                                              uint32_t acc_phase, uint32_t drop_seed) {
+                                              uint32_t acc_phase, uint32_t drop_seed, uint32_t lead_rank) {
     const int nchunks = min(BLOCK_N / kChunkN, (p.n - n0 + kChunkN - 1) / kChunkN);
     const int last_c = ((nchunks - 1 - chunk_par) & ~1) + chunk_par;   // this warp's last chunk (< 0: none)
     EpiPrefetch pf_next;
@@ -307,7 +307,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-            if (CG == 2) mbar_arrive_remote(empty_bar, 0);
+            if (CG == 2) mbar_arrive_remote(empty_bar, lead_rank);
             else mbar_arrive(empty_bar);
         }
     }
@@ -330,7 +330,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
-                    if (CG == 2) mbar_arrive_remote(empty_bar, 0);
+                    if (CG == 2) mbar_arrive_remote(empty_bar, lead_rank);
                     else mbar_arrive(empty_bar);
                 }
             }
@@ -340,12 +340,19 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int
     }
 }
 
-template <int BLOCK_N, int A_MN, int B_MN, int CG>
+// MC = CTA pairs per cluster (CG == 2 only).  MC == 2: a cluster of 4 CTAs computes a 512 x 256
+// super-tile -- two pairs on vertically adjacent 256-row tiles that need the SAME B tile.  Each
+// CTA then fetches only a quarter of B (64 rows) and TMA-multicasts it to its counterpart in the
+// other pair: L2 -> shared-memory traffic per CTA drops from 32 KB to 24 KB per k-block, and that
+// traffic (not the tensor pipe) is what bounds this kernel.
+template <int BLOCK_N, int A_MN, int B_MN, int CG, int MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BLOCK_N, CG>;
+    static_assert(MC == 1 || (MC == 2 && CG == 2 && BLOCK_N == 256), "pair multicast needs 256-wide CTA-pair tiles");
     constexpr int kStages = Cfg::kStages;
-    constexpr int kBRows = BLOCK_N / CG;   // rows of the B tile staged by this CTA
+    constexpr int kBRows = BLOCK_N / CG;   // rows of the B tile staged in this CTA's shared memory
+    constexpr int CL = CG * MC;            // CTAs per cluster
 
     // SWIZZLE_128B tiles need 1024-byte alignment; the kernel has no static shared memory, so the
     // dynamic window starts at the (1024-aligned) base of the CTA's shared memory.
@@ -367,8 +374,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0U;   // position in the CTA pair
-    const bool leader = (rank == 0);
+    const uint32_t crank = (CL > 1) ? cluster_ctarank() : 0U;   // position in the cluster
+    const uint32_t rank = crank & (uint32_t)(CG - 1);             // position in the CTA pair
+    const uint32_t pair = crank / CG;                             // which pair of the cluster (MC == 2)
+    const uint32_t lead_rank = pair * CG;                         // cluster rank of this pair's leader
+    const bool leader = (rank == 0);                              // issues the pair's MMAs, owns its barriers
+    const bool cl_leader = (crank == 0);                          // runs the dynamic tile scheduler
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < p.num_seg; ++s) {
@@ -380,7 +391,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         if (lane == 0) {
             for (int s = 0; s < kStages; ++s) {
                 mbar_init(&full_bar[s], 1);    // CG==2: only the leader's is used (bytes of both CTAs)
-                mbar_init(&empty_bar[s], 1);
+                mbar_init(&empty_bar[s], MC);  // one commit per pair whose MMAs read (multicast) data of this slot
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tmem_full_bar[s], 1);
@@ -389,7 +400,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             for (int s = 0; s < kSchedStages; ++s) {
                 mbar_init(&sched_full[s], 1);
                 // readers: producer + MMA thread + epilogue warps of the leader, producer + epilogue warps of the peer
-                mbar_init(&sched_empty[s], (2 + kEpilogueWarps) + (CG == 2 ? 1 + kEpilogueWarps : 0));
+                mbar_init(&sched_empty[s], ((2 + kEpilogueWarps) + (CG == 2 ? 1 + kEpilogueWarps : 0)) * MC);
             }
             fence_mbar_init();
         }
@@ -410,13 +421,13 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     // from here on global memory is touched: wait for the prerequisite grids to complete
     pdl_wait();
 
-    const int tiles = p.m_tiles * p.n_tiles;      // m_tiles counts (128*CG)-row tiles
+    const int tiles = p.m_tiles * p.n_tiles;      // m_tiles counts (128*CG*MC)-row (super-)tiles
     const int units = tiles * p.splits;
-    const int nclusters = gridDim.x / CG;
+    const int nclusters = gridDim.x / CL;
     // p.tile_counter == nullptr: static schedule (cluster c takes units c, c + nclusters, ...), no
     // atomics and no broadcast on the critical path -- the default when nothing else shares the GPU.
     const bool dyn = p.tile_counter != nullptr;
-    int sunit = (int)blockIdx.x / CG;
+    int sunit = (int)blockIdx.x / CL;
     int sslot = 0;            // position in the work-unit ring (every role walks it in lock step)
     uint32_t sphase = 0;
     // consumer side of the ring: returns the next work unit (>= units: no more work)
@@ -428,10 +439,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         }
         // the leader's own consumers see a local write (CTA scope is enough and much cheaper);
         // the peer's consumers need cluster-scope acquire / release
-        if (CG == 2 && !leader) mbar_wait_acq_cluster(&sched_full[sslot], sphase);
+        if (CL > 1 && !cl_leader) mbar_wait_acq_cluster(&sched_full[sslot], sphase);
         else mbar_wait(&sched_full[sslot], sphase);
         const int u = (int)*reinterpret_cast<volatile uint32_t*>(&sched_unit[sslot]);
-        if (CG == 2 && !leader) mbar_arrive_release_cluster(&sched_empty[sslot], 0);
+        if (CL > 1 && !cl_leader) mbar_arrive_release_cluster(&sched_empty[sslot], 0);
         else mbar_arrive(&sched_empty[sslot]);
         if (++sslot == kSchedStages) { sslot = 0; sphase ^= 1; }
         return u;
@@ -446,8 +457,10 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                 const int unit = next_unit();
                 if (unit >= units) break;
                 const int tile = unit % tiles, split = unit / tiles;
-                const int m0 = (tile / p.n_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
-                const int n0 = (tile % p.n_tiles) * BLOCK_N + (int)rank * kBRows;
+                const int m0 = (tile / p.n_tiles) * (BLOCK_M * CL) + (int)crank * BLOCK_M;
+                // MC == 2: this CTA fetches rows [pair*64, pair*64+64) of its half of B for both pairs
+                const int n0 = (tile % p.n_tiles) * BLOCK_N + (int)rank * kBRows + (MC == 2 ? (int)pair * (kBRows / 2) : 0);
+                const uint16_t mc_mask = (uint16_t)((1U << rank) | (1U << (CG + rank)));
                 const int kb0 = (int)((long long)p.kblocks * split / p.splits);
                 const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.splits);
                 for (int seg = 0; seg < p.num_seg; ++seg) {
@@ -468,7 +481,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                         } else {
                             load(sa, &p.tma_a[seg], kb * BLOCK_K, m0);
                         }
-                        if (B_MN) {
+                        if (MC == 2) {
+                            // one 64-row (K-major) / 64-column (MN-major) box = 8 KiB, at the same offset in both pairs
+                            uint8_t* dst = sb + pair * (BLOCK_K * 128);
+                            if (B_MN) tma_load_2d_cg2_mc(dst, &p.tma_b[seg], &full_bar[stage], n0, kb * BLOCK_K, mc_mask);
+                            else tma_load_2d_cg2_mc(dst, &p.tma_b[seg], &full_bar[stage], kb * BLOCK_K, n0, mc_mask);
+                        } else if (B_MN) {
 #pragma unroll
                             for (int c = 0; c < kBRows / 64; ++c)
                                 load(sb + c * (BLOCK_K * 128), &p.tma_b[seg], n0 + c * 64, kb * BLOCK_K);
@@ -519,11 +537,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                         else umma_bf16(tmem_d, ad, bd, idesc, accum);
                     }
                     // frees the smem slot (in both CTAs) when the MMAs retire
-                    if (CG == 2) umma_commit_cg2(&empty_bar[stage], 3); else umma_commit(&empty_bar[stage]);
+                    // (MC == 2: in all four CTAs -- the other pair multicasts into our slot and vice versa)
+                    if (CG == 2) umma_commit_cg2(&empty_bar[stage], (uint16_t)((1U << CL) - 1U)); else umma_commit(&empty_bar[stage]);
                     if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
                 // accumulator ready for the epilogue warps (of both CTAs)
-                if (CG == 2) umma_commit_cg2(&tmem_full_bar[acc], 3); else umma_commit(&tmem_full_bar[acc]);
+                if (CG == 2) umma_commit_cg2(&tmem_full_bar[acc], (uint16_t)(3U << lead_rank)); else umma_commit(&tmem_full_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 unit = unit_after;
             }
@@ -534,7 +553,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         // (pair) through the ring; runs kSchedStages units ahead of the slowest reader, so the
         // atomic's round trip to L2 and the cross-CTA broadcast never stall a tile.  Exactly one
         // failing claim per cluster; the very last claim of the grid resets the counter.
-        if (dyn && leader && lane == 0) {
+        if (dyn && cl_leader && lane == 0) {
             int slot = 0;
             uint32_t ph = 0;
             while (true) {
@@ -542,9 +561,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                 if (unit == units + nclusters - 1) atomicExch(p.tile_counter, 0);
                 mbar_wait(&sched_empty[slot], ph ^ 1);
                 sched_unit[slot] = (uint32_t)unit;
-                if (CG == 2) {
-                    st_shared_remote_u32(&sched_unit[slot], 1, (uint32_t)unit);
-                    mbar_arrive_release_cluster(&sched_full[slot], 1);
+                if (CL > 1) {
+#pragma unroll
+                    for (int c = 1; c < CL; ++c) {
+                        st_shared_remote_u32(&sched_unit[slot], (uint32_t)c, (uint32_t)unit);
+                        mbar_arrive_release_cluster(&sched_full[slot], (uint32_t)c);
+                    }
                     mbar_arrive_release_cluster(&sched_full[slot], 0);
                 } else {
                     mbar_arrive(&sched_full[slot]);
@@ -569,16 +591,16 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             if (lane == 0) unit_after = next_unit();     // published one tile ahead
             unit_after = __shfl_sync(0xffffffffU, unit_after, 0);
             const int tile = unit % tiles;
-            const int m0 = (tile / p.n_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
+            const int m0 = (tile / p.n_tiles) * (BLOCK_M * CL) + (int)crank * BLOCK_M;
             const int n0 = (tile % p.n_tiles) * BLOCK_N;
             const long long row0 = m0 + quad * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             if (p.resid != nullptr || p.gate != nullptr)
                 epilogue_tile<BLOCK_N, CG, true>(p, lane, chunk_par, row0, n0, taddr, &tmem_full_bar[acc],
-                                                 &tmem_empty_bar[acc], acc_phase, drop_seed);
+                                                 &tmem_empty_bar[acc], acc_phase, drop_seed, lead_rank);
             else
                 epilogue_tile<BLOCK_N, CG, false>(p, lane, chunk_par, row0, n0, taddr, &tmem_full_bar[acc],
-                                                  &tmem_empty_bar[acc], acc_phase, drop_seed);
+                                                  &tmem_empty_bar[acc], acc_phase, drop_seed, lead_rank);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             unit = unit_after;
         }
@@ -716,32 +738,50 @@ static int next_tile_counter(int** out) {
     return 0;
 }
 
-template <int BLOCK_N, int A_MN, int B_MN, int CG>
-static int launch_gemm(const GemmParams& p, int grid, cudaStream_t stream) {
+template <int BLOCK_N, int A_MN, int B_MN, int CG, int MC>
+static int launch_gemm(const GemmParams& p, int64_t units, int sms, cudaStream_t stream) {
     using Cfg = GemmCfg<BLOCK_N, CG>;
+    constexpr int CL = CG * MC;
     static bool configured[64] = {false};
+    static int max_clusters[64] = {0};
     int dev = 0;
     MCAN_CHECK_CUDA(cudaGetDevice(&dev));
-    auto kernel = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, CG>;
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        MCAN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)Cfg::kSmemBytes));
-        configured[dev] = true;
-    }
+    MCAN_REQUIRE(dev >= 0 && dev < 64, "device index %d", dev);
+    auto kernel = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, CG, MC>;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
+    if (!configured[dev]) {
+        MCAN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)Cfg::kSmemBytes));
+        // how many clusters of this shape fit on the device at once (GPC boundaries cost a few SMs
+        // for clusters of 4): a persistent grid must be fully co-resident
+        int n = 0;
+        cfg.gridDim = dim3((unsigned)(device_num_sms_raw() / CL * CL), 1, 1);
+        cfg.numAttrs = 1;
+        if (CL > 2) {
+            MCAN_CHECK_CUDA(cudaOccupancyMaxActiveClusters(&n, kernel, &cfg));
+            MCAN_REQUIRE(n > 0, "mcan_gemm: no cluster of %d CTAs fits", CL);
+        } else {
+            n = device_num_sms_raw() / CL;
+        }
+        max_clusters[dev] = n;
+        configured[dev] = true;
+    }
+    int64_t slots = sms / CL;
+    if (slots > max_clusters[dev]) slots = max_clusters[dev];
+    const int grid = (int)(units < slots ? units : slots) * CL;
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
     MCAN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
     return 0;
@@ -842,12 +882,14 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     TileCfg tc = pick_tile(a->m, a->n, sms);
     if (a->block_n) tc.bn = a->block_n;
     if (a->cta_group) tc.cg = a->cta_group;
-    const int block_n = tc.bn, cg = tc.cg;
+    // cta_group 4 = CTA pairs (cta_group::2 MMAs) in clusters of two pairs that share the B tile by multicast
+    const int block_n = tc.bn, cl = tc.cg, cg = cl == 4 ? 2 : cl, mc = cl == 4 ? 2 : 1;
     MCAN_REQUIRE(block_n == 128 || block_n == 256, "mcan_gemm: block_n=%d", block_n);
-    MCAN_REQUIRE(cg == 1 || cg == 2, "mcan_gemm: cta_group=%d", cg);
-    p.m_tiles = (int)((a->m + BLOCK_M * cg - 1) / (BLOCK_M * cg));
+    MCAN_REQUIRE(cl == 1 || cl == 2 || cl == 4, "mcan_gemm: cta_group=%d", cl);
+    MCAN_REQUIRE(cl != 4 || block_n == 256, "mcan_gemm: cta_group 4 needs block_n 256");
+    p.m_tiles = (int)((a->m + BLOCK_M * cl - 1) / (BLOCK_M * cl));
     p.n_tiles = (int)((a->n + block_n - 1) / block_n);
-    const int slots = sms / cg;
+    const int slots = sms / cl;
     int splits = 1;
     if (a->accumulate) {
         splits = a->split_k > 0 ? a->split_k : pick_splits((int64_t)p.m_tiles * p.n_tiles, p.kblocks, slots);
@@ -864,7 +906,7 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
             rc = make_tmap(&p.tma_a[s], a->a[s], (uint64_t)a->m, (uint64_t)a->k, (uint64_t)a->lda, 64);
         if (rc) return rc;
         if (a->b_layout == 0)
-            rc = make_tmap(&p.tma_b[s], a->b[s], (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)(block_n / cg));
+            rc = make_tmap(&p.tma_b[s], a->b[s], (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)(block_n / cl));
         else
             rc = make_tmap(&p.tma_b[s], a->b[s], (uint64_t)a->n, (uint64_t)a->k, (uint64_t)a->ldb, 64);
         if (rc) return rc;
@@ -894,18 +936,18 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     { const char* d = getenv("MCAN_GEMM_DEBUG"); p.debug = d ? atoi(d) : 0; }
 
     const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
-    const int grid = (int)(units < slots ? units : slots) * cg;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
     const int am = a->a_layout ? 1 : 0, bm = a->b_layout ? 1 : 0;
 
-#define MCAN_GEMM_CASE(BN, AM, BM, CG) \
-    if (block_n == BN && am == AM && bm == BM && cg == CG) return launch_gemm<BN, AM, BM, CG>(p, grid, st);
-#define MCAN_GEMM_CASES(BN, CG) \
-    MCAN_GEMM_CASE(BN, 0, 0, CG) MCAN_GEMM_CASE(BN, 0, 1, CG) MCAN_GEMM_CASE(BN, 1, 0, CG) MCAN_GEMM_CASE(BN, 1, 1, CG)
-    MCAN_GEMM_CASES(128, 1)
-    MCAN_GEMM_CASES(256, 1)
-    MCAN_GEMM_CASES(128, 2)
-    MCAN_GEMM_CASES(256, 2)
+#define MCAN_GEMM_CASE(BN, AM, BM, CG, MC) \
+    if (block_n == BN && am == AM && bm == BM && cg == CG && mc == MC) return launch_gemm<BN, AM, BM, CG, MC>(p, units, sms, st);
+#define MCAN_GEMM_CASES(BN, CG, MC) \
+    MCAN_GEMM_CASE(BN, 0, 0, CG, MC) MCAN_GEMM_CASE(BN, 0, 1, CG, MC) MCAN_GEMM_CASE(BN, 1, 0, CG, MC) MCAN_GEMM_CASE(BN, 1, 1, CG, MC)
+    MCAN_GEMM_CASES(128, 1, 1)
+    MCAN_GEMM_CASES(256, 1, 1)
+    MCAN_GEMM_CASES(128, 2, 1)
+    MCAN_GEMM_CASES(256, 2, 1)
+    MCAN_GEMM_CASES(256, 2, 2)
 #undef MCAN_GEMM_CASES
 #undef MCAN_GEMM_CASE
     set_last_error("mcan_gemm: no kernel for block_n=%d", block_n);

@@ -42,9 +42,10 @@ class GradSync(object):
         self.group = group
         self.world = world_size(group)
         self.overlap = overlap
-        self.pending = []
+        self.pending = []       # [(work handle, tensors it reduces)] in launch order
         self.ready = []
         self._queued = False
+        self.defer_wait = False  # True: the optimiser waits per bucket (take_buckets) instead of _final waiting for all
         self.launches = 0
         self.hooks = []
         if self.world > 1 and overlap:
@@ -71,7 +72,11 @@ class GradSync(object):
     def _launch(self, tensors):
         if self.world == 1 or not tensors:
             return
-        self.pending.extend(_all_reduce_sum_async(tensors, self.group))
+        works = _all_reduce_sum_async(tensors, self.group)
+        if len(works) == len(tensors):      # one handle per tensor (backends without coalescing)
+            self.pending.extend((w, [t]) for w, t in zip(works, tensors))
+        else:
+            self.pending.extend((w, tensors) for w in works)
         self.launches += 1
 
     def _ensure_final_callback(self):
@@ -81,10 +86,19 @@ class GradSync(object):
 
     def _final(self):
         self._flush_ready()
-        for w in self.pending:
+        self._queued = False
+        if self.defer_wait:
+            return            # the optimiser consumes the buckets one by one (take_buckets)
+        for w, _ in self.pending:
             w.wait()          # current stream waits for the NCCL stream; no host sync
         self.pending = []
-        self._queued = False
+
+    def take_buckets(self):
+        """[(work, tensors)] of this backward in launch order; the caller waits on each work before
+        it touches that bucket's gradients (FusedAdamW.step_buckets: the parameter update of the
+        first buckets overlaps the all-reduce of the last ones)."""
+        out, self.pending = self.pending, []
+        return out
 
     def remove(self):
         for h in self.hooks:

@@ -93,7 +93,7 @@ class FusedAdamW(object):
         entry = self._tables.get(key)
         if entry is not None:
             return entry
-        if len(self._tables) > 16:
+        if len(self._tables) > 96:
             self._tables.clear()
         rows, chunk = [], 0
         for i, g in active:
@@ -115,16 +115,16 @@ class FusedAdamW(object):
         self._tables[key] = entry
         return entry
 
-    @torch.no_grad()
-    def step(self, closure=None):
-        if closure is not None:
-            raise capi.McanError("FusedAdamW.step: closures are not supported")
+    def _begin_step(self):
         g0 = self.param_groups[0]
         lr = g0["lr"]
         if torch.is_tensor(lr):
             self.lr_t.copy_(lr.detach().reshape(()).to(_F32), non_blocking=True)
         else:
             self.lr_t.fill_(float(lr))
+        if not torch.cuda.is_current_stream_capturing():
+            while len(self._pinned) < 40:     # keep staging buffers ready for tables built during a capture
+                self._pinned.append(torch.empty((len(self.params), _WORDS), dtype=torch.int64).pin_memory())
         active = []
         for i, p in enumerate(self.params):
             g = p.grad
@@ -133,15 +133,49 @@ class FusedAdamW(object):
             if g.dtype != _F32 or not g.is_contiguous():
                 g = g.to(_F32).contiguous()
             active.append((i, g))
+        if active:
+            self.step_t.add_(1.0)
+        return active
+
+    def _launch(self, active):
         if not active:
-            return None
-        self.step_t.add_(1.0)
+            return
+        g0 = self.param_groups[0]
         table, _host, nseg, chunks = self._table(active)
         b1, b2 = g0["betas"]
         lib = capi.load()
         capi.check(lib.mcan_adamw_multi(table.data_ptr(), nseg, chunks, self.lr_t.data_ptr(), self.step_t.data_ptr(),
                                         float(b1), float(b2), float(g0["eps"]), float(g0["weight_decay"]),
                                         ops._stream()), "mcan_adamw_multi")
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        if closure is not None:
+            raise capi.McanError("FusedAdamW.step: closures are not supported")
+        self._launch(self._begin_step())
+        self.epoch += 1
+        return None
+
+    @torch.no_grad()
+    def step_buckets(self, buckets):
+        """Data-parallel step: `buckets` = [(work, tensors)] from dp.GradSync.take_buckets(), in the
+        order the gradient all-reduces were launched.  Each bucket's parameters are updated as
+        soon as ITS all-reduce has finished, so the update of the early buckets (the decoder layers)
+        overlaps the all-reduce of the late ones (encoder, LSTM, embedding) instead of waiting behind
+        them.  Every gradient must belong to some bucket."""
+        remaining = self._begin_step()
+        for work, tensors in buckets:
+            work.wait()       # the current stream waits for this all-reduce; no host sync
+            spans = [(t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()) for t in tensors]
+            mine, rest = [], []
+            for i, g in remaining:
+                a = g.data_ptr()
+                (mine if any(lo <= a < hi for lo, hi in spans) else rest).append((i, g))
+            remaining = rest
+            self._launch(mine)
+        if remaining:
+            raise capi.McanError("FusedAdamW.step_buckets: %d gradients were not part of any all-reduce bucket"
+                                 % len(remaining))
         self.epoch += 1
         return None
 

@@ -55,6 +55,10 @@ class Trainer(object):
                                          fused=True, capturable=use_graph)
         self.loss_fn = torch.nn.BCELoss(reduction="sum")
         self.sync = dp.attach(self.net, overlap=True) if data_parallel else None
+        # data parallel + fused optimiser: update bucket by bucket as the all-reduces finish
+        self.bucketed = self.sync is not None and self.sync.world > 1 and isinstance(self.opt, FusedAdamW)
+        if self.bucketed:
+            self.sync.defer_wait = True
         self.graph = None
         self.static = None
         self.loss = None
@@ -80,7 +84,10 @@ class Trainer(object):
         probs = self.net(img, ques)[0]
         loss = self.loss_fn(probs, ans)
         loss.backward()
-        self.opt.step()
+        if self.bucketed:
+            self.opt.step_buckets(self.sync.take_buckets())
+        else:
+            self.opt.step()
         return loss.detach()
 
     def _set_lr(self):

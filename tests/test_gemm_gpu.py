@@ -185,3 +185,37 @@ def test_gemm_dynamic_schedule_matches_static(m, n, k, cta_group, block_n):
         _close(acc, _rand((m, n), 23, 0.1).float().t() @ a.float(), 5e-5, "dynamic wgrad split-K")
     finally:
         ops.set_gemm_schedule(False)
+
+
+@pytest.mark.parametrize("m,n,k", [(512, 256, 64), (6400, 1024, 1024), (896, 1024, 512), (700, 520, 192), (6400, 4096, 1024)])
+@pytest.mark.parametrize("dynamic", [False, True])
+def test_gemm_cluster_of_two_pairs_multicast(m, n, k, dynamic):
+    """cta_group=4: clusters of two CTA pairs on a 512 x 256 super-tile, the B tile fetched once per
+    cluster and TMA-multicast to both pairs.  Must equal the plain CTA-pair kernel bit for bit, in
+    all three operand layouts (forward, dgrad, wgrad with split-K)."""
+    ops = _ops()
+    try:
+        ops.set_gemm_schedule(dynamic)
+        a, w = _rand((m, k), 31), _rand((n, k), 32, 0.05)
+        ref = torch.full((m, n), float("nan"), device="cuda")
+        out = torch.full((m, n), float("nan"), device="cuda")
+        ops.gemm(a, w, out_f32=ref, block_n=256, cta_group=2)
+        for _ in range(2):
+            ops.gemm(a, w, out_f32=out, block_n=256, cta_group=4)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+        _close(out, a.float() @ w.float().t(), 2e-5, "cluster-4 NT")
+        # dgrad layout: B MN-major
+        wt = _rand((k, n), 33, 0.05)
+        ops.gemm(a, wt, b_layout=1, out_f32=ref, block_n=256, cta_group=2)
+        ops.gemm(a, wt, b_layout=1, out_f32=out, block_n=256, cta_group=4)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+        # wgrad layout: both MN-major, split-K atomics
+        dy = _rand((m, n), 34, 0.1)
+        acc = torch.zeros((n, k), device="cuda")
+        ops.gemm(dy, a, a_layout=1, b_layout=1, out_f32=acc, accumulate=True, split_k=2, block_n=256, cta_group=4)
+        torch.cuda.synchronize()
+        _close(acc, dy.float().t() @ a.float(), 5e-5, "cluster-4 wgrad")
+    finally:
+        ops.set_gemm_schedule(False)

@@ -43,11 +43,14 @@ def main():
         ("wgrad ffn1 large", 4096, 1024, 6400, 1, 1, True),
         ("wgrad merge large", 1024, 1024, 6400, 1, 1, True),
         ("wgrad merge small", 512, 512, 6400, 1, 1, True),
+        ("wgrad qkv large", 3072, 1024, 6400, 1, 1, True),
+        ("dgrad merge large", 6400, 1024, 1024, 0, 1, False),
+        ("enc ffn2 large", 896, 1024, 4096, 0, 0, False),
     ]
     for name, m, n, k, al, bl, acc in shapes:
         a = torch.randn((m, k) if al == 0 else (k, m), device="cuda").to(torch.bfloat16)
         b = (torch.randn((n, k) if bl == 0 else (k, n), device="cuda") * 0.05).to(torch.bfloat16)
-        for cg, bn in ((1, 128), (1, 256), (2, 128), (2, 256), (0, 0)):
+        for cg, bn in ((2, 256), (4, 256), (0, 0)):
             if acc:
                 out = torch.zeros(m, n, device="cuda")
                 fn = lambda: ops.gemm(a, b, a_layout=al, b_layout=bl, out_f32=out, accumulate=True, block_n=bn, cta_group=cg)
