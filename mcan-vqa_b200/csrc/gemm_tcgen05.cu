@@ -149,7 +149,7 @@ struct EpiPrefetch {
 
 __device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPrefetch& pf, int lane,
                                                   long long row0, int col0) {
-    if (col0 + kChunkN > p.n || (p.n & 1)) return;   // ragged chunks use the slow path
+    if (col0 + kChunkN > p.n || ((p.n & 1) && p.drop_thr != 0)) return;   // ragged chunks use the slow path
     const int g = lane >> 2, t = lane & 3;
     const int col = col0 + 2 * t;
 #pragma unroll
@@ -175,7 +175,9 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_
                                               long long row0, int col0, uint32_t drop_seed,
                                               const EpiPrefetch& pf) {
     const int g = lane >> 2, t = lane & 3;
-    if (col0 + kChunkN > p.n || (p.n & 1)) {
+    // (odd N: only the dropout pair index needs N even; every other access is addressed through the
+    // 16-byte aligned leading dimensions)
+    if (col0 + kChunkN > p.n || ((p.n & 1) && p.drop_thr != 0)) {
         // only this copy has its address taken; v[] below must stay in registers (an escaping v[]
         // made the compiler mirror it to local memory after every pass: +15 us per epilogue stage)
         float tmp[32];
@@ -792,15 +794,19 @@ static int launch_gemm(const GemmParams& p, int64_t units, int sms, cudaStream_t
 // 256x256 tile has the highest arithmetic intensity, the single-CTA 128x128 tile the lowest.
 struct TileCfg { int cg, bn; };
 
-static TileCfg pick_tile(int64_t m, int64_t n, int sms) {
-    const TileCfg cand[4] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}};
-    const double rate[4] = {1.00, 0.62, 0.85, 0.62};
+static TileCfg pick_tile(int64_t m, int64_t n, int64_t k, bool accumulate, int sms) {
+    // {1, 64}: short-M GEMMs (the 896-row question side) are latency bound -- twice as many,
+    // half as long tiles
+    const TileCfg cand[5] = {{2, 256}, {2, 128}, {1, 256}, {1, 128}, {1, 64}};
+    const double rate[5] = {1.00, 0.62, 0.85, 0.62, 0.45};
     TileCfg best = cand[3];
     double best_cost = 1e30;
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 5; ++i) {
         const int cg = cand[i].cg, bn = cand[i].bn;
         if (bn == 256 && n <= 128) continue;
         if (cg == 2 && m <= 128) continue;
+        // 128 x 64 tiles re-read the operands from L2 most often: only for short contractions
+        if (bn == 64 && (k > 4096 || (accumulate && k > 1024))) continue;
         const int64_t tiles = ((m + 128 * cg - 1) / (128 * cg)) * ((n + bn - 1) / bn);
         const int64_t slots = sms / cg;
         const int64_t waves = (tiles + slots - 1) / slots;
@@ -879,12 +885,14 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     p.n = (int)a->n;
     p.k = (int)a->k;
     p.kblocks = (int)((a->k + BLOCK_K - 1) / BLOCK_K);
-    TileCfg tc = pick_tile(a->m, a->n, sms);
+    TileCfg tc = pick_tile(a->m, a->n, a->k, a->accumulate != 0, sms);
     if (a->block_n) tc.bn = a->block_n;
     if (a->cta_group) tc.cg = a->cta_group;
+    if (tc.bn == 64 && tc.cg != 1 && !a->block_n) tc.bn = 128;     // forced cta_group: 64-wide tiles are single-CTA
     // cta_group 4 = CTA pairs (cta_group::2 MMAs) in clusters of two pairs that share the B tile by multicast
     const int block_n = tc.bn, cl = tc.cg, cg = cl == 4 ? 2 : cl, mc = cl == 4 ? 2 : 1;
-    MCAN_REQUIRE(block_n == 128 || block_n == 256, "mcan_gemm: block_n=%d", block_n);
+    MCAN_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "mcan_gemm: block_n=%d", block_n);
+    MCAN_REQUIRE(block_n != 64 || cl == 1, "mcan_gemm: block_n 64 is a single-CTA tile");
     MCAN_REQUIRE(cl == 1 || cl == 2 || cl == 4, "mcan_gemm: cta_group=%d", cl);
     MCAN_REQUIRE(cl != 4 || block_n == 256, "mcan_gemm: cta_group 4 needs block_n 256");
     p.m_tiles = (int)((a->m + BLOCK_M * cl - 1) / (BLOCK_M * cl));
@@ -943,6 +951,7 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     if (block_n == BN && am == AM && bm == BM && cg == CG && mc == MC) return launch_gemm<BN, AM, BM, CG, MC>(p, units, sms, st);
 #define MCAN_GEMM_CASES(BN, CG, MC) \
     MCAN_GEMM_CASE(BN, 0, 0, CG, MC) MCAN_GEMM_CASE(BN, 0, 1, CG, MC) MCAN_GEMM_CASE(BN, 1, 0, CG, MC) MCAN_GEMM_CASE(BN, 1, 1, CG, MC)
+    MCAN_GEMM_CASES(64, 1, 1)
     MCAN_GEMM_CASES(128, 1, 1)
     MCAN_GEMM_CASES(256, 1, 1)
     MCAN_GEMM_CASES(128, 2, 1)

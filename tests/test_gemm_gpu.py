@@ -219,3 +219,32 @@ def test_gemm_cluster_of_two_pairs_multicast(m, n, k, dynamic):
         _close(acc, dy.float().t() @ a.float(), 5e-5, "cluster-4 wgrad")
     finally:
         ops.set_gemm_schedule(False)
+
+
+@pytest.mark.parametrize("m,n,k", SHAPES_NT + [(64, 3129, 2048), (896, 1024, 4096)])
+def test_gemm_block_n_64(m, n, k):
+    """128 x 64 single-CTA tiles (picked for the short-M question-side GEMMs), all three layouts,
+    and the fused epilogue on an odd N (answer head: 3129 columns)."""
+    ops = _ops()
+    a, w = _rand((m, k), 41), _rand((n, k), 42, 0.05)
+    ldo = (n + 3) // 4 * 4
+    out = torch.full((m, ldo), float("nan"), device="cuda")[:, :n]
+    ops.gemm(a, w, out_f32=out, block_n=64, cta_group=1)
+    torch.cuda.synchronize()
+    _close(out, a.float() @ w.float().t(), 2e-5, "NT 128x64")
+    bias = torch.randn(n, device="cuda")
+    outp = torch.full((m, ldo), float("nan"), device="cuda")[:, :n]
+    ops.gemm(a, w, bias=bias, relu=True, out_f32=outp)         # auto-picked tile
+    torch.cuda.synchronize()
+    _close(outp, torch.relu(a.float() @ w.float().t() + bias), 2e-5, "bias+relu, auto tile")
+    if n % 8 == 0:
+        wt = _rand((k, n), 43, 0.05)
+        ops.gemm(a, wt, b_layout=1, out_f32=out, block_n=64, cta_group=1)
+        torch.cuda.synchronize()
+        _close(out, a.float() @ wt.float(), 2e-5, "dgrad 128x64")
+    if n % 8 == 0 and k % 8 == 0:
+        dy = _rand((m, n), 44, 0.1)
+        acc = torch.zeros((n, k), device="cuda")
+        ops.gemm(dy, a, a_layout=1, b_layout=1, out_f32=acc, accumulate=True, block_n=64, cta_group=1)
+        torch.cuda.synchronize()
+        _close(acc, dy.float().t() @ a.float(), 5e-5, "wgrad 128x64")
