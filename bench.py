@@ -135,6 +135,11 @@ def cpu_port_step_time(model, batch, iters, warm, threads=None):
     return sum(times) / len(times), torch.get_num_threads()
 
 
+def workload_name(model):
+    return ("MCAN-%s full training step (Net fwd + BCE(sum) + bwd + AdamW), batch %d per GPU, "
+            "100x2048 region feats, 14 tokens, 3129 answers, dropout 0.1, random init" % (model, BATCH))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -146,8 +151,10 @@ def run_reference(args):
         "impl": "reference", "metric": "MCAN train samples/sec", "value": val, "unit": "samples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "MCAN-%s training step (CPU oracle port of the reference, torch fp32, dropout 0.1, AdamW)" % args.model,
-                   "batch_per_step": sample_b},
+        "config": {"workload": workload_name(args.model), "global_batch": BATCH, "parallelism": "cpu",
+                   "implementation": "CPU oracle port of the reference (torch fp32, all host threads); the reference is "
+                                     "Python + PyTorch and /root/reference does not exist on the GPU box",
+                   "sample": "each step = %d samples of the %d-sample batch (bounded CPU sample)" % (sample_b, BATCH)},
         "cpu_baseline": {"value": val, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": "%d-sample training steps (fwd+bwd+AdamW), %d timed after %d warm-up" % (sample_b, args.steps, args.warmup)},
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -198,7 +205,13 @@ def gemm_roofline(trainer, batch_dev, peaks):
     achieved = flops / secs / 1e12
     peak = peaks.get("bf16_tflops_sustained") or peaks.get("bf16_tflops") or 1590.0
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "gemm_tcgen05_kernel (all %d launches of one training step)" % len(records),
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant shape (FFN1 forward,
+            # 6400x4096x1024: 21.56 MB read = A + W exactly once, 3.49 MB written -- the 52 MB bf16 output stays
+            # in the 126 MB L2), ncu --set full, profiles/r01b_ncu_full_gemm_6400x4096x1024.metrics.csv;
+            # algorithmic bytes of that launch: 73.9 MB.  Same capture: tensor pipe active 54.6 % of elapsed cycles.
+            "traffic": 25056512, "traffic_launch": "gemm_tcgen05_kernel<256,0,0,2,1> 6400x4096x1024 (one launch)",
+            "tensor_pipe_active_pct_ncu": 54.6,
+            "kernel": "gemm_tcgen05_kernel (all %d launches of one training step)" % len(records),
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)"
             if "bf16_tflops_sustained" in peaks else "fallback 1590 (B200_PROFILING.md)",
             "gemm_ms_per_step": secs * 1e3, "gemm_flops_per_step": flops}
@@ -355,8 +368,7 @@ def main():
             "metric": "MCAN train samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "MCAN-%s full training step (Net fwd + BCE(sum) + bwd + AdamW), batch %d per GPU, "
-                                   "100x2048 region feats, 14 tokens, 3129 answers, dropout 0.1, random init" % (args.model, BATCH),
+            "config": {"workload": workload_name(args.model),
                        "global_batch": BATCH * world, "parallelism": "dp%d" % world, "launch": graph_note,
                        "sms_reserved_for_nccl": reserve if world > 1 else 0,
                        "gemm_tile_schedule": "dynamic" if dynamic else "static",
