@@ -723,7 +723,7 @@ int device_num_sms_raw() {
 static std::atomic<int> g_dynamic_schedule{0};
 
 // Pool of zero-initialised work-unit counters (one per in-flight launch; each kernel resets its own
-// counter with its last claim).  The only device memory the library owns besides nothing else.
+// counter with its last claim).  Besides the debug sink this pool is the only device memory the library owns.
 static int next_tile_counter(int** out) {
     constexpr int kPool = 256;
     static int* pool[64] = {nullptr};
