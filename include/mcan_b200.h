@@ -77,8 +77,11 @@ int mcan_set_pdl(int enabled);
  *   v  = gate[m,n] > 0 ? v*gate_scale : 0  (gate != NULL; backward through ReLU+dropout)
  *   v += resid[m,n]                      (resid != NULL, fp32)
  *   out_f32[m,n] = v / out_bf16[m,n] = bf16(v) / out_bf16_lo[m,n] = bf16(v - bf16(v))
- * accumulate != 0: out_f32[m,n] += v with fp32 atomics (required for split_k > 1; only
- * out_f32 may be set and no other epilogue stage).
+ * accumulate != 0: out_f32[m,n] += v with fp32 atomics (required for split_k > 1).  Only out_f32
+ * may be set and no ReLU: the remaining stages are linear in the accumulator, so with K splits every
+ * split scales its partial sum (dropout, gate) and split 0 alone adds bias and resid --
+ * out = resid + keep/(1-p) * (sum_s acc_s + bias) accumulates correctly into a ZEROED out_f32.
+ * This is how the short-M (question-side) GEMMs with K >= 2048 use all SMs.
  * Alignment: operand base pointers 16 B, leading dimensions multiples of 8 elements.
  */
 typedef struct mcan_gemm_args {

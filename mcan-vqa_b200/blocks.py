@@ -153,6 +153,25 @@ def _mm(rt, a, lp, i0, i1, out_bf16=None, out_lo=None, **kw):
         ops.gemm(a.bf, w, bias=b, out_bf16=out_bf16, **kw)
 
 
+# Short-M GEMMs with a long contraction (the 896-row question side: FFN2 forward, the dgrads of
+# FFN1 / QKV / the batched K,V projection) fill only 16-32 CTA pairs and run 64-192 k-blocks each.
+# Their epilogues (bias, dropout, residual) are linear in the accumulator, so they run split-K
+# (red.global.add into a zeroed fp32 output, K split 0 adds bias + residual) on all SMs instead.
+SPLITK_MAX_ROWS = 1024
+SPLITK_MIN_K = 2048
+
+
+def _resid_gemm(a, w, M, N, K, dev, **kw):
+    """out_f32[M,N] = epilogue(a w^T) for an epilogue without ReLU / bf16 output; split-K when short and deep."""
+    if SPLITK_MIN_K > 0 and M <= SPLITK_MAX_ROWS and K >= SPLITK_MIN_K:
+        out = torch.zeros((M, N), dtype=_F32, device=dev)
+        ops.gemm(a, w, out_f32=out, accumulate=True, **kw)
+    else:
+        out = _empty(M, N, _F32, dev)
+        ops.gemm(a, w, out_f32=out, **kw)
+    return out
+
+
 def _empty(rows, cols, dtype, device):
     return torch.empty((rows, cols), dtype=dtype, device=device)
 
@@ -507,8 +526,7 @@ def att_bwd(rt, mh, c, dout, norm=None, dkv=None, need_dx=True):
         rt.wgrad(ops.colsum, dqkv, g.b)
         rt.wgrad(ops.gemm, dqkv, c.x_bf, a_layout=1, b_layout=1, out_f32=g.w, accumulate=True)
         if need_dx:
-            dx = _empty(M, H, _F32, dev)
-            ops.gemm(dqkv, lp.w, b_layout=1, resid=ds_f32, out_f32=dx)
+            dx = _resid_gemm(dqkv, lp.w, M, H, 3 * H, dev, b_layout=1, resid=ds_f32)
     else:
         rt.wgrad(ops.colsum, dq, g.rows_b(0, 1))
         rt.wgrad(ops.gemm, dq, c.x_bf, a_layout=1, b_layout=1, out_f32=g.rows_w(0, 1), accumulate=True)
@@ -565,9 +583,10 @@ def mlp_fwd(rt, mlp, x, norm=None):
             out = torch.empty((M, ldp), dtype=_F32, device=dev)[:, :lp2.n]
         _mm(rt, ha, lp2, 0, 1, out_f32=out)
         return out, c
-    s = _empty(M, lp2.n, _F32, dev)
+    use_sk = SPLITK_MIN_K > 0 and M <= SPLITK_MAX_ROWS and lp1.n >= SPLITK_MIN_K     # see _resid_gemm
+    s = torch.zeros((M, lp2.n), dtype=_F32, device=dev) if use_sk else _empty(M, lp2.n, _F32, dev)
     c.seed_out = rt.seed()
-    _mm(rt, ha, lp2, 0, 1, dropout_p=rt.p, seed=c.seed_out, resid=x.f32, out_f32=s)
+    _mm(rt, ha, lp2, 0, 1, dropout_p=rt.p, seed=c.seed_out, resid=x.f32, out_f32=s, accumulate=use_sk)
     out, c.mean, c.sigma = ln_fwd(norm, s, split=rt.split)
     c.s = s
     return out, c
@@ -601,8 +620,7 @@ def mlp_bwd(rt, mlp, c, dout, norm=None, need_dx=True):
     rt.wgrad(ops.gemm, dh, c.x_bf, a_layout=1, b_layout=1, out_f32=g1.w, accumulate=True)
     dx = None
     if need_dx:
-        dx = _empty(M, c.lp1.k, _F32, dev)
-        ops.gemm(dh, c.lp1.w, b_layout=1, resid=ds_f32, out_f32=dx)
+        dx = _resid_gemm(dh, c.lp1.w, M, c.lp1.k, c.lp1.n, dev, b_layout=1, resid=ds_f32)
     (w1, b1), = g1.per_param()
     (w2, b2), = g2.per_param()
     grads[mlp.fc.linear.weight], grads[mlp.fc.linear.bias] = w1, b1
@@ -742,9 +760,7 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
             rt.deferred = []
         rt.wgrad(ops.colsum, dkv_all, gkv.b)
         rt.wgrad(ops.gemm, dkv_all, ctx.xenc_bf, a_layout=1, b_layout=1, out_f32=gkv.w, accumulate=True)
-        dxe = _empty(B * Sx, H, _F32, dev)
-        ops.gemm(dkv_all, ctx.lpkv.w, b_layout=1, resid=dx_out, out_f32=dxe)
-        dx = dxe
+        dx = _resid_gemm(dkv_all, ctx.lpkv.w, B * Sx, H, 2 * H * L, dev, b_layout=1, resid=dx_out)
         gk = {}
         for (w, b), (gw, gb) in zip(ctx.lpkv.pairs, gkv.per_param()):
             gk[w], gk[b] = gw, gb

@@ -48,9 +48,16 @@ constexpr int kGemmThreads = 32 * (kSchedWarp + 1);
 struct alignas(64) GemmParams {
     CUtensorMap tma_a[MCAN_MAX_GEMM_SEGMENTS];
     CUtensorMap tma_b[MCAN_MAX_GEMM_SEGMENTS];
+    CUtensorMap tma_b_half[MCAN_MAX_GEMM_SEGMENTS];   // K-major B, box of half as many rows (tail splitting)
     int num_seg;
     int m, n, k;
     int m_tiles, n_tiles, splits, kblocks;
+    // Tail splitting (splits == 1, BLOCK_N == 256): output tiles [0, full_tiles) are work units of
+    // the full BLOCK_N width; each remaining tile is TWO units of width BLOCK_N / 2.  The host picks
+    // full_tiles = whole waves, so the last, partial wave runs as half-width tiles on twice as many
+    // CTA pairs (100 tiles on 74 pairs: 2 tile-times -> ~1.6).  full_tiles == tiles: no splitting.
+    int full_tiles;
+    int units;
     // epilogue
     const float* bias;
     int relu;
@@ -112,7 +119,7 @@ constexpr int kChunkN = 64;
 
 // generic (slow) path for chunks that cross the N boundary or odd N: per element, rolled loops
 __device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const float* v, int lane,
-                                                  long long row0, int col0, uint32_t drop_seed) {
+                                                  long long row0, int col0, uint32_t drop_seed, bool addends) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll 1
     for (int i = 0; i < 32; ++i) {
@@ -121,12 +128,12 @@ __device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const flo
         const int col = col0 + 8 * k + 2 * t + c;
         if (row >= p.m || col >= p.n) continue;
         float x = v[i];
-        if (p.bias != nullptr) x += __ldg(p.bias + col);
+        if (p.bias != nullptr && addends) x += __ldg(p.bias + col);
         if (p.relu) x = fmaxf(x, 0.f);
         if (p.drop_thr != 0)
             x = dropout_u16((uint32_t)(row * (long long)p.n + col), drop_seed) >= p.drop_thr ? x * p.drop_scale : 0.f;
         if (p.gate != nullptr) x = __bfloat162float(p.gate[row * p.ldg + col]) > 0.f ? x * p.gate_scale : 0.f;
-        if (p.resid != nullptr) x += p.resid[row * p.ldr + col];
+        if (p.resid != nullptr && addends) x += p.resid[row * p.ldr + col];
         if (p.out_f32 != nullptr) {
             if (p.accumulate) atomicAdd(p.out_f32 + row * p.ldo_f32 + col, x);
             else p.out_f32[row * p.ldo_f32 + col] = x;
@@ -170,10 +177,13 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPrefet
     }
 }
 
+// addends: this work unit adds the bias and the residual (false for K splits > 0 of a split-K GEMM
+// with a fused LINEAR epilogue: out = resid + keep*scale*(sum_s acc_s + bias), every split scales
+// its partial sum, only split 0 contributes the addends; all through red.global.add).
 template <bool PF>
 __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_t (&r)[32], int lane,
                                               long long row0, int col0, uint32_t drop_seed,
-                                              const EpiPrefetch& pf) {
+                                              const EpiPrefetch& pf, bool addends) {
     const int g = lane >> 2, t = lane & 3;
     // (odd N: only the dropout pair index needs N even; every other access is addressed through the
     // 16-byte aligned leading dimensions)
@@ -183,7 +193,7 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_
         float tmp[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) tmp[i] = __uint_as_float(r[i]);
-        epilogue_frag_ragged(p, tmp, lane, row0, col0, drop_seed);
+        epilogue_frag_ragged(p, tmp, lane, row0, col0, drop_seed, addends);
         return;
     }
     float v[32];
@@ -193,7 +203,7 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_
     const long long rows[2] = {row0 + g, row0 + g + 8};
     const bool ok[2] = {rows[0] < p.m, rows[1] < p.m};
 
-    if (p.bias != nullptr) {
+    if (p.bias != nullptr && addends) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             const float2 b = __ldg(reinterpret_cast<const float2*>(p.bias + col + 8 * k));
@@ -232,7 +242,7 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_
             }
         }
     }
-    if (PF && p.resid != nullptr) {
+    if (PF && p.resid != nullptr && addends) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (ok[h]) {
@@ -293,12 +303,13 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_
 // Epilogue of one 128-row output tile for one of the 8 epilogue warps.  PF = the residual / gate
 // operands are prefetched one fragment ahead (separate instantiation so that plain epilogues do
 // not carry the prefetch registers).
-template <int BLOCK_N, int CG, bool PF>
+template <int CG, bool PF>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int chunk_par,
-                                              long long row0, int n0, uint32_t taddr,
+                                              long long row0, int n0, int width, uint32_t taddr,
                                               uint64_t* full_bar, uint64_t* empty_bar,
-                                              uint32_t acc_phase, uint32_t drop_seed, uint32_t lead_rank) {
-    const int nchunks = min(BLOCK_N / kChunkN, (p.n - n0 + kChunkN - 1) / kChunkN);
+                                              uint32_t acc_phase, uint32_t drop_seed, uint32_t lead_rank,
+                                              bool addends) {
+    const int nchunks = min(width / kChunkN, (p.n - n0 + kChunkN - 1) / kChunkN);
     const int last_c = ((nchunks - 1 - chunk_par) & ~1) + chunk_par;   // this warp's last chunk (< 0: none)
     EpiPrefetch pf_next;
     if (PF && last_c >= 0)   // operands of the first fragment, before waiting for the MMAs
@@ -337,7 +348,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int
                 }
             }
             if (row0 + hb * 16 < p.m)
-                epilogue_frag<PF>(p, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed, pf);
+                epilogue_frag<PF>(p, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed, pf, addends);
         }
     }
 }
@@ -347,6 +358,31 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int
 // CTA then fetches only a quarter of B (64 rows) and TMA-multicasts it to its counterpart in the
 // other pair: L2 -> shared-memory traffic per CTA drops from 32 KB to 24 KB per k-block, and that
 // traffic (not the tensor pipe) is what bounds this kernel.
+// work unit -> (output tile, K split, first column offset inside the tile, width in columns)
+struct UnitInfo { int tile, split, ncol, width; };
+template <int BLOCK_N>
+__device__ __forceinline__ UnitInfo decode_unit(const GemmParams& p, int unit, int tiles) {
+    UnitInfo u;
+    if (p.full_tiles >= tiles) {
+        u.tile = unit % tiles;
+        u.split = unit / tiles;
+        u.ncol = 0;
+        u.width = BLOCK_N;
+    } else if (unit < p.full_tiles) {
+        u.tile = unit;
+        u.split = 0;
+        u.ncol = 0;
+        u.width = BLOCK_N;
+    } else {
+        const int r = unit - p.full_tiles;
+        u.tile = p.full_tiles + (r >> 1);
+        u.split = 0;
+        u.ncol = (r & 1) * (BLOCK_N / 2);
+        u.width = BLOCK_N / 2;
+    }
+    return u;
+}
+
 template <int BLOCK_N, int A_MN, int B_MN, int CG, int MC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
@@ -424,7 +460,7 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     pdl_wait();
 
     const int tiles = p.m_tiles * p.n_tiles;      // m_tiles counts (128*CG*MC)-row (super-)tiles
-    const int units = tiles * p.splits;
+    const int units = p.units;                    // tiles * splits, or full_tiles + 2 * (tiles - full_tiles)
     const int nclusters = gridDim.x / CL;
     // p.tile_counter == nullptr: static schedule (cluster c takes units c, c + nclusters, ...), no
     // atomics and no broadcast on the critical path -- the default when nothing else shares the GPU.
@@ -458,10 +494,14 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             while (true) {
                 const int unit = next_unit();
                 if (unit >= units) break;
-                const int tile = unit % tiles, split = unit / tiles;
+                const UnitInfo ui = decode_unit<BLOCK_N>(p, unit, tiles);
+                const int tile = ui.tile, split = ui.split;
+                const bool half = ui.width != BLOCK_N;          // half-width unit: this CTA stages kBRows / 2 rows of B
+                const int brows = half ? kBRows / 2 : kBRows;
+                const uint32_t stage_tx = Cfg::kABytes + (uint32_t)brows * BLOCK_K * 2;
                 const int m0 = (tile / p.n_tiles) * (BLOCK_M * CL) + (int)crank * BLOCK_M;
                 // MC == 2: this CTA fetches rows [pair*64, pair*64+64) of its half of B for both pairs
-                const int n0 = (tile % p.n_tiles) * BLOCK_N + (int)rank * kBRows + (MC == 2 ? (int)pair * (kBRows / 2) : 0);
+                const int n0 = (tile % p.n_tiles) * BLOCK_N + ui.ncol + (int)rank * brows + (MC == 2 ? (int)pair * (kBRows / 2) : 0);
                 const uint16_t mc_mask = (uint16_t)((1U << rank) | (1U << (CG + rank)));
                 const int kb0 = (int)((long long)p.kblocks * split / p.splits);
                 const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.splits);
@@ -470,8 +510,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         uint8_t* sa = smem + stage * Cfg::kStageBytes;
                         uint8_t* sb = sa + Cfg::kABytes;
-                        if (CG == 1) mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                        else if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                        if (CG == 1) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+                        else if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * stage_tx);
                         auto load = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
                             if (CG == 2) tma_load_2d_cg2(dst, m, &full_bar[stage], c0, c1);
                             else tma_load_2d(dst, m, &full_bar[stage], c0, c1);
@@ -491,9 +531,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
                         } else if (B_MN) {
 #pragma unroll
                             for (int c = 0; c < kBRows / 64; ++c)
-                                load(sb + c * (BLOCK_K * 128), &p.tma_b[seg], n0 + c * 64, kb * BLOCK_K);
+                                if (c * 64 < brows) load(sb + c * (BLOCK_K * 128), &p.tma_b[seg], n0 + c * 64, kb * BLOCK_K);
                         } else {
-                            load(sb, &p.tma_b[seg], kb * BLOCK_K, n0);
+                            load(sb, half ? &p.tma_b_half[seg] : &p.tma_b[seg], kb * BLOCK_K, n0);
                         }
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
@@ -503,7 +543,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread of the leader CTA) =====================
         if (lane == 0 && leader) {
-            constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M * CG, BLOCK_N, A_MN, B_MN);
+            constexpr uint32_t idesc_full = make_idesc_bf16(BLOCK_M * CG, BLOCK_N, A_MN, B_MN);
+            constexpr uint32_t idesc_half = make_idesc_bf16(BLOCK_M * CG, BLOCK_N / 2, A_MN, B_MN);
             constexpr uint32_t a_lbo = A_MN ? BLOCK_K * 128 : 0;
             constexpr uint32_t b_lbo = B_MN ? BLOCK_K * 128 : 0;
             constexpr uint32_t a_kstep = A_MN ? (UMMA_K * 128) : (UMMA_K * 2);
@@ -516,7 +557,9 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             while (unit < units) {
                 // units are published one tile ahead: fetch the next one now, off the critical path
                 const int unit_after = next_unit();
-                const int split = unit / tiles;
+                const UnitInfo ui = decode_unit<BLOCK_N>(p, unit, tiles);
+                const int split = ui.split;
+                const uint32_t idesc = (ui.width == BLOCK_N) ? idesc_full : idesc_half;
                 const int kb0 = (int)((long long)p.kblocks * split / p.splits);
                 const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.splits);
                 const int iters = (kb1 - kb0) * p.num_seg;
@@ -592,17 +635,18 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             int unit_after = 0;
             if (lane == 0) unit_after = next_unit();     // published one tile ahead
             unit_after = __shfl_sync(0xffffffffU, unit_after, 0);
-            const int tile = unit % tiles;
+            const UnitInfo ui = decode_unit<BLOCK_N>(p, unit, tiles);
+            const int tile = ui.tile;
             const int m0 = (tile / p.n_tiles) * (BLOCK_M * CL) + (int)crank * BLOCK_M;
-            const int n0 = (tile % p.n_tiles) * BLOCK_N;
+            const int n0 = (tile % p.n_tiles) * BLOCK_N + ui.ncol;
             const long long row0 = m0 + quad * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
             if (p.resid != nullptr || p.gate != nullptr)
-                epilogue_tile<BLOCK_N, CG, true>(p, lane, chunk_par, row0, n0, taddr, &tmem_full_bar[acc],
-                                                 &tmem_empty_bar[acc], acc_phase, drop_seed, lead_rank);
+                epilogue_tile<CG, true>(p, lane, chunk_par, row0, n0, ui.width, taddr, &tmem_full_bar[acc],
+                                        &tmem_empty_bar[acc], acc_phase, drop_seed, lead_rank, ui.split == 0);
             else
-                epilogue_tile<BLOCK_N, CG, false>(p, lane, chunk_par, row0, n0, taddr, &tmem_full_bar[acc],
-                                                  &tmem_empty_bar[acc], acc_phase, drop_seed, lead_rank);
+                epilogue_tile<CG, false>(p, lane, chunk_par, row0, n0, ui.width, taddr, &tmem_full_bar[acc],
+                                         &tmem_empty_bar[acc], acc_phase, drop_seed, lead_rank, ui.split == 0);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             unit = unit_after;
         }
@@ -721,6 +765,8 @@ int device_num_sms_raw() {
 
 // 0: static round-robin tile schedule, 1: dynamic (work-unit counter).  See mcan_set_gemm_schedule.
 static std::atomic<int> g_dynamic_schedule{0};
+// MCAN_GEMM_TAIL_SPLIT=0 disables tail splitting (A/B timing)
+static std::atomic<int> g_tail_split{[] { const char* e = getenv("MCAN_GEMM_TAIL_SPLIT"); return (e && e[0] == '0') ? 0 : 1; }()};
 
 // Pool of zero-initialised work-unit counters (one per in-flight launch; each kernel resets its own
 // counter with its last claim).  Besides the debug sink this pool is the only device memory the library owns.
@@ -860,9 +906,10 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     MCAN_REQUIRE(a->out_f32 || a->out_bf16, "mcan_gemm: no output");
     MCAN_REQUIRE(!(a->out_bf16_lo && !a->out_bf16), "mcan_gemm: out_bf16_lo needs out_bf16");
     if (a->accumulate) {
-        MCAN_REQUIRE(a->out_f32 && !a->out_bf16 && !a->bias && !a->relu && a->dropout_p == 0.f &&
-                         !a->gate && !a->resid,
-                     "mcan_gemm: accumulate mode supports only out_f32");
+        // split-K / accumulate: every epilogue stage must be linear in the accumulator (bias and
+        // residual are added by K split 0 only; dropout and the gate scale every partial sum)
+        MCAN_REQUIRE(a->out_f32 && !a->out_bf16 && !a->relu,
+                     "mcan_gemm: accumulate mode needs out_f32 only and no ReLU");
     } else {
         MCAN_REQUIRE(a->split_k <= 1, "mcan_gemm: split_k needs accumulate");
     }
@@ -904,6 +951,16 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
         if (splits > p.kblocks) splits = p.kblocks;
     }
     p.splits = splits;
+    // tail splitting: the last, partial wave as half-width tiles (see GemmParams::full_tiles)
+    {
+        const int tiles = p.m_tiles * p.n_tiles;
+        p.full_tiles = tiles;
+        const int rem = tiles % slots;
+        if (g_tail_split.load(std::memory_order_relaxed) && splits == 1 && mc == 1 && block_n == 256 &&
+            a->n % 256 == 0 && tiles > slots && rem > 0 && 2 * rem <= slots)
+            p.full_tiles = tiles - rem;
+        p.units = splits > 1 ? tiles * splits : p.full_tiles + 2 * (tiles - p.full_tiles);
+    }
 
     for (int s = 0; s < a->num_seg; ++s) {
         MCAN_REQUIRE(a->a[s] && a->b[s], "mcan_gemm: null operand in segment %d", s);
@@ -913,9 +970,12 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
         else
             rc = make_tmap(&p.tma_a[s], a->a[s], (uint64_t)a->m, (uint64_t)a->k, (uint64_t)a->lda, 64);
         if (rc) return rc;
-        if (a->b_layout == 0)
+        if (a->b_layout == 0) {
             rc = make_tmap(&p.tma_b[s], a->b[s], (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)(block_n / cl));
-        else
+            if (rc) return rc;
+            if (p.full_tiles < p.m_tiles * p.n_tiles)
+                rc = make_tmap(&p.tma_b_half[s], a->b[s], (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)(block_n / cl / 2));
+        } else
             rc = make_tmap(&p.tma_b[s], a->b[s], (uint64_t)a->n, (uint64_t)a->k, (uint64_t)a->ldb, 64);
         if (rc) return rc;
     }
@@ -943,7 +1003,7 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     }
     { const char* d = getenv("MCAN_GEMM_DEBUG"); p.debug = d ? atoi(d) : 0; }
 
-    const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
+    const int64_t units = p.units;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
     const int am = a->a_layout ? 1 : 0, bm = a->b_layout ? 1 : 0;
 

@@ -248,3 +248,64 @@ def test_gemm_block_n_64(m, n, k):
         ops.gemm(dy, a, a_layout=1, b_layout=1, out_f32=acc, accumulate=True, block_n=64, cta_group=1)
         torch.cuda.synchronize()
         _close(acc, dy.float().t() @ a.float(), 5e-5, "wgrad 128x64")
+
+
+@pytest.mark.parametrize("m,n,k", [(6400, 1024, 1024), (6400, 3072, 512), (6400, 4096, 256), (4800, 1024, 192)])
+def test_gemm_tail_split_half_width_tiles(m, n, k):
+    """With more 256-wide tiles than CTA pairs, the last partial wave runs as half-width (128) work
+    units.  Results must equal the single-CTA 128-wide tiling bit for bit -- plain, fused epilogue
+    (bias + ReLU + dropout + bf16 store), dgrad layout with residual, wgrad layout."""
+    ops = _ops()
+    a, w = _rand((m, k), 51), _rand((n, k), 52, 0.05)
+    bias = torch.randn(n, device="cuda")
+    ref, out = torch.empty((m, n), device="cuda"), torch.full((m, n), float("nan"), device="cuda")
+    ops.gemm(a, w, out_f32=ref, block_n=128, cta_group=1)
+    ops.gemm(a, w, out_f32=out, block_n=256, cta_group=2)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    rb, ob = torch.empty((m, n), device="cuda", dtype=torch.bfloat16), torch.empty((m, n), device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, bias=bias, relu=True, dropout_p=0.1, seed=5, out_bf16=rb, block_n=128, cta_group=1)
+    ops.gemm(a, w, bias=bias, relu=True, dropout_p=0.1, seed=5, out_bf16=ob, block_n=256, cta_group=2)
+    torch.cuda.synchronize()
+    assert torch.equal(ob, rb)
+    wt = _rand((k, n), 53, 0.05)
+    resid = torch.randn(m, n, device="cuda")
+    ops.gemm(a, wt, b_layout=1, resid=resid, out_f32=ref, block_n=128, cta_group=1)
+    ops.gemm(a, wt, b_layout=1, resid=resid, out_f32=out, block_n=256, cta_group=2)
+    ops.gemm(a, wt, b_layout=1, resid=resid, out_f32=ref.clone(), block_n=256, cta_group=1)   # 1-CTA 256-wide tiles split too
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    # wgrad layout without K split: D[n, k2] = dY^T X with dY [rows, n], X [rows, k2]
+    rows, k2 = 512, 6400
+    dy, x = _rand((rows, 6400), 54, 0.1), _rand((rows, n), 55)
+    acc, accr = torch.zeros((6400, n), device="cuda"), torch.zeros((6400, n), device="cuda")
+    ops.gemm(dy, x, a_layout=1, b_layout=1, out_f32=accr, accumulate=True, split_k=1, block_n=128, cta_group=1)
+    ops.gemm(dy, x, a_layout=1, b_layout=1, out_f32=acc, accumulate=True, split_k=1, block_n=256, cta_group=2)
+    torch.cuda.synchronize()
+    assert torch.equal(acc, accr)
+
+
+@pytest.mark.parametrize("m,n,k", [(896, 1024, 4096), (896, 1024, 12288), (200, 512, 2048)])
+@pytest.mark.parametrize("split_k", [0, 1, 4])
+def test_gemm_split_k_with_linear_fused_epilogue(m, n, k, split_k):
+    """Split-K with bias + dropout + residual: out = resid + keep/(1-p) * (A W^T + bias), every split
+    scales its partial sum, split 0 adds bias and residual, all via red.add into a zeroed buffer.
+    Same for the dgrad layout with the ReLU/dropout gate."""
+    ops = _ops()
+    a, w = _rand((m, k), 61), _rand((n, k), 62, 0.05)
+    bias = torch.randn(n, device="cuda")
+    resid = torch.randn(m, n, device="cuda")
+    ref = torch.empty((m, n), device="cuda")
+    ops.gemm(a, w, bias=bias, dropout_p=0.1, seed=9, resid=resid, out_f32=ref)
+    out = torch.zeros((m, n), device="cuda")
+    ops.gemm(a, w, bias=bias, dropout_p=0.1, seed=9, resid=resid, out_f32=out, accumulate=True, split_k=split_k)
+    torch.cuda.synchronize()
+    _close(out, ref, 2e-5, "split-K fused epilogue")
+    assert torch.equal(out == resid, ref == resid)          # identical dropout mask
+    wt = _rand((k, n), 63, 0.05)
+    gate = _rand((m, n), 64)
+    ops.gemm(a, wt, b_layout=1, gate=gate, gate_scale=1.25, resid=resid, out_f32=ref)
+    out.zero_()
+    ops.gemm(a, wt, b_layout=1, gate=gate, gate_scale=1.25, resid=resid, out_f32=out, accumulate=True, split_k=split_k)
+    torch.cuda.synchronize()
+    _close(out, ref, 2e-5, "split-K gated dgrad")
