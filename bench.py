@@ -361,6 +361,16 @@ def main():
     per_step = capi.launch_count - c0
     roof = gemm_roofline(probe, batch_dev, peaks)
 
+    # data parallel sanity: every replica applied the same summed gradients, so the parameters of all
+    # ranks must still be bit-identical after ~100 optimiser steps (per-parameter checksums, max - min over ranks)
+    divergence = None
+    if world > 1:
+        sums = torch.stack([p.detach().double().sum() for p in trainer.net.parameters()])
+        hi, lo = sums.clone(), sums.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        divergence = float((hi - lo).abs().max().item())
+
     if rank == 0:
         flops_sample = hot_path_train_flops_per_sample(cfg)
         sustained = peaks.get("bf16_tflops_sustained", 1400.0)
@@ -386,6 +396,8 @@ def main():
                          "frac_of_sustained_peak": value / world * flops_sample / 1e12 / sustained},
             "loss": loss_val,
         }
+        if divergence is not None:
+            line["replica_checksum_divergence"] = divergence
         if world == 1 and not args.skip_cpu:
             t, cores = cpu_port_step_time(args.model, args.cpu_batch, 2, 1)
             line["cpu_baseline"] = {"value": args.cpu_batch / t, "unit": "samples/s", "cores": cores, "kind": "port",
