@@ -49,6 +49,7 @@ class FusedAdamW(object):
         self._shadow = {}       # id(param) -> up to two contiguous bf16 / fp32 tensors of the same numel
         self._managed = []      # LinearParams whose operand copies this optimiser keeps current
         self._tables = {}
+        self._captured = []
         # pinned staging for the segment tables, allocated up front: a table built while a CUDA graph is
         # being captured must not allocate host memory, and the captured upload re-reads its buffer
         # on every replay, so buffers are never recycled
@@ -113,6 +114,8 @@ class FusedAdamW(object):
         table.copy_(host, non_blocking=True)      # captured with the step when a graph is being recorded
         entry = (table, host, len(rows), chunk)
         self._tables[key] = entry
+        if torch.cuda.is_current_stream_capturing():
+            self._captured.append(entry)     # a graph replays the upload from `host`: keep it alive for good
         return entry
 
     def _begin_step(self):

@@ -70,6 +70,24 @@ def _worker(rank, world, port, mode, out):
         sync = dp.attach(model, overlap=True)
         loss_fn(model(xs), ys).backward()
         assert sync.launches >= 2      # layer buffers + hooked parameters went out separately
+    elif mode == "buckets":
+        # the optimiser consumes the all-reduces one by one (FusedAdamW.step_buckets protocol):
+        # nothing is waited for at the end of backward, every gradient belongs to exactly one bucket
+        sync = dp.attach(model, overlap=True)
+        sync.defer_wait = True
+        loss_fn(model(xs), ys).backward()
+        buckets = sync.take_buckets()
+        assert len(buckets) >= 2 and sync.pending == []
+        seen = set()
+        for work, tensors in buckets:
+            work.wait()
+            for t in tensors:
+                lo, hi = t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()
+                for n, p in model.named_parameters():
+                    if lo <= p.grad.data_ptr() < hi:
+                        assert n not in seen
+                        seen.add(n)
+        assert seen == {n for n, _ in model.named_parameters()}
     else:
         dp.attach(model, overlap=False)
         sys.path.insert(0, ROOT)
@@ -90,9 +108,9 @@ def _worker(rank, world, port, mode, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["overlap", "at_step"])
+@pytest.mark.parametrize("mode", ["overlap", "buckets", "at_step"])
 def test_two_rank_sum_allreduce_equals_global_batch_gradient(mode, tmp_path):
     out = str(tmp_path / "ok.txt")
-    port = 29500 + (os.getpid() % 2000) + (0 if mode == "overlap" else 1)
+    port = 29500 + (os.getpid() % 2000) + {"overlap": 0, "at_step": 1, "buckets": 2}[mode]
     mp.spawn(_worker, args=(2, port, mode, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
