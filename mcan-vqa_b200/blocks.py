@@ -162,7 +162,8 @@ SPLITK_MIN_K = 2048
 
 
 def _resid_gemm(a, w, M, N, K, dev, **kw):
-    """out_f32[M,N] = epilogue(a w^T) for an epilogue without ReLU / bf16 output; split-K when short and deep."""
+    """out_f32[M,N] = epilogue(a w^T) for an epilogue without ReLU / bf16 output; split-K when short and deep.
+    Used by the backward chain only (the forward's FFN2 applies the same rule when grad is enabled)."""
     if SPLITK_MIN_K > 0 and M <= SPLITK_MAX_ROWS and K >= SPLITK_MIN_K:
         out = torch.zeros((M, N), dtype=_F32, device=dev)
         ops.gemm(a, w, out_f32=out, accumulate=True, **kw)
@@ -583,7 +584,9 @@ def mlp_fwd(rt, mlp, x, norm=None):
             out = torch.empty((M, ldp), dtype=_F32, device=dev)[:, :lp2.n]
         _mm(rt, ha, lp2, 0, 1, out_f32=out)
         return out, c
-    use_sk = SPLITK_MIN_K > 0 and M <= SPLITK_MAX_ROWS and lp1.n >= SPLITK_MIN_K     # see _resid_gemm
+    # split-K (see _resid_gemm) only when training: fp32 atomics make the result depend on the
+    # arrival order (1e-7 relative), and inference must stay bit-reproducible run to run
+    use_sk = SPLITK_MIN_K > 0 and M <= SPLITK_MAX_ROWS and lp1.n >= SPLITK_MIN_K and torch.is_grad_enabled()
     s = torch.zeros((M, lp2.n), dtype=_F32, device=dev) if use_sk else _empty(M, lp2.n, _F32, dev)
     c.seed_out = rt.seed()
     _mm(rt, ha, lp2, 0, 1, dropout_p=rt.p, seed=c.seed_out, resid=x.f32, out_f32=s, accumulate=use_sk)

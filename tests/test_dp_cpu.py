@@ -68,13 +68,20 @@ def _worker(rank, world, port, mode, out):
     loss_fn = torch.nn.BCELoss(reduction="sum")
     if mode == "overlap":
         sync = dp.attach(model, overlap=True)
+        sync.bucket_bytes = 0          # every layer's buffers go out as soon as they are complete
         loss_fn(model(xs), ys).backward()
         assert sync.launches >= 2      # layer buffers + hooked parameters went out separately
+    elif mode == "merged":
+        sync = dp.attach(model, overlap=True)
+        assert sync.bucket_bytes > 1e6  # default: layers are merged into >= 192 MB buckets
+        loss_fn(model(xs), ys).backward()
+        assert sync.launches == 1      # the toy model's gradients fit one bucket
     elif mode == "buckets":
         # the optimiser consumes the all-reduces one by one (FusedAdamW.step_buckets protocol):
         # nothing is waited for at the end of backward, every gradient belongs to exactly one bucket
         sync = dp.attach(model, overlap=True)
         sync.defer_wait = True
+        sync.bucket_bytes = 0
         loss_fn(model(xs), ys).backward()
         buckets = sync.take_buckets()
         assert len(buckets) >= 2 and sync.pending == []
@@ -108,9 +115,9 @@ def _worker(rank, world, port, mode, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["overlap", "buckets", "at_step"])
+@pytest.mark.parametrize("mode", ["overlap", "merged", "buckets", "at_step"])
 def test_two_rank_sum_allreduce_equals_global_batch_gradient(mode, tmp_path):
     out = str(tmp_path / "ok.txt")
-    port = 29500 + (os.getpid() % 2000) + {"overlap": 0, "at_step": 1, "buckets": 2}[mode]
+    port = 29500 + (os.getpid() % 2000) + {"overlap": 0, "at_step": 1, "buckets": 2, "merged": 3}[mode]
     mp.spawn(_worker, args=(2, port, mode, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
