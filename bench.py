@@ -382,6 +382,8 @@ def main():
                        "global_batch": BATCH * world, "parallelism": "dp%d" % world, "launch": graph_note,
                        "sms_reserved_for_nccl": reserve if world > 1 else 0,
                        "gemm_tile_schedule": "dynamic" if dynamic else "static",
+                       "grad_exchange": ("all-reduce(SUM), %s, buckets >= %s MB" % (os.environ.get("MCAN_DP_COMPRESS", "") or "fp32",
+                                                                                 os.environ.get("MCAN_DP_BUCKET_MB", "192"))) if world > 1 else "none",
                        "optimizer": "fused multi-tensor AdamW (library kernel, emits the bf16 operand copies)",
                        "decoder_wgrads": "second stream, next to the encoder backward" if blocks.OVERLAP_WGRAD else "inline",
                        "l2": "working set per step (fp32 masters + bf16 copies + activations, > 1 GB) exceeds the 126 MB L2; no explicit flush"},

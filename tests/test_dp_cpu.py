@@ -76,6 +76,12 @@ def _worker(rank, world, port, mode, out):
         assert sync.bucket_bytes > 1e6  # default: layers are merged into >= 192 MB buckets
         loss_fn(model(xs), ys).backward()
         assert sync.launches == 1      # the toy model's gradients fit one bucket
+    elif mode == "bf16":
+        # opt-in compressed exchange: bf16 on the wire, fp32 sums written back into .grad
+        sync = dp.attach(model, overlap=True)
+        sync.compress = "bf16"
+        loss_fn(model(xs), ys).backward()
+        assert sync.launches == 1
     elif mode == "buckets":
         # the optimiser consumes the all-reduces one by one (FusedAdamW.step_buckets protocol):
         # nothing is waited for at the end of backward, every gradient belongs to exactly one bucket
@@ -108,16 +114,19 @@ def _worker(rank, world, port, mode, out):
         ref = _Toy()
         ref.load_state_dict(model.state_dict())
         loss_fn(ref(x), y).backward()
+        tol = dict(rtol=2e-2, atol=1e-3) if mode == "bf16" else dict(rtol=1e-5, atol=1e-6)
         for n, p in ref.named_parameters():
-            assert torch.allclose(grads[n], p.grad, rtol=1e-5, atol=1e-6), n
+            assert torch.allclose(grads[n], p.grad, **tol), n
+            if mode == "bf16":     # the values really went through bf16
+                assert torch.equal(grads[n], grads[n].to(torch.bfloat16).float()), n
         open(out, "w").write("ok")
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["overlap", "merged", "buckets", "at_step"])
+@pytest.mark.parametrize("mode", ["overlap", "merged", "bf16", "buckets", "at_step"])
 def test_two_rank_sum_allreduce_equals_global_batch_gradient(mode, tmp_path):
     out = str(tmp_path / "ok.txt")
-    port = 29500 + (os.getpid() % 2000) + {"overlap": 0, "at_step": 1, "buckets": 2, "merged": 3}[mode]
+    port = 29500 + (os.getpid() % 2000) + {"overlap": 0, "at_step": 1, "buckets": 2, "merged": 3, "bf16": 4}[mode]
     mp.spawn(_worker, args=(2, port, mode, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
