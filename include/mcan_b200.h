@@ -229,6 +229,12 @@ int mcan_colsum_bf16(const void* x, int64_t rows, int64_t cols, int64_t ld, floa
 int mcan_colsum_f32(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out,
                     void* stream);
 
+/* Launch plan mcan_gemm would use for this shape on `sms` SMs (0 = the current device): pure host logic,
+ * callable without a GPU.  plan_out[7] = {block_n, CTAs per cluster, m_tiles, n_tiles, K splits,
+ * full_tiles (tiles issued at full width; the remaining ones as two half-width units each), work units}. */
+int mcan_gemm_plan(int64_t m, int64_t n, int64_t k, int32_t accumulate, int32_t split_k, int32_t block_n,
+                   int32_t cta_group, int32_t sms, int32_t* plan_out);
+
 /* -- fused multi-tensor AdamW (reference core/model/optim.py:58-64) -----------------
  * One launch updates every fp32 master parameter with torch.optim.AdamW semantics (decoupled weight
  * decay, bias correction with the step count t) and re-emits, in the same pass, the operand copy

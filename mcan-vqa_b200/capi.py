@@ -120,6 +120,7 @@ SYMBOLS = {
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcan_cast_bf16": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "mcan_cast_multi": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_void_p]),
+    "mcan_gemm_plan": (ctypes.c_int, [c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mcan_adamw_multi": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_float, c_float, c_float,
                                         c_float, c_void_p]),
     "mcan_debug_hog": (ctypes.c_int, [c_int32, c_int64, c_int32, c_void_p]),

@@ -882,9 +882,71 @@ static int pick_splits(int64_t tiles, int kblocks, int slots) {
     return best;
 }
 
+// Launch plan of one GEMM: tile shape, cluster shape, K splits, tail splitting.  Pure host logic
+// (exposed as mcan_gemm_plan so that it can be tested without a GPU).
+struct GemmPlan {
+    int block_n, cl, cg, mc;        // cl = CTAs per cluster (1, 2, 4), cg = CTAs per MMA, mc = pairs per cluster
+    int m_tiles, n_tiles, splits, full_tiles, units;
+};
+
+static int plan_gemm(int64_t m, int64_t n, int64_t k, bool accumulate, int split_k, int block_n_req, int cg_req,
+                     int sms, GemmPlan* out) {
+    const int kblocks = (int)((k + BLOCK_K - 1) / BLOCK_K);
+    TileCfg tc = pick_tile(m, n, k, accumulate, sms);
+    if (block_n_req) tc.bn = block_n_req;
+    if (cg_req) tc.cg = cg_req;
+    if (tc.bn == 64 && tc.cg != 1 && !block_n_req) tc.bn = 128;     // forced cta_group: 64-wide tiles are single-CTA
+    // cta_group 4 = CTA pairs (cta_group::2 MMAs) in clusters of two pairs that share the B tile by multicast
+    const int block_n = tc.bn, cl = tc.cg, cg = cl == 4 ? 2 : cl, mc = cl == 4 ? 2 : 1;
+    MCAN_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "mcan_gemm: block_n=%d", block_n);
+    MCAN_REQUIRE(block_n != 64 || cl == 1, "mcan_gemm: block_n 64 is a single-CTA tile");
+    MCAN_REQUIRE(cl == 1 || cl == 2 || cl == 4, "mcan_gemm: cta_group=%d", cl);
+    MCAN_REQUIRE(cl != 4 || block_n == 256, "mcan_gemm: cta_group 4 needs block_n 256");
+    out->block_n = block_n;
+    out->cl = cl;
+    out->cg = cg;
+    out->mc = mc;
+    out->m_tiles = (int)((m + BLOCK_M * cl - 1) / (BLOCK_M * cl));
+    out->n_tiles = (int)((n + block_n - 1) / block_n);
+    const int slots = sms / cl;
+    MCAN_REQUIRE(slots > 0, "mcan_gemm: %d SMs cannot hold a cluster of %d", sms, cl);
+    int splits = 1;
+    if (accumulate) {
+        splits = split_k > 0 ? split_k : pick_splits((int64_t)out->m_tiles * out->n_tiles, kblocks, slots);
+        if (splits > kblocks) splits = kblocks;
+    }
+    out->splits = splits;
+    // tail splitting: the last, partial wave as half-width tiles (see GemmParams::full_tiles)
+    const int tiles = out->m_tiles * out->n_tiles;
+    out->full_tiles = tiles;
+    const int rem = tiles % slots;
+    if (g_tail_split.load(std::memory_order_relaxed) && splits == 1 && mc == 1 && block_n == 256 &&
+        n % 256 == 0 && tiles > slots && rem > 0 && 2 * rem <= slots)
+        out->full_tiles = tiles - rem;
+    out->units = splits > 1 ? tiles * splits : out->full_tiles + 2 * (tiles - out->full_tiles);
+    return 0;
+}
+
 }  // namespace mcan
 
 using namespace mcan;
+
+extern "C" int mcan_gemm_plan(int64_t m, int64_t n, int64_t k, int32_t accumulate, int32_t split_k,
+                              int32_t block_n, int32_t cta_group, int32_t sms, int32_t* plan_out) {
+    MCAN_REQUIRE(plan_out != nullptr && m > 0 && n > 0 && k > 0, "mcan_gemm_plan: bad args");
+    if (sms <= 0) sms = device_num_sms();
+    MCAN_REQUIRE(sms > 0, "mcan_gemm_plan: no CUDA device and no SM count given");
+    GemmPlan pl;
+    if (int rc = plan_gemm(m, n, k, accumulate != 0, split_k, block_n, cta_group, sms, &pl)) return rc;
+    plan_out[0] = pl.block_n;
+    plan_out[1] = pl.cl;
+    plan_out[2] = pl.m_tiles;
+    plan_out[3] = pl.n_tiles;
+    plan_out[4] = pl.splits;
+    plan_out[5] = pl.full_tiles;
+    plan_out[6] = pl.units;
+    return 0;
+}
 
 extern "C" int mcan_set_sm_limit(int sms) {
     MCAN_REQUIRE(sms >= 0, "mcan_set_sm_limit: %d", sms);
@@ -935,35 +997,15 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     p.n = (int)a->n;
     p.k = (int)a->k;
     p.kblocks = (int)((a->k + BLOCK_K - 1) / BLOCK_K);
-    TileCfg tc = pick_tile(a->m, a->n, a->k, a->accumulate != 0, sms);
-    if (a->block_n) tc.bn = a->block_n;
-    if (a->cta_group) tc.cg = a->cta_group;
-    if (tc.bn == 64 && tc.cg != 1 && !a->block_n) tc.bn = 128;     // forced cta_group: 64-wide tiles are single-CTA
-    // cta_group 4 = CTA pairs (cta_group::2 MMAs) in clusters of two pairs that share the B tile by multicast
-    const int block_n = tc.bn, cl = tc.cg, cg = cl == 4 ? 2 : cl, mc = cl == 4 ? 2 : 1;
-    MCAN_REQUIRE(block_n == 64 || block_n == 128 || block_n == 256, "mcan_gemm: block_n=%d", block_n);
-    MCAN_REQUIRE(block_n != 64 || cl == 1, "mcan_gemm: block_n 64 is a single-CTA tile");
-    MCAN_REQUIRE(cl == 1 || cl == 2 || cl == 4, "mcan_gemm: cta_group=%d", cl);
-    MCAN_REQUIRE(cl != 4 || block_n == 256, "mcan_gemm: cta_group 4 needs block_n 256");
-    p.m_tiles = (int)((a->m + BLOCK_M * cl - 1) / (BLOCK_M * cl));
-    p.n_tiles = (int)((a->n + block_n - 1) / block_n);
-    const int slots = sms / cl;
-    int splits = 1;
-    if (a->accumulate) {
-        splits = a->split_k > 0 ? a->split_k : pick_splits((int64_t)p.m_tiles * p.n_tiles, p.kblocks, slots);
-        if (splits > p.kblocks) splits = p.kblocks;
-    }
-    p.splits = splits;
-    // tail splitting: the last, partial wave as half-width tiles (see GemmParams::full_tiles)
-    {
-        const int tiles = p.m_tiles * p.n_tiles;
-        p.full_tiles = tiles;
-        const int rem = tiles % slots;
-        if (g_tail_split.load(std::memory_order_relaxed) && splits == 1 && mc == 1 && block_n == 256 &&
-            a->n % 256 == 0 && tiles > slots && rem > 0 && 2 * rem <= slots)
-            p.full_tiles = tiles - rem;
-        p.units = splits > 1 ? tiles * splits : p.full_tiles + 2 * (tiles - p.full_tiles);
-    }
+    GemmPlan plan;
+    if (int rc = plan_gemm(a->m, a->n, a->k, a->accumulate != 0, a->split_k, a->block_n, a->cta_group, sms, &plan))
+        return rc;
+    const int block_n = plan.block_n, cl = plan.cl, cg = plan.cg, mc = plan.mc;
+    p.m_tiles = plan.m_tiles;
+    p.n_tiles = plan.n_tiles;
+    p.splits = plan.splits;
+    p.full_tiles = plan.full_tiles;
+    p.units = plan.units;
 
     for (int s = 0; s < a->num_seg; ++s) {
         MCAN_REQUIRE(a->a[s] && a->b[s], "mcan_gemm: null operand in segment %d", s);

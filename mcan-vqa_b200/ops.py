@@ -109,6 +109,16 @@ def set_pdl(enabled):
     capi.check(capi.load().mcan_set_pdl(1 if enabled else 0), "mcan_set_pdl")
 
 
+def gemm_plan(m, n, k, *, accumulate=False, split_k=0, block_n=0, cta_group=0, sms=0):
+    """The launch plan mcan_gemm uses for this shape (host logic only, no GPU needed when `sms` is given)."""
+    out = (ctypes.c_int32 * 7)()
+    capi.check(capi.load().mcan_gemm_plan(int(m), int(n), int(k), 1 if accumulate else 0, int(split_k), int(block_n),
+                                          int(cta_group), int(sms), ctypes.cast(out, ctypes.c_void_p)), "mcan_gemm_plan")
+    capi.launch_count -= 1      # not a kernel launch
+    keys = ("block_n", "cluster", "m_tiles", "n_tiles", "splits", "full_tiles", "units")
+    return dict(zip(keys, (int(v) for v in out)))
+
+
 def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, seed=0, gate=None,
          gate_scale=1.0, resid=None, out_f32=None, out_bf16=None, out_lo=None, accumulate=False,
          split_k=0, block_n=0, cta_group=0):

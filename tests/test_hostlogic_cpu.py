@@ -1,0 +1,109 @@
+"""Host-side logic that needs no GPU: the GEMM launch planner (tile / cluster / split-K / tail
+splitting choice, include/mcan_b200.h: mcan_gemm_plan) and the protocol by which an optimiser
+keeps the bf16 operand copies of blocks.LinearParams current."""
+import pytest
+import torch
+
+SMS = 148        # B200
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from mcan_vqa_b200 import ops as o
+    return o
+
+
+def _tiles(pl):
+    return pl["m_tiles"] * pl["n_tiles"]
+
+
+@pytest.mark.parametrize("m,n,k,acc", [
+    (6400, 4096, 1024, False), (6400, 1024, 4096, False), (6400, 3072, 1024, False), (6400, 1024, 1024, False),
+    (896, 1024, 4096, False), (896, 4096, 1024, False), (896, 1024, 1024, False), (64, 3129, 2048, False),
+    (1024, 1024, 6400, True), (4096, 1024, 6400, True), (1024, 1024, 896, True), (896, 1024, 4096, True),
+    (100, 512, 512, False), (42, 136, 64, False), (1, 8, 8, False),
+])
+def test_plan_invariants(ops, m, n, k, acc):
+    pl = ops.gemm_plan(m, n, k, accumulate=acc, sms=SMS)
+    assert pl["block_n"] in (64, 128, 256) and pl["cluster"] in (1, 2)       # clusters of 4 are never auto-selected
+    assert pl["m_tiles"] * 128 * pl["cluster"] >= m and pl["n_tiles"] * pl["block_n"] >= n
+    assert (pl["m_tiles"] - 1) * 128 * pl["cluster"] < m and (pl["n_tiles"] - 1) * pl["block_n"] < n
+    kblocks = (k + 63) // 64
+    assert 1 <= pl["splits"] <= kblocks and (acc or pl["splits"] == 1)
+    tiles = _tiles(pl)
+    assert 0 < pl["full_tiles"] <= tiles
+    if pl["splits"] > 1:
+        assert pl["full_tiles"] == tiles and pl["units"] == tiles * pl["splits"]
+    else:
+        assert pl["units"] == pl["full_tiles"] + 2 * (tiles - pl["full_tiles"])
+    if pl["full_tiles"] < tiles:          # tail splitting: whole waves at full width, the rest fits one half-wave
+        slots = SMS // pl["cluster"]
+        assert pl["block_n"] == 256 and n % 256 == 0 and pl["full_tiles"] % slots == 0
+        assert 2 * (tiles - pl["full_tiles"]) <= slots
+
+
+def test_plan_of_the_mcan_large_shapes(ops):
+    """Regression guard for the choices the measurements in DESIGN.md section 4 were taken with."""
+    ffn1 = ops.gemm_plan(6400, 4096, 1024, sms=SMS)          # 400 tiles on 74 pairs: 5 whole waves + 30 tiles split
+    assert (ffn1["block_n"], ffn1["cluster"], ffn1["full_tiles"], ffn1["units"]) == (256, 2, 370, 430)
+    merge = ops.gemm_plan(6400, 1024, 1024, sms=SMS)         # 100 tiles: 74 full + 26 x 2 halves
+    assert (merge["block_n"], merge["cluster"], merge["full_tiles"], merge["units"]) == (256, 2, 74, 126)
+    enc = ops.gemm_plan(896, 1024, 1024, sms=SMS)            # short M, short K: 128 x 64 single-CTA tiles
+    assert (enc["block_n"], enc["cluster"]) == (64, 1) and enc["units"] == 7 * 16
+    enc_sk = ops.gemm_plan(896, 1024, 4096, accumulate=True, sms=SMS)    # split-K with the linear fused epilogue
+    assert enc_sk["block_n"] == 256 and enc_sk["cluster"] == 2 and enc_sk["splits"] >= 4
+    assert _tiles(enc_sk) * enc_sk["splits"] <= SMS // 2
+    wgrad = ops.gemm_plan(1024, 1024, 6400, accumulate=True, sms=SMS)    # deep split-K: the 256 x 256 pair tile
+    assert (wgrad["block_n"], wgrad["cluster"], wgrad["splits"]) == (256, 2, 4)
+    head = ops.gemm_plan(64, 3129, 2048, sms=SMS)
+    assert head["cluster"] == 1 and head["n_tiles"] * head["block_n"] >= 3129
+
+
+def test_plan_honours_forced_configuration_and_sm_limit(ops):
+    pl = ops.gemm_plan(6400, 4096, 1024, block_n=256, cta_group=4, sms=SMS)      # two pairs per cluster: 512-row super-tiles
+    assert pl["cluster"] == 4 and pl["m_tiles"] == 13 and pl["full_tiles"] == _tiles(pl)
+    pl = ops.gemm_plan(6400, 1024, 1024, cta_group=2, sms=SMS)
+    assert pl["cluster"] == 2 and pl["block_n"] in (128, 256)
+    few = ops.gemm_plan(6400, 4096, 1024, sms=40)             # persistent grids shrink with mcan_set_sm_limit
+    assert few["units"] >= _tiles(few)
+    from mcan_vqa_b200 import capi
+    with pytest.raises(capi.McanError):
+        ops.gemm_plan(6400, 4096, 1024, block_n=64, cta_group=2, sms=SMS)
+
+
+class _FakeOptimizer(object):
+    epoch = 0
+
+
+def test_linear_params_shadow_protocol():
+    """blocks.LinearParams: first use casts; once an optimiser manages the copy nothing is re-cast
+    (even on the forced per-forward refresh) until a master changes behind its back; the low-order
+    halves of the split-precision mode are refreshed once per optimiser epoch."""
+    from mcan_vqa_b200.blocks import LinearParams
+    lin1, lin2 = torch.nn.Linear(16, 8), torch.nn.Linear(16, 24)
+    lp = LinearParams([(lin1.weight, lin1.bias), (lin2.weight, lin2.bias)])
+    items = lp.shadow_items()
+    assert [tuple(d.shape) for d, _ in items] == [(8, 16), (8,), (24, 16), (24,)]
+    assert items[0][0].dtype == torch.bfloat16 and items[1][0].dtype == torch.float32
+    assert items[0][0].data_ptr() == lp.w.data_ptr() and items[2][0].data_ptr() == lp.w[8:].data_ptr()
+    assert len(lp.pending()) == 4                 # first use: everything
+    assert lp.pending() == []                     # current
+    assert len(lp.pending(force=True)) == 4       # unmanaged: a training forward re-casts
+    opt = _FakeOptimizer()
+    lp.managed = opt
+    lp.pending()
+    assert lp.pending(force=True) == []           # managed: the optimiser keeps the copy current
+    with torch.no_grad():
+        lin1.weight.add_(1.0)                     # e.g. load_state_dict: version counter moves
+    assert len(lp.pending()) == 4
+    assert lp.pending(force=True) == []
+    # split precision: lo halves are created on demand and refreshed once per optimiser epoch
+    first = lp.pending(need_lo=True)
+    assert len(first) == 4 and len(first[0]) == 3
+    assert lp.pending(need_lo=True) == []
+    opt.epoch += 1
+    assert len(lp.pending(need_lo=True)) == 4
+    assert lp.pending(need_lo=True) == []
+    # a weight whose row length is not a multiple of 8 has a padded copy: not eligible for shadowing
+    odd = torch.nn.Linear(12, 4)
+    assert LinearParams([(odd.weight, odd.bias)]).shadow_items() is None
