@@ -401,9 +401,9 @@ def main():
         if divergence is not None:
             line["replica_checksum_divergence"] = divergence
         if world == 1 and not args.skip_cpu:
-            t, cores = cpu_port_step_time(args.model, args.cpu_batch, 2, 1)
+            t, cores = cpu_port_step_time(args.model, args.cpu_batch, 12, 2)     # about 10 s of CPU work
             line["cpu_baseline"] = {"value": args.cpu_batch / t, "unit": "samples/s", "cores": cores, "kind": "port",
-                                    "sample": "oracle port, %d-sample training steps (fwd+bwd+AdamW, dropout 0.1), 2 timed after 1 warm-up" % args.cpu_batch}
+                                    "sample": "oracle port, %d-sample training steps (fwd+bwd+AdamW, dropout 0.1), 12 timed after 2 warm-up" % args.cpu_batch}
         print(json.dumps(line), flush=True)
     if world > 1:
         # every collective this rank takes part in is done; skip the NCCL teardown (it can hang
