@@ -239,6 +239,18 @@ def net_forward(p, v, ques_ix, cfg):
     return probs, v, v_mask, v_w, q, q_mask, q_w, a
 
 
+def classifier_forward(p, v, cfg):
+    """core/model/net.py:155-184 (ClassifierNet.forward): image-only SA stack -> AttFlat -> proj_norm ->
+    proj -> sigmoid.  Returns the reference's 5-tuple (probs, v, v_mask, v_w, a)."""
+    v_mask = make_mask(v)
+    v = linear(v, p["img_feat_linear.weight"], p["img_feat_linear.bias"])
+    v = mca_classifier(p, "backbone.", v, v_mask, cfg)
+    img, v_w = attflat(p, "attflat_img.", v, v_mask, cfg)
+    a = layer_norm(img, p["proj_norm.a_2"], p["proj_norm.b_2"])
+    probs = torch.sigmoid(linear(a, p["proj.weight"], p["proj.bias"]))
+    return probs, v, v_mask, v_w, a
+
+
 def bce_sum(probs, target):
     """torch.nn.BCELoss(reduction='sum') (core/exec.py:67): log clamped at -100 like torch."""
     lp = torch.clamp(torch.log(probs), min=-100.0)

@@ -305,3 +305,30 @@ def test_top1_agreement_1024_samples_small():
     print("top-1 agreement over %d samples: fp32 mode %.4f, bf16 mode %.4f" % (total, same32 / total, same16 / total))
     assert same32 / total >= 0.999
     assert same16 / total >= 0.95
+
+
+def test_classifier_net_against_oracle():
+    """ClassifierNet / MCAClassifier (reference net.py:138-184, mca.py:189-207): the SA-only
+    stack over the image regions, forward 5-tuple and every parameter gradient vs the oracle (which
+    tests/test_oracle_cpu.py pins to the unmodified reference module)."""
+    from core.model.net import ClassifierNet
+    cfg = orc.Cfg(dropout_rate=0.0, **dict(orc.TINY, layer=2))
+    answer_size = 24
+    sd = orc.synth_state_dict(cfg, 50, answer_size, seed=21, classifier=True)
+    v, _, ans = orc.synth_batch(cfg, 5, 12, 7, 50, answer_size, seed=22, ragged="random")
+    p = {k: t.double().clone().requires_grad_(True) for k, t in sd.items()}
+    ref = orc.classifier_forward(p, v.double(), cfg)
+    orc.bce_sum(ref[0], ans.double()).backward()
+    net = ClassifierNet(cfg, answer_size)
+    assert [k for k in net.state_dict()] == [k for k in sd]          # reference key order, incl. the unused attflat_lang
+    net = _load_params(net, sd).train()
+    probs, v_out, v_mask, v_w, a = net(v.cuda())
+    assert torch.equal(v_mask.cpu(), ref[2])
+    assert _rel_max(probs, ref[0]) < TOL_OUT and _rel_max(a, ref[4]) < 3e-2 and _rel_max(v_w, ref[3]) < 3e-2
+    valid = ~ref[2].reshape(5, 12)
+    assert _rel_max(v_out.cpu()[valid], ref[1][valid]) < 3e-2
+    loss = torch.nn.BCELoss(reduction="sum")(probs, ans.cuda())
+    loss.backward()
+    used = [(n, q) for n, q in net.named_parameters() if not n.startswith("attflat_lang.")]
+    _check_param_grads(used, {n: p[n].grad for n, _ in used}, TOL_GRAD, "classifier")
+    assert all(q.grad is None for n, q in net.named_parameters() if n.startswith("attflat_lang."))

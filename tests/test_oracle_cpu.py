@@ -158,3 +158,34 @@ def test_oracle_matches_live_reference_small_config():
         mine = orc.net_forward(sd, v, q, cfg)
     assert (ref[0] - mine[0]).abs().max() < 1e-5
     assert (ref[1] - mine[1]).abs().max() < 1e-4 and (ref[4] - mine[4]).abs().max() < 1e-4
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/core/model"), reason="reference not mounted")
+def test_oracle_classifier_matches_live_reference():
+    """ClassifierNet (reference net.py:138-184: SA-only stack over the image): outputs and
+    parameter gradients of the oracle restatement vs the unmodified reference module."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import make_golden
+    ref_net, _, _ = make_golden.import_reference()
+    cfg = orc.Cfg(dropout_rate=0.0, **dict(orc.TINY, layer=2))
+    torch.manual_seed(1)
+    net = ref_net.ClassifierNet(cfg, 24).double().train()
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    assert set(sd) == {n for n, _ in orc.param_shapes(cfg, 50, 24, classifier=True)}
+    v, _, ans = orc.synth_batch(cfg, 3, 12, 7, 50, 24, seed=6, ragged="random")
+    v, ans = v.double(), ans.double()
+    ref = net(v)
+    orc.bce_sum(ref[0], ans).backward()
+    p = {k: t.clone().requires_grad_(True) for k, t in sd.items()}
+    mine = orc.classifier_forward(p, v, cfg)
+    orc.bce_sum(mine[0], ans).backward()
+    for a, b in zip(ref, mine):
+        assert a.shape == b.shape and (a.double() - b.double()).abs().max() < 1e-10
+    gmax = max(float(q.grad.abs().max()) for q in net.parameters() if q.grad is not None)
+    for n, q in net.named_parameters():
+        if q.grad is None:            # attflat_lang is part of the state_dict but unused (net.py:150)
+            assert n.startswith("attflat_lang.") and p[n].grad is None
+            continue
+        # (the key biases have a mathematically zero gradient -- softmax is shift invariant -- so the
+        # error is measured against the largest gradient entry of the model, not per tensor)
+        assert np.abs(p[n].grad.numpy() - q.grad.numpy()).max() < 1e-10 * gmax, n
