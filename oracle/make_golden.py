@@ -146,13 +146,43 @@ def module_goldens(ref_mca, ref_utils, ref_net):
     print("modules_tiny: %d arrays" % len(out))
 
 
+def classifier_golden(ref_net):
+    """ClassifierNet (reference net.py:138-184): the image-only SA stack; forward 5-tuple, loss, grad digests."""
+    cfg = orc.Cfg(dropout_rate=0.0, **dict(orc.TINY, layer=2))
+    batch, regions, answer_size, wseed, bseed = 5, 12, 24, 21, 22
+    sd = orc.synth_state_dict(cfg, 50, answer_size, seed=wseed, dtype=torch.float64, classifier=True)
+    v, _, ans = orc.synth_batch(cfg, batch, regions, 7, 50, answer_size, seed=bseed, ragged="random", dtype=torch.float64)
+    net = ref_net.ClassifierNet(cfg, answer_size).double()
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    probs, v_out, v_mask, v_w, a = net(v)
+    loss = torch.nn.BCELoss(reduction="sum")(probs, ans)
+    loss.backward()
+    used = [(n, p) for n, p in net.named_parameters() if p.grad is not None]
+    out = {
+        "img_feat": v.numpy(), "ans": ans.numpy(), "probs": probs.detach().numpy(), "v": v_out.detach().numpy(),
+        "v_mask": v_mask.numpy(), "v_w": v_w.detach().numpy(), "a": a.detach().numpy(), "loss": np.array(loss.item()),
+        "meta": np.array([batch, regions, answer_size, wseed, bseed]),
+        "grad_names": np.array([n for n, _ in used]),
+        "grad_digests": np.stack([orc.grad_digest(p.grad) for _, p in used]),
+        "no_grad_names": np.array([n for n, p in net.named_parameters() if p.grad is None]),
+    }
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "classifier_tiny.npz"), **out)
+    print("classifier_tiny loss=%.6f  params with grad=%d, without=%d" % (loss.item(), len(used), len(out["no_grad_names"])))
+
+
 def main():
     torch.manual_seed(0)
     ref_net, ref_mca, ref_utils = import_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
-    for case in CASES:
-        run_case(ref_net, *case)
-    module_goldens(ref_mca, ref_utils, ref_net)
+    only = sys.argv[1] if len(sys.argv) > 1 else None       # e.g. `make_golden.py classifier`: just that fixture
+    if only in (None, "net"):
+        for case in CASES:
+            run_case(ref_net, *case)
+    if only in (None, "modules"):
+        module_goldens(ref_mca, ref_utils, ref_net)
+    if only in (None, "classifier"):
+        classifier_golden(ref_net)
 
 
 if __name__ == "__main__":

@@ -315,7 +315,10 @@ def test_classifier_net_against_oracle():
     cfg = orc.Cfg(dropout_rate=0.0, **dict(orc.TINY, layer=2))
     answer_size = 24
     sd = orc.synth_state_dict(cfg, 50, answer_size, seed=21, classifier=True)
-    v, _, ans = orc.synth_batch(cfg, 5, 12, 7, 50, answer_size, seed=22, ragged="random")
+    # weights and inputs of the fixture the unmodified reference produced (oracle/make_golden.py classifier)
+    g = np.load(os.path.join(GOLD, "classifier_tiny.npz"))
+    assert [int(x) for x in g["meta"]] == [5, 12, answer_size, 21, 22]
+    v, ans = torch.from_numpy(g["img_feat"]).float(), torch.from_numpy(g["ans"]).float()
     p = {k: t.double().clone().requires_grad_(True) for k, t in sd.items()}
     ref = orc.classifier_forward(p, v.double(), cfg)
     orc.bce_sum(ref[0], ans.double()).backward()
@@ -332,3 +335,6 @@ def test_classifier_net_against_oracle():
     used = [(n, q) for n, q in net.named_parameters() if not n.startswith("attflat_lang.")]
     _check_param_grads(used, {n: p[n].grad for n, _ in used}, TOL_GRAD, "classifier")
     assert all(q.grad is None for n, q in net.named_parameters() if n.startswith("attflat_lang."))
+    # ... and directly against what the unmodified reference computed for these weights and inputs
+    assert _rel_max(probs, torch.from_numpy(g["probs"])) < TOL_OUT
+    assert abs(loss.item() - float(g["loss"])) < 2e-3 * abs(float(g["loss"]))

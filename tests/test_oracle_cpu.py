@@ -189,3 +189,25 @@ def test_oracle_classifier_matches_live_reference():
         # (the key biases have a mathematically zero gradient -- softmax is shift invariant -- so the
         # error is measured against the largest gradient entry of the model, not per tensor)
         assert np.abs(p[n].grad.numpy() - q.grad.numpy()).max() < 1e-10 * gmax, n
+
+
+def test_oracle_classifier_matches_reference_golden():
+    """ClassifierNet fixture produced by the unmodified reference (oracle/make_golden.py classifier): runs
+    wherever the repository is, also on the GPU box where /root/reference does not exist."""
+    g = np.load(os.path.join(GOLD, "classifier_tiny.npz"))
+    batch, regions, answer_size, wseed, bseed = [int(v) for v in g["meta"]]
+    cfg = orc.Cfg(dropout_rate=0.0, **dict(orc.TINY, layer=2))
+    sd = orc.synth_state_dict(cfg, 50, answer_size, seed=wseed, dtype=torch.float64, classifier=True)
+    p = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    probs, v_out, v_mask, v_w, a = orc.classifier_forward(p, torch.from_numpy(g["img_feat"]), cfg)
+    assert np.array_equal(v_mask.numpy(), g["v_mask"])
+    for got, key in ((probs, "probs"), (v_out, "v"), (v_w, "v_w"), (a, "a")):
+        assert _rel(got.detach().numpy(), g[key]) < 1e-10, key
+    loss = orc.bce_sum(probs, torch.from_numpy(g["ans"]))
+    assert abs(loss.item() - float(g["loss"])) < 1e-8 * abs(float(g["loss"]))
+    loss.backward()
+    for n, dig in zip([str(n) for n in g["grad_names"]], g["grad_digests"]):
+        mine = orc.grad_digest(p[n].grad)
+        assert np.abs(mine - dig).max() < 1e-8 * max(1.0, np.abs(dig).max()), n
+    unused = [str(n) for n in g["no_grad_names"]]
+    assert unused and all(n.startswith("attflat_lang.") and p[n].grad is None for n in unused)
