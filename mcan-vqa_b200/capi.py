@@ -159,9 +159,12 @@ def load():
 launch_count = 0   # successful C-ABI calls == kernels enqueued by this process
 
 
-def check(rc, what):
+def check(rc, what, launch=True):
+    """Raises McanError for a non-zero return code; counts the call as a kernel launch unless told otherwise
+    (configuration / query entry points enqueue nothing)."""
     global launch_count
-    launch_count += 1
+    if launch:
+        launch_count += 1
     if rc != 0:
         msg = load().mcan_last_error()
         raise McanError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))

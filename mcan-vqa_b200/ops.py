@@ -76,13 +76,13 @@ _state = {"sm_limit": 0, "dynamic": False}
 
 def set_sm_limit(sms):
     """Persistent kernels use at most `sms` SMs (0 = all); see include/mcan_b200.h."""
-    capi.check(capi.load().mcan_set_sm_limit(int(sms)), "mcan_set_sm_limit")
+    capi.check(capi.load().mcan_set_sm_limit(int(sms)), "mcan_set_sm_limit", launch=False)
     _state["sm_limit"] = int(sms)
 
 
 def set_gemm_schedule(dynamic):
     """Static (False, default) or dynamic (True) tile schedule of the GEMM; see include/mcan_b200.h."""
-    capi.check(capi.load().mcan_set_gemm_schedule(1 if dynamic else 0), "mcan_set_gemm_schedule")
+    capi.check(capi.load().mcan_set_gemm_schedule(1 if dynamic else 0), "mcan_set_gemm_schedule", launch=False)
     _state["dynamic"] = bool(dynamic)
 
 
@@ -106,15 +106,15 @@ class launch_config(object):
 
 def set_pdl(enabled):
     """Programmatic dependent launch between the library's kernels (default on)."""
-    capi.check(capi.load().mcan_set_pdl(1 if enabled else 0), "mcan_set_pdl")
+    capi.check(capi.load().mcan_set_pdl(1 if enabled else 0), "mcan_set_pdl", launch=False)
 
 
 def gemm_plan(m, n, k, *, accumulate=False, split_k=0, block_n=0, cta_group=0, sms=0):
     """The launch plan mcan_gemm uses for this shape (host logic only, no GPU needed when `sms` is given)."""
     out = (ctypes.c_int32 * 7)()
     capi.check(capi.load().mcan_gemm_plan(int(m), int(n), int(k), 1 if accumulate else 0, int(split_k), int(block_n),
-                                          int(cta_group), int(sms), ctypes.cast(out, ctypes.c_void_p)), "mcan_gemm_plan")
-    capi.launch_count -= 1      # not a kernel launch
+                                          int(cta_group), int(sms), ctypes.cast(out, ctypes.c_void_p)), "mcan_gemm_plan",
+               launch=False)
     keys = ("block_n", "cluster", "m_tiles", "n_tiles", "splits", "full_tiles", "units")
     return dict(zip(keys, (int(v) for v in out)))
 
