@@ -396,6 +396,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
     d |= (uint64_t)2 << 61;  // SWIZZLE_128B
     return d;
 }
+__host__ __device__ constexpr uint64_t make_smem_desc_sw128_const(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                                  uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr & 0x3FFFFU) >> 4) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFU) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFU) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
 // instruction descriptor, kind::f16: bf16 A/B, fp32 accumulate
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_major,
                                                        int b_mn_major) {
