@@ -1,0 +1,239 @@
+"""Parity against the UNMODIFIED reference running on the same B200 (baseline/_ref, copied by
+oracle/fetch_ref.py; fp64 / fp32 eager PyTorch on the GPU is the fast oracle) at the BASELINE.json
+sizes: MCAN-small and MCAN-large, batch 64, 100 regions, 14 tokens, 3129 answers.
+
+SURVEY 8d "Parity protocol": probabilities, every parameter gradient (relative L2 + cosine), top-1
+agreement over 4096 samples in both precision modes, the 100-step loss curve with the reference's
+optimiser, and the reference's own core/exec.py training loop through the overlay.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import mcan_oracle as orc  # noqa: E402
+import refload  # noqa: E402
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(refload.reference_root() is None, reason="no copy of the reference (oracle/fetch_ref.py)")]
+
+T, A, B, P, S = 20000, 3129, 64, 100, 14
+CFGS = {"small": orc.SMALL, "large": orc.LARGE}
+REPORT = os.path.join(ROOT, "gpurun_out", "parity_report.jsonl")
+
+
+def _report(**kw):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    with open(REPORT, "a") as f:
+        f.write(json.dumps(kw) + "\n")
+    print("PARITY", json.dumps(kw))
+
+
+def _reference_net(cfg, dtype, seed=0, cls="Net"):
+    """The reference's own module with its own default initialisation (torch.manual_seed(seed))."""
+    ref = refload.load()
+    torch.manual_seed(seed)
+    net = getattr(ref.net, cls)(cfg, None, T, A)
+    return net.to(dtype).cuda()
+
+
+def _overlay_net(state_dict, cfg, cls="Net"):
+    import core.model.net as ov
+    net = getattr(ov, cls)(cfg, None, T, A)
+    net.load_state_dict({k: v.float() for k, v in state_dict.items()}, strict=True)
+    return net.cuda()
+
+
+def _batch(cfg, ragged, seed=1234, batch=B):
+    v, q, a = orc.synth_batch(cfg, batch, P, S, T, A, seed=seed, ragged=ragged)
+    return v.cuda(), q.cuda(), a.cuda()
+
+
+@pytest.fixture(autouse=True)
+def _no_tf32():
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+
+
+# north star: answer probabilities within 1e-2 relative at bf16; weight gradients: DESIGN.md section 2
+TOL_PROBS_BF16 = 1e-2
+# Measured on B200 (gpurun_out/parity_report.jsonl, round 2): median relative L2 error of a parameter gradient
+# 0.4 %; worst weight matrix 1.8 %, worst bias / LayerNorm vector 1.0 % -- EXCEPT the first layer of the two
+# AttFlat MLPs (3-7 % / 5-10 %).  That is bf16 operand rounding, not a defect: the softmax over the sequence
+# makes the per-sample logit gradients sum to zero, so the wgrad of that layer is a covariance-like sum with
+# heavy cancellation; rounding ONLY the GEMM input x to bf16 in an otherwise fp64 computation already moves
+# it by 3 % (tests/test_hostlogic_cpu.py::test_attflat_fc_gradient_bf16_noise_floor).
+TOL_GRAD_REL_L2 = 2.5e-2        # weight matrices
+TOL_GRAD_COS = 0.9995
+TOL_GRAD_REL_L2_1D = 1.5e-2     # bias / LayerNorm vectors
+TOL_GRAD_COS_1D = 0.9998
+TOL_GRAD_REL_L2_ATTFLAT_FC = 1.2e-1
+TOL_GRAD_COS_ATTFLAT_FC = 0.992
+
+
+@pytest.mark.parametrize("ragged", ["none", "prefix", "random"])
+@pytest.mark.parametrize("model", ["small", "large"])
+def test_training_step_all_parameter_gradients_vs_reference_fp64(model, ragged):
+    """One training-mode step (dropout 0) at batch 64: probabilities, loss and ALL 275 parameter gradients of
+    the CUDA path vs the unmodified reference in fp64 on the same GPU."""
+    cfg = orc.Cfg(dropout_rate=0.0, **CFGS[model])
+    ref = _reference_net(cfg, torch.float64).train()
+    v, q, a = _batch(cfg, ragged)
+    probs_ref = ref(v.double(), q)[0]
+    loss_ref = torch.nn.BCELoss(reduction="sum")(probs_ref, a.double())
+    loss_ref.backward()
+    net = _overlay_net(ref.state_dict(), cfg).train()
+    probs = net(v, q)[0]
+    loss = torch.nn.BCELoss(reduction="sum")(probs, a)
+    loss.backward()
+    torch.cuda.synchronize()
+    rel = ((probs.double() - probs_ref).abs() / probs_ref.abs().clamp_min(1e-6)).max().item()
+    names = [n for n, _ in ref.named_parameters()]
+    assert names == [n for n, _ in net.named_parameters()] and len(names) == 275
+    errs = []
+    gref = dict((n, p.grad) for n, p in ref.named_parameters())
+    total_norm = torch.sqrt(sum(g.double().pow(2).sum() for g in gref.values())).item()
+    for n, p in net.named_parameters():
+        g, r = p.grad.double(), gref[n]
+        assert torch.isfinite(g).all(), n
+        rn = r.norm().item()
+        if rn < 1e-7 * total_norm:          # numerically-zero gradients (e.g. unused embedding rows only)
+            assert g.norm().item() < 1e-5 * total_norm, n
+            continue
+        l2 = ((g - r).norm() / r.norm()).item()
+        cos = (torch.dot(g.reshape(-1), r.reshape(-1)) / (g.norm() * r.norm())).item()
+        errs.append((l2, cos, n, r.dim()))
+    errs.sort(reverse=True)
+    flat_fc = [e for e in errs if ".mlp.fc.linear." in e[2] and e[2].startswith("attflat_")]
+    assert len(flat_fc) == 4
+    w2 = [e for e in errs if e[3] >= 2 and e not in flat_fc]
+    w1 = [e for e in errs if e[3] < 2 and e not in flat_fc]
+    _report(test="grads_vs_reference_fp64", model=model, ragged=ragged, batch=B, probs_max_rel=rel,
+            loss=loss.item(), loss_ref=loss_ref.item(), compared=len(errs),
+            worst_matrices=[(round(e[0], 5), round(e[1], 6), e[2]) for e in w2[:4]],
+            worst_vectors=[(round(e[0], 5), round(e[1], 6), e[2]) for e in w1[:4]],
+            attflat_fc=[(round(e[0], 5), round(e[1], 6), e[2]) for e in flat_fc],
+            median_rel_l2=errs[len(errs) // 2][0])
+    assert rel < TOL_PROBS_BF16, rel
+    assert abs(loss.item() - loss_ref.item()) < 2e-3 * abs(loss_ref.item())
+    # (the 18 linear_k biases have an exactly-zero gradient -- softmax is shift invariant -- and attflat_*.mlp.linear.bias too)
+    assert len(errs) >= 275 - 18 - 2
+    assert w2[0][0] < TOL_GRAD_REL_L2 and min(e[1] for e in w2) > TOL_GRAD_COS, w2[:3]
+    assert w1[0][0] < TOL_GRAD_REL_L2_1D and min(e[1] for e in w1) > TOL_GRAD_COS_1D, w1[:3]
+    assert flat_fc[0][0] < TOL_GRAD_REL_L2_ATTFLAT_FC and min(e[1] for e in flat_fc) > TOL_GRAD_COS_ATTFLAT_FC, flat_fc
+
+
+@pytest.mark.parametrize("model", ["small", "large"])
+def test_top1_agreement_4096_samples_both_precisions(model):
+    """Top-1 answers over 4096 ragged samples vs the reference in fp64: the split-precision ("fp32") mode
+    must agree on >= 99.9 % (north star); the bf16 mode is reported and must agree on every sample whose
+    reference margin exceeds twice the largest probability error (SURVEY 8c noise floors: the median
+    top-1/top-2 gap at random init is 1e-2, so raw bf16 agreement is ~98-99 %; measured here: 99.0-99.1 %).
+    Probabilities: every sample within 1e-2 relative L2; the single worst of the 12.8 M elements was measured
+    at 1.02e-2 (small) -- the batch-64 tests above hold the element-wise 1e-2 bound."""
+    import mcan_vqa_b200
+    cfg = orc.Cfg(dropout_rate=0.1, **CFGS[model])
+    ref = _reference_net(cfg, torch.float64).eval()
+    net = _overlay_net(ref.state_dict(), cfg).eval()
+    agree = {"bf16": 0, "fp32": 0}
+    margin_ok = margin_n = 0
+    max_rel = {"bf16": 0.0, "fp32": 0.0}
+    row_rel = {"bf16": 0.0, "fp32": 0.0}
+    n = 0
+    with torch.no_grad():
+        for i in range(4096 // B):
+            v, q, _ = _batch(cfg, "prefix" if i % 2 else "random", seed=5000 + i)
+            pr = ref(v.double(), q)[0]
+            top = pr.argmax(1)
+            two = pr.topk(2, dim=1).values
+            for mode in ("bf16", "fp32"):
+                mcan_vqa_b200.set_precision(mode)
+                try:
+                    p = net(v, q)[0].double()
+                finally:
+                    mcan_vqa_b200.set_precision("bf16")
+                agree[mode] += (p.argmax(1) == top).sum().item()
+                max_rel[mode] = max(max_rel[mode], ((p - pr).abs() / pr.abs().clamp_min(1e-6)).max().item())
+                row_rel[mode] = max(row_rel[mode], ((p - pr).norm(dim=1) / pr.norm(dim=1)).max().item())
+                if mode == "bf16":
+                    err = (p - pr).abs().max(dim=1).values
+                    clear = (two[:, 0] - two[:, 1]) > 2 * err
+                    margin_n += clear.sum().item()
+                    margin_ok += ((p.argmax(1) == top) & clear).sum().item()
+            n += B
+    _report(test="top1_agreement", model=model, samples=n, top1_bf16=agree["bf16"] / n, top1_fp32=agree["fp32"] / n,
+            margin_filtered=[margin_ok, margin_n], probs_max_rel=max_rel, probs_per_sample_rel_l2=row_rel)
+    assert n >= 4096
+    assert agree["fp32"] / n >= 0.999
+    assert max_rel["fp32"] < 1e-4 and row_rel["bf16"] < TOL_PROBS_BF16 and max_rel["bf16"] < 1.5e-2
+    assert margin_ok == margin_n and margin_n > 0.5 * n
+    assert agree["bf16"] / n >= 0.97
+
+
+@pytest.mark.parametrize("model", ["small", "large"])
+def test_loss_curve_100_steps_vs_reference_optimizer(model):
+    """100 optimiser steps, batch 64, data_size = 25 * 64 (all four warm-up learning-rate levels of
+    WarmupOptimizer.rate, reference optim.py:36-49), dropout 0: the reference Net2 + its get_optim (AdamW) in
+    fp32 on the GPU vs the overlay Net2 + the overlay get_optim (fused AdamW); per-step relative loss
+    difference <= 2e-2."""
+    import core.model.optim as ov_optim
+    rl = refload.load()
+    cfg = orc.Cfg(dropout_rate=0.0, **CFGS[model])
+    cfg.lr_base = 1e-4 if model == "small" else 5e-5
+    cfg.batch_size = B
+    cfg.opt_betas, cfg.opt_eps = (0.9, 0.98), 1e-9
+    data_size = 25 * B
+    ref = _reference_net(cfg, torch.float32, cls="Net2").train()
+    net = _overlay_net(ref.state_dict(), cfg, cls="Net2").train()
+    opt_ref = rl.optim.get_optim(cfg, ref, data_size)
+    opt = ov_optim.get_optim(cfg, net, data_size)
+    loss_fn = torch.nn.BCELoss(reduction="sum")
+    batches = [_batch(cfg, ("none", "prefix", "random")[i % 3], seed=9000 + i) for i in range(25)]
+    worst, curve = 0.0, []
+    for step in range(100):
+        v, q, a = batches[step % 25]
+        opt_ref.zero_grad()
+        lr = loss_fn(ref(v, q)[0], a)
+        lr.backward()
+        opt_ref.step()
+        opt.zero_grad()
+        lo = loss_fn(net(v, q)[0], a)
+        lo.backward()
+        opt.step()
+        assert abs(opt._rate - opt_ref._rate) < 1e-12
+        d = abs(lo.item() - lr.item()) / abs(lr.item())
+        curve.append((lr.item(), lo.item()))
+        worst = max(worst, d)
+    _report(test="loss_curve_100_steps", model=model, worst_rel=worst, first=curve[0], last=curve[-1],
+            rates=sorted(set(round(opt_ref.rate(s), 10) for s in range(1, 101))))
+    assert curve[-1][0] < 0.5 * curve[0][0]        # it actually trains
+    assert len(set(round(opt_ref.rate(s), 10) for s in range(1, 101))) == 4
+    assert worst < 2e-2, worst
+
+
+def test_reference_exec_py_trains_through_the_overlay(tmp_path):
+    """The reference's UNMODIFIED core/exec.py (Execution.train, exec.py:43-253) runs two epochs on a synthetic
+    dataset with this repository's overlay of core/model/* on the path; the checkpoint it writes loads into the
+    reference's own Net2 and reproduces the overlay's probabilities (tests/run_exec_overlay.py)."""
+    out = tmp_path / "result.json"
+    env = dict(os.environ)
+    env.pop("CUDA_VISIBLE_DEVICES", None)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_exec_overlay.py"), str(tmp_path), str(out)],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = json.load(open(out))
+    _report(test="exec_py_through_overlay", **res)
+    assert res["model_class"] == "core.model.net.Net2" and res["model_file"].startswith(ROOT + "/core/model")
+    assert res["exec_file"].startswith(refload.reference_root())
+    assert res["native_launches"] > 1000
+    assert res["epochs"] == 2 and res["loss_epoch2"] < res["loss_epoch1"]
+    assert res["lr_epoch1"] == pytest.approx(0.25 * res["lr_base"]) and res["lr_epoch2"] == pytest.approx(0.5 * res["lr_base"])
+    assert res["ckpt_probs_max_rel_vs_reference_net2"] < TOL_PROBS_BF16

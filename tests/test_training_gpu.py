@@ -159,12 +159,35 @@ def test_full_size_properties(model):
         v_w, q_w = out[3], out[6]
         assert (v_w.sum(1) - 1).abs().max() < 1e-4 and (q_w.sum(1) - 1).abs().max() < 1e-4
         assert (v_w[out[2].reshape(B, 100)] < 1e-6).all()
-        # padded query rows never reach the logits: perturbing masked image rows changes nothing
-        v2 = v.clone()
-        pad = out[2].reshape(B, 100)
-        # (masked rows are all-zero rows; keep them zero but perturb *valid-row-independent* padding tokens)
-        q2 = q.clone()
-        assert torch.equal(net(v2, q2)[0], probs)
+        # padded rows never reach the logits (SURVEY section 4 edge case): the hidden states of masked
+        # positions are perturbed by +100 at the input of the backbone; every masked position is excluded
+        # as a key in MHAtt and as a row in AttFlat, so the logits must not move by a single bit
+        H = cfg.hidden_size
+        g = torch.Generator(device="cuda").manual_seed(5)
+        qh = torch.randn(B, 14, H, device="cuda", generator=g)
+        vh = torch.randn(B, 100, H, device="cuda", generator=g)
+        q_mask, v_mask = out[5], out[2]
+        assert q_mask.any() and v_mask.any()          # the prefix-ragged batch has padding on both sides
+
+        def head(qh, vh):
+            qo, vo = net.backbone(qh, vh, q_mask, v_mask)
+            lang, _ = net.attflat_lang(qo, q_mask)
+            img, _ = net.attflat_img(vo, v_mask)
+            return net.proj(net.proj_norm(lang + img))
+
+        base = head(qh, vh)
+        qh2 = qh + 100.0 * q_mask.reshape(B, 14, 1)
+        vh2 = vh + 100.0 * v_mask.reshape(B, 100, 1)
+        assert not torch.equal(qh2, qh) and not torch.equal(vh2, vh)
+        assert torch.equal(head(qh2, vh2), base)
+    # ... and they receive an exactly-zero gradient
+    qh_g = qh.clone().requires_grad_(True)
+    vh_g = vh.clone().requires_grad_(True)
+    head(qh_g, vh_g).square().sum().backward()
+    assert torch.isfinite(qh_g.grad).all() and torch.isfinite(vh_g.grad).all()
+    assert qh_g.grad[q_mask.reshape(B, 14)].abs().max().item() == 0.0
+    assert vh_g.grad[v_mask.reshape(B, 100)].abs().max().item() == 0.0
+    assert qh_g.grad[~q_mask.reshape(B, 14)].abs().max().item() > 0.0
     # one training step at full size produces finite gradients for every parameter
     net.train()
     loss = torch.nn.BCELoss(reduction="sum")(net(v, q)[0], a)
