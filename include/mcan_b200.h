@@ -76,6 +76,9 @@ int mcan_set_pdl(int enabled);
  *   v  = keep(m*N+n) ? v/(1-p) : 0       (dropout_p > 0)
  *   v  = gate[m,n] > 0 ? v*gate_scale : 0  (gate != NULL; backward through ReLU+dropout)
  *   v += resid[m,n]                      (resid != NULL, fp32)
+ *   colsum[n] += sum_m v                 (colsum != NULL, fp32 atomics into a zeroed / running buffer: the
+ *                                         bias gradient of the layer whose input gradient this GEMM computes;
+ *                                         only with a bf16-only output and no residual / accumulate)
  *   out_f32[m,n] = v / out_bf16[m,n] = bf16(v) / out_bf16_lo[m,n] = bf16(v - bf16(v))
  * accumulate != 0: out_f32[m,n] += v with fp32 atomics (required for split_k > 1).  Only out_f32
  * may be set and no ReLU: the remaining stages are linear in the accumulator, so with K splits every
@@ -109,6 +112,7 @@ typedef struct mcan_gemm_args {
     void* out_bf16;
     void* out_bf16_lo;
     int64_t ldo_bf16;
+    float* colsum; /* optional fp32 [N]: += column sums of the epilogue output */
 
     int32_t accumulate;
     int32_t split_k; /* 0 = choose automatically (only when accumulate != 0) */

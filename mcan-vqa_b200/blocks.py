@@ -618,8 +618,8 @@ def mlp_bwd(rt, mlp, c, dout, norm=None, need_dx=True):
     gate_scale = 1.0 / (1.0 - c.p_mid) if c.p_mid > 0 else 1.0
     if gate is not None and not mlp.fc.use_relu:
         raise ops.capi.McanError("dropout without ReLU in FC is not supported by the fused gate")
-    ops.gemm(ds_bf, c.lp2.w, b_layout=1, gate=gate, gate_scale=gate_scale, out_bf16=dh)
-    rt.wgrad(ops.colsum, dh, g1.b)
+    # the FFN1 bias gradient (column sums of dh) comes out of the same epilogue, from the fp32 values
+    ops.gemm(ds_bf, c.lp2.w, b_layout=1, gate=gate, gate_scale=gate_scale, out_bf16=dh, colsum=g1.b)
     rt.wgrad(ops.gemm, dh, c.x_bf, a_layout=1, b_layout=1, out_f32=g1.w, accumulate=True)
     dx = None
     if need_dx:

@@ -46,6 +46,7 @@ class GemmArgs(ctypes.Structure):
         ("out_bf16", c_void_p),
         ("out_bf16_lo", c_void_p),
         ("ldo_bf16", c_int64),
+        ("colsum", c_void_p),
         ("accumulate", c_int32),
         ("split_k", c_int32),
         ("block_n", c_int32),

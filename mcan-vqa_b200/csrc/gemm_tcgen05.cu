@@ -30,6 +30,7 @@
 #include <mutex>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include <unordered_map>
 
 #include "../../include/mcan_b200.h"
@@ -82,6 +83,7 @@ struct alignas(64) GemmParams {
     bf16* out_lo;
     long long ldo_bf16;
     int accumulate;
+    float* colsum;   // += column sums of the epilogue output (fp32 [N]); see mcan_gemm_args::colsum
     int debug;   // profiling experiments only (MCAN_GEMM_DEBUG): bit0 skip all global stores, bit1 skip the TMA
                  // loads (MMAs run on stale shared memory), bit2 skip the MMAs (loads and commits only)
     int* tile_counter;   // dynamic tile scheduler: next unclaimed work unit (0 at launch, reset by the last claim)
@@ -112,11 +114,17 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
-// Fused epilogue for a [16 rows x 64 columns] accumulator fragment held in the tcgen05.ld
-// 16x256b layout: thread (g = lane/4, t = lane%4) owns, for k < 8 and h < 2, the two adjacent
-// columns col0 + 8k + 2t, +1 of row row0 + g + 8h (register r[4k + 2h + c]).  Four neighbouring
-// lanes cover one contiguous 32-byte sector of a row with their float2 accesses -- no shared
-// memory staging, which would compete with the UMMA operand reads.
+// Fused epilogue for a [16 rows x 64 columns] accumulator fragment.  tcgen05.ld 16x256b hands thread
+// (g = lane/4, t = lane%4), for k < 8 and h < 2, the two adjacent columns col0 + 8k + 2t, +1 of row
+// row0 + g + 8h (register r[4k + 2h + c]).  Storing straight from that layout means 4- / 8-byte
+// accesses whose warp-wide footprint is 8 rows x 16 / 32 bytes: every instruction costs 8 L1TEX
+// wavefronts for 128 / 256 bytes.  ncu on round 1's kernel: the epilogue's LSU wavefronts took 40 % of
+// the L1TEX data pipe -- the same pipe the tensor core reads its shared-memory operands through (32 %) --
+// and switching the stores off made the FFN1 GEMM 9 % faster.  So the fragment is first transposed
+// inside each quad of lanes (32 SHFL): afterwards thread (g, t) owns, for q < 2 and h < 2, the EIGHT
+// consecutive columns col0 + 32q + 8t .. +7 of row row0 + g + 8h (T8 layout), and every global access
+// of the epilogue is a 16-byte vector: bf16 stores / gate loads touch 4x fewer wavefronts per byte,
+// fp32 stores / residual loads / split-K reductions 2x fewer.
 //
 // The code is organised as one straight-line PASS per epilogue stage with the runtime flag tested
 // once per pass: the first version tested every flag for every element pair, unrolled to 4096
@@ -124,7 +132,8 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
 // (ncu: stall_no_inst on every line).
 constexpr int kChunkN = 64;
 
-// generic (slow) path for chunks that cross the N boundary or odd N: per element, rolled loops
+// generic (slow) path for chunks that cross the N boundary or odd N: per element, rolled loops, on the
+// UNtransposed fragment
 __device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const float* v, int lane,
                                                   long long row0, int col0, uint32_t drop_seed, bool addends) {
     const int g = lane >> 2, t = lane & 3;
@@ -141,6 +150,7 @@ __device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const flo
             x = dropout_u16((uint32_t)(row * (long long)p.n + col), drop_seed) >= p.drop_thr ? x * p.drop_scale : 0.f;
         if (p.gate != nullptr) x = __bfloat162float(p.gate[row * p.ldg + col]) > 0.f ? x * p.gate_scale : 0.f;
         if (p.resid != nullptr && addends) x += p.resid[row * p.ldr + col];
+        if (p.colsum != nullptr) atomicAdd(p.colsum + col, x);
         if (p.out_f32 != nullptr) {
             if (p.accumulate) atomicAdd(p.out_f32 + row * p.ldo_f32 + col, x);
             else p.out_f32[row * p.ldo_f32 + col] = x;
@@ -153,15 +163,216 @@ __device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const flo
     }
 }
 
+// 4 x 4 transpose inside every quad of lanes, on each of the 8 groups {q, h, c} of four registers
+// v[16q + 4kk + 2h + c] (kk < 4): afterwards register kk holds what lane (t & ~3) + kk held in register t,
+// i.e. v[16q + 4p + 2h + c] = D[row0 + g + 8h][col0 + 32q + 8t + 2p + c].
+__device__ __forceinline__ void quad_transpose(float (&v)[32], int t) {
+    const bool odd = (t & 1) != 0, hi = (t & 2) != 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int hc = 0; hc < 4; ++hc) {
+            const int b = 16 * q + hc;
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) {          // exchange with lane ^ 1
+                const float x = v[b + 4 * i], y = v[b + 4 * (i + 1)];
+                const float recv = __shfl_xor_sync(0xffffffffU, odd ? x : y, 1);
+                v[b + 4 * i] = odd ? recv : x;
+                v[b + 4 * (i + 1)] = odd ? y : recv;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {             // exchange with lane ^ 2
+                const float x = v[b + 4 * i], y = v[b + 4 * (i + 2)];
+                const float recv = __shfl_xor_sync(0xffffffffU, hi ? x : y, 2);
+                v[b + 4 * i] = hi ? recv : x;
+                v[b + 4 * (i + 2)] = hi ? y : recv;
+            }
+        }
+    }
+}
+// element e (< 8) of column group q, row half h in the T8 layout
+#define T8(v, q, h, e) v[16 * (q) + 4 * ((e) >> 1) + 2 * (h) + ((e) & 1)]
+
+// Residual / gate operands of one fragment (T8 layout), fetched from global memory one fragment AHEAD
+// of their use so that the ~1 us load latency overlaps the previous fragment's work (and, for the
+// first fragment of a tile, the wait for the accumulator).
+struct EpiPrefetch {
+    uint4 gt[4];      // [2h + q]: 8 bf16 of the gate operand
+};
+
+__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPrefetch& pf, int lane,
+                                                  long long row0, int col0) {
+    if (col0 + kChunkN > p.n || ((p.n & 1) && p.drop_thr != 0)) return;   // ragged chunks use the slow path
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const long long row = row0 + g + 8 * h;
+        if (row < p.m) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int col = col0 + 32 * q + 8 * t;
+                if (p.gate != nullptr)
+                    pf.gt[2 * h + q] = __ldg(reinterpret_cast<const uint4*>(p.gate + row * p.ldg + col));
+            }
+        }
+    }
+}
+
+// addends: this work unit adds the bias and the residual (false for K splits > 0 of a split-K GEMM
+// with a fused LINEAR epilogue: out = resid + keep*scale*(sum_s acc_s + bias), every split scales
+// its partial sum, only split 0 contributes the addends; all through red.global.add).
+template <bool PF>
+__device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_t (&r)[32], int lane,
+                                              long long row0, int col0, uint32_t drop_seed,
+                                              const EpiPrefetch& pf, bool addends, float (&cs)[16], bool cs_first,
+                                              bool cs_flush) {
+    const int g = lane >> 2, t = lane & 3;
+    // (odd N: only the dropout pair index needs N even; every other access is addressed through the
+    // 16-byte aligned leading dimensions)
+    if (col0 + kChunkN > p.n || ((p.n & 1) && p.drop_thr != 0)) {
+        // only this copy has its address taken; v[] below must stay in registers (an escaping v[]
+        // made the compiler mirror it to local memory after every pass: +15 us per epilogue stage)
+        float tmp[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tmp[i] = __uint_as_float(r[i]);
+        epilogue_frag_ragged(p, tmp, lane, row0, col0, drop_seed, addends);
+        return;
+    }
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    quad_transpose(v, t);
+    const int col = col0 + 8 * t;   // + 32q + e
+    const long long rows[2] = {row0 + g, row0 + g + 8};
+    const bool ok[2] = {rows[0] < p.m, rows[1] < p.m};
+
+    if (p.bias != nullptr && addends) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 32 * q));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 32 * q) + 1);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                T8(v, q, h, 0) += b0.x; T8(v, q, h, 1) += b0.y; T8(v, q, h, 2) += b0.z; T8(v, q, h, 3) += b0.w;
+                T8(v, q, h, 4) += b1.x; T8(v, q, h, 5) += b1.y; T8(v, q, h, 6) += b1.z; T8(v, q, h, 7) += b1.w;
+            }
+        }
+    }
+    if (p.relu) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (p.drop_thr != 0) {
+        const uint32_t thr = p.drop_thr;
+        const float sc = p.drop_scale;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const uint32_t base = (uint32_t)(rows[h] * (long long)p.n + col + 32 * q) >> 1;   // pair index (n even)
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    const uint32_t rnd = dropout_bits_pair(base + (e >> 1), drop_seed);
+                    T8(v, q, h, e) = ((rnd & 0xFFFFU) >= thr) ? T8(v, q, h, e) * sc : 0.f;
+                    T8(v, q, h, e + 1) = ((rnd >> 16) >= thr) ? T8(v, q, h, e + 1) * sc : 0.f;
+                }
+            }
+        }
+    }
+    if (PF && p.gate != nullptr) {
+        const float gs = p.gate_scale;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (ok[h]) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const uint4 gq = pf.gt[2 * h + q];
+                    const uint32_t gw[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        T8(v, q, h, e) = (bf16_lo_to_f(gw[e >> 1]) > 0.f) ? T8(v, q, h, e) * gs : 0.f;
+                        T8(v, q, h, e + 1) = (bf16_hi_to_f(gw[e >> 1]) > 0.f) ? T8(v, q, h, e + 1) * gs : 0.f;
+                    }
+                }
+            }
+        }
+    }
+    if (p.debug & 1) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += v[i];
+        if (acc == 123.456f && p.out_f32 != nullptr) p.out_f32[0] = acc;
+        return;
+    }
+    if (p.colsum != nullptr) {
+        // column sums of the epilogue output (the bias gradient of the layer that produced this GEMM's
+        // input gradient): the two 16-row fragments of a chunk are summed in registers first, then the 8
+        // row groups of the warp through shuffles, then one red.global.add per column and warp
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float x = (ok[0] ? T8(v, q, 0, e) : 0.f) + (ok[1] ? T8(v, q, 1, e) : 0.f);
+                cs[8 * q + e] = cs_first ? x : cs[8 * q + e] + x;
+            }
+        }
+        if (cs_flush) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float x = cs[i];
+                x += __shfl_xor_sync(0xffffffffU, x, 4);
+                x += __shfl_xor_sync(0xffffffffU, x, 8);
+                x += __shfl_xor_sync(0xffffffffU, x, 16);
+                cs[i] = x;
+            }
+            if (g == 0) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    float* o = p.colsum + col + 32 * q;
+                    red_add_v4(o, cs[8 * q], cs[8 * q + 1], cs[8 * q + 2], cs[8 * q + 3]);
+                    red_add_v4(o + 4, cs[8 * q + 4], cs[8 * q + 5], cs[8 * q + 6], cs[8 * q + 7]);
+                }
+            }
+        }
+    }
+    if (p.out_bf16 != nullptr) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if (ok[h]) {
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) pk[e >> 1] = pack_bf16x2(T8(v, q, h, e), T8(v, q, h, e + 1));
+                    *reinterpret_cast<uint4*>(p.out_bf16 + rows[h] * p.ldo_bf16 + col + 32 * q) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    if (p.out_lo != nullptr) {
+                        uint32_t lo[4];
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2)
+                            lo[e >> 1] = pack_bf16x2(T8(v, q, h, e) - bf16_lo_to_f(pk[e >> 1]),
+                                                     T8(v, q, h, e + 1) - bf16_hi_to_f(pk[e >> 1]));
+                        *reinterpret_cast<uint4*>(p.out_lo + rows[h] * p.ldo_bf16 + col + 32 * q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---- direct-layout epilogue (fp32 outputs, residual add, split-K reductions) -------------------------
+// Measured A/B inside the training step: for fp32 outputs the quad transpose does NOT pay -- these
+// epilogues are latency bound (the last tile of a GEMM is not overlapped) and the 32 extra shuffles per
+// fragment cost more than the halved wavefront count saves (+2 .. +5 % per GEMM); bf16-only outputs
+// gain (QKV forward 953 -> 1037 TFLOP/s).  So: T8 layout for bf16-only outputs, this one otherwise.
 // Residual / gate operands of one fragment, fetched from global memory one fragment AHEAD of
 // their use so that the ~1 us load latency overlaps the previous fragment's work (and, for the
 // first fragment of a tile, the wait for the accumulator).
-struct EpiPrefetch {
+struct EpiPrefetchDirect {
     float2 res[16];    // [8*h + k]
     uint32_t gt[16];
 };
 
-__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPrefetch& pf, int lane,
+__device__ __forceinline__ void epilogue_prefetch_direct(const GemmParams& p, EpiPrefetchDirect& pf, int lane,
                                                   long long row0, int col0) {
     if (col0 + kChunkN > p.n || ((p.n & 1) && p.drop_thr != 0)) return;   // ragged chunks use the slow path
     const int g = lane >> 2, t = lane & 3;
@@ -188,9 +399,9 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPrefet
 // with a fused LINEAR epilogue: out = resid + keep*scale*(sum_s acc_s + bias), every split scales
 // its partial sum, only split 0 contributes the addends; all through red.global.add).
 template <bool PF>
-__device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_t (&r)[32], int lane,
+__device__ __forceinline__ void epilogue_frag_direct(const GemmParams& p, const uint32_t (&r)[32], int lane,
                                               long long row0, int col0, uint32_t drop_seed,
-                                              const EpiPrefetch& pf, bool addends) {
+                                              const EpiPrefetchDirect& pf, bool addends) {
     const int g = lane >> 2, t = lane & 3;
     // (odd N: only the dropout pair index needs N even; every other access is addressed through the
     // 16-byte aligned leading dimensions)
@@ -310,17 +521,20 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_
 // Epilogue of one 128-row output tile for one of the 8 epilogue warps.  PF = the residual / gate
 // operands are prefetched one fragment ahead (separate instantiation so that plain epilogues do
 // not carry the prefetch registers).
-template <int CG, bool PF>
+template <int CG, bool PF, bool T8L>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int chunk_par,
                                               long long row0, int n0, int width, uint32_t taddr,
                                               uint64_t* full_bar, uint64_t* empty_bar,
                                               uint32_t acc_phase, uint32_t drop_seed, uint32_t lead_rank,
                                               bool addends) {
+    using Pref = typename std::conditional<T8L, EpiPrefetch, EpiPrefetchDirect>::type;
     const int nchunks = min(width / kChunkN, (p.n - n0 + kChunkN - 1) / kChunkN);
     const int last_c = ((nchunks - 1 - chunk_par) & ~1) + chunk_par;   // this warp's last chunk (< 0: none)
-    EpiPrefetch pf_next;
-    if (PF && last_c >= 0)   // operands of the first fragment, before waiting for the MMAs
-        epilogue_prefetch(p, pf_next, lane, row0, n0 + chunk_par * kChunkN);
+    Pref pf_next;
+    if (PF && last_c >= 0) {   // operands of the first fragment, before waiting for the MMAs
+        if constexpr (T8L) epilogue_prefetch(p, pf_next, lane, row0, n0 + chunk_par * kChunkN);
+        else epilogue_prefetch_direct(p, pf_next, lane, row0, n0 + chunk_par * kChunkN);
+    }
     mbar_wait(full_bar, acc_phase);
     tc_fence_after();
     if (last_c < 0) {
@@ -331,18 +545,21 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int
             else mbar_arrive(empty_bar);
         }
     }
+    float cs[16];   // column sums of the current chunk (T8 epilogue with colsum)
 #pragma unroll 1
     for (int c = chunk_par; c < nchunks; c += 2) {
 #pragma unroll 1
         for (int hb = 0; hb < 2; ++hb) {
             uint32_t r[32];
             tmem_ld_16x256b_x8(taddr + ((uint32_t)(hb * 16) << 16) + (uint32_t)(c * kChunkN), r);
-            EpiPrefetch pf;
+            Pref pf;
             if (PF) {
                 pf = pf_next;
                 const int nc = hb ? c + 2 : c, nhb = hb ^ 1;    // next fragment of this tile
-                if (nc < nchunks && row0 + nhb * 16 < p.m)
-                    epilogue_prefetch(p, pf_next, lane, row0 + nhb * 16, n0 + nc * kChunkN);
+                if (nc < nchunks && row0 + nhb * 16 < p.m) {
+                    if constexpr (T8L) epilogue_prefetch(p, pf_next, lane, row0 + nhb * 16, n0 + nc * kChunkN);
+                    else epilogue_prefetch_direct(p, pf_next, lane, row0 + nhb * 16, n0 + nc * kChunkN);
+                }
             }
             tmem_ld_wait();
             if (c == last_c && hb == 1) {
@@ -354,8 +571,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int
                     else mbar_arrive(empty_bar);
                 }
             }
-            if (row0 + hb * 16 < p.m)
-                epilogue_frag<PF>(p, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed, pf, addends);
+            if (row0 + hb * 16 < p.m) {
+                if constexpr (T8L)
+                    epilogue_frag<PF>(p, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed, pf, addends, cs, hb == 0,
+                                      hb == 1 || row0 + 16 >= p.m);
+                else epilogue_frag_direct<PF>(p, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed, pf, addends);
+            }
         }
     }
 }
@@ -390,7 +611,10 @@ __device__ __forceinline__ UnitInfo decode_unit(const GemmParams& p, int unit, i
     return u;
 }
 
-template <int BLOCK_N, int A_MN, int B_MN, int CG, int MC>
+// EPI = 1: bf16-only outputs, quad-transposed (T8) epilogue with 16-byte accesses; EPI = 0: fp32 outputs /
+// residual / split-K reductions in the direct layout (see the A/B note above epilogue_frag_direct).  A template
+// parameter, not a runtime branch: with both epilogues inlined into one kernel ptxas spilled 100+ bytes.
+template <int BLOCK_N, int A_MN, int B_MN, int CG, int MC, int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     using Cfg = GemmCfg<BLOCK_N, CG>;
@@ -667,12 +891,14 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             const int n0 = (tile % p.n_tiles) * BLOCK_N + ui.ncol;
             const long long row0 = m0 + quad * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-            if (p.resid != nullptr || p.gate != nullptr)
-                epilogue_tile<CG, true>(p, lane, chunk_par, row0, n0, ui.width, taddr, &tmem_full_bar[acc],
-                                        &tmem_empty_bar[acc], acc_phase, drop_seed, lead_rank, ui.split == 0);
-            else
-                epilogue_tile<CG, false>(p, lane, chunk_par, row0, n0, ui.width, taddr, &tmem_full_bar[acc],
-                                         &tmem_empty_bar[acc], acc_phase, drop_seed, lead_rank, ui.split == 0);
+#define MCAN_EPI_TILE(PF, T8L) epilogue_tile<CG, PF, T8L>(p, lane, chunk_par, row0, n0, ui.width, taddr, &tmem_full_bar[acc], \
+                                                          &tmem_empty_bar[acc], acc_phase, drop_seed, lead_rank, ui.split == 0)
+            if (EPI == 1) {
+                if (p.gate != nullptr) MCAN_EPI_TILE(true, true); else MCAN_EPI_TILE(false, true);
+            } else {
+                if (p.resid != nullptr || p.gate != nullptr) MCAN_EPI_TILE(true, false); else MCAN_EPI_TILE(false, false);
+            }
+#undef MCAN_EPI_TILE
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             unit = unit_after;
         }
@@ -812,7 +1038,7 @@ static int next_tile_counter(int** out) {
     return 0;
 }
 
-template <int BLOCK_N, int A_MN, int B_MN, int CG, int MC>
+template <int BLOCK_N, int A_MN, int B_MN, int CG, int MC, int EPI>
 static int launch_gemm(const GemmParams& p, int64_t units, int sms, cudaStream_t stream) {
     using Cfg = GemmCfg<BLOCK_N, CG>;
     constexpr int CL = CG * MC;
@@ -821,7 +1047,7 @@ static int launch_gemm(const GemmParams& p, int64_t units, int sms, cudaStream_t
     int dev = 0;
     MCAN_CHECK_CUDA(cudaGetDevice(&dev));
     MCAN_REQUIRE(dev >= 0 && dev < 64, "device index %d", dev);
-    auto kernel = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, CG, MC>;
+    auto kernel = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, CG, MC, EPI>;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.blockDim = dim3(kGemmThreads, 1, 1);
@@ -1012,6 +1238,9 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     if (a->resid) MCAN_REQUIRE(a->ldr % 4 == 0 && ((uintptr_t)a->resid & 15) == 0, "mcan_gemm: resid alignment");
     if (a->gate) MCAN_REQUIRE(a->ldg % 8 == 0 && ((uintptr_t)a->gate & 15) == 0, "mcan_gemm: gate alignment");
     if (a->bias) MCAN_REQUIRE(((uintptr_t)a->bias & 15) == 0, "mcan_gemm: bias alignment");
+    if (a->colsum)
+        MCAN_REQUIRE(((uintptr_t)a->colsum & 15) == 0 && !a->out_f32 && !a->resid && !a->accumulate,
+                     "mcan_gemm: colsum needs a 16-byte aligned buffer and a bf16-only output without residual");
 
     const int sms = device_num_sms();
     MCAN_REQUIRE(sms > 0, "mcan_gemm: no CUDA device");
@@ -1068,6 +1297,7 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     p.out_lo = reinterpret_cast<bf16*>(a->out_bf16_lo);
     p.ldo_bf16 = a->ldo_bf16;
     p.accumulate = a->accumulate;
+    p.colsum = a->colsum;
     p.tile_counter = nullptr;
     if (g_dynamic_schedule.load(std::memory_order_relaxed)) {
         if (int rc = next_tile_counter(&p.tile_counter)) return rc;
@@ -1078,8 +1308,10 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a->stream);
     const int am = a->a_layout ? 1 : 0, bm = a->b_layout ? 1 : 0;
 
+    const int epi = (a->out_f32 == nullptr && a->resid == nullptr) ? 1 : 0;
 #define MCAN_GEMM_CASE(BN, AM, BM, CG, MC) \
-    if (block_n == BN && am == AM && bm == BM && cg == CG && mc == MC) return launch_gemm<BN, AM, BM, CG, MC>(p, units, sms, st);
+    if (block_n == BN && am == AM && bm == BM && cg == CG && mc == MC) \
+        return epi ? launch_gemm<BN, AM, BM, CG, MC, 1>(p, units, sms, st) : launch_gemm<BN, AM, BM, CG, MC, 0>(p, units, sms, st);
 #define MCAN_GEMM_CASES(BN, CG, MC) \
     MCAN_GEMM_CASE(BN, 0, 0, CG, MC) MCAN_GEMM_CASE(BN, 0, 1, CG, MC) MCAN_GEMM_CASE(BN, 1, 0, CG, MC) MCAN_GEMM_CASE(BN, 1, 1, CG, MC)
     MCAN_GEMM_CASES(64, 1, 1)

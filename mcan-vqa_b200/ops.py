@@ -121,7 +121,7 @@ def gemm_plan(m, n, k, *, accumulate=False, split_k=0, block_n=0, cta_group=0, s
 
 def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, seed=0, gate=None,
          gate_scale=1.0, resid=None, out_f32=None, out_bf16=None, out_lo=None, accumulate=False,
-         split_k=0, block_n=0, cta_group=0):
+         split_k=0, block_n=0, cta_group=0, colsum=None):
     """D[M,N] = epilogue(sum_s A_s B_s^T) on the tcgen05 GEMM (see include/mcan_b200.h).
 
     a / b: bf16 tensors or equal-length lists of them (segments).  a_layout 0: [M,K], 1: [K,M];
@@ -176,6 +176,11 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, 
         if out_bf16 is None or out_lo.stride(0) != out_bf16.stride(0):
             raise capi.McanError("gemm: out_lo needs out_bf16 with the same leading dimension")
         args.out_bf16_lo = out_lo.data_ptr()
+    if colsum is not None:
+        _req(colsum, _F32, "gemm colsum")
+        if colsum.numel() != n or not colsum.is_contiguous():
+            raise capi.McanError("gemm: colsum must be a contiguous fp32 vector of length N")
+        args.colsum = colsum.data_ptr()
     args.accumulate = 1 if accumulate else 0
     args.split_k = int(split_k)
     args.block_n = int(block_n)

@@ -309,3 +309,19 @@ def test_gemm_split_k_with_linear_fused_epilogue(m, n, k, split_k):
     ops.gemm(a, wt, b_layout=1, gate=gate, gate_scale=1.25, resid=resid, out_f32=out, accumulate=True, split_k=split_k)
     torch.cuda.synchronize()
     _close(out, ref, 2e-5, "split-K gated dgrad")
+
+
+@pytest.mark.parametrize("m,n,k,cta_group", [(6400, 1024, 512, 2), (896, 512, 256, 1), (100, 192, 128, 1), (300, 136, 64, 1)])
+def test_gemm_epilogue_colsum_of_gated_output(m, n, k, cta_group):
+    """colsum[n] += sum_m epilogue(acc)[m, n] (the bias gradient of the previous layer, fused into the dgrad
+    GEMM that produces that layer's input gradient): fp32 values before the bf16 rounding, ragged M and N."""
+    ops = _ops()
+    a, w = _rand((m, k), 31), _rand((k, n), 32, 0.1)
+    gate = _rand((m, n), 33)
+    out = torch.empty(m, (n + 7) // 8 * 8, device="cuda", dtype=torch.bfloat16)[:, :n]
+    cs = torch.full((n,), 0.5, device="cuda")
+    ops.gemm(a, w, b_layout=1, gate=gate, gate_scale=1.25, out_bf16=out, colsum=cs, cta_group=cta_group)
+    torch.cuda.synchronize()
+    ref = torch.where(gate.float() > 0, (a.float() @ w.float()) * 1.25, torch.zeros((), device="cuda"))
+    _close(out, ref, 6e-3, "gate")
+    _close(cs, ref.sum(0) + 0.5, 2e-5 * (m ** 0.5), "colsum")
