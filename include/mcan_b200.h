@@ -248,10 +248,11 @@ int mcan_gemm_plan(int64_t m, int64_t n, int64_t k, int32_t accumulate, int32_t 
  * first_chunk is set; 0 = none) -- two, because a weight can sit in two stacked operand buffers;
  * n elements; first_chunk (bits 0..60) = running index of the segment's first 4096-element chunk.
  * lr_dev / step_dev: device scalars (fp32) holding the learning rate and t >= 1, so a captured CUDA
- * graph replays with new values. */
+ * graph replays with new values.  flags bit 0: one chunk per CTA (short-lived CTAs) instead of a persistent
+ * grid, for an update that shares the GPU with latency-bound kernels of a higher-priority stream. */
 int mcan_adamw_multi(const void* seg_table_dev, int32_t num_segments, int64_t total_chunks,
                      const float* lr_dev, const float* step_dev, float beta1, float beta2, float eps,
-                     float weight_decay, void* stream);
+                     float weight_decay, int32_t flags, void* stream);
 
 /* experiment helper (tools/contention_bench.py): keep `ctas` SMs busy for `cycles` clocks */
 int mcan_debug_hog(int32_t ctas, int64_t cycles, int32_t smem_bytes, void* stream);

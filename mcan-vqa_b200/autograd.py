@@ -271,6 +271,9 @@ class _MCAEDRunner(_Runner):
         dxo = _as_f32_2d(gx, H) if gx is not None else torch.zeros((self.B * self.Sx, H), device=dev)
         dyo = _as_f32_2d(gy, H) if gy is not None else torch.zeros((self.B * self.Sy, H), device=dev)
         hook = dp.layer_hook()
+        if hook is None:
+            from . import optim as _optim
+            hook = _optim.early_hook()
         dx, dy, grads = blocks.mca_ed_bwd(self.rt, m, self.c, dxo, dyo, after_layer=hook)
         return [dx.view(self.B, self.Sx, H), dy.view(self.B, self.Sy, H), None, None], grads
 

@@ -731,9 +731,10 @@ def _side_stream(dev):
 
 
 def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
-    """dx_out/dy_out: fp32 grads of the two outputs.  after_layer(bufs) is called with the flat
-    gradient buffers of a layer as soon as its kernels are enqueued (hook for the overlapped
-    gradient all-reduce in dp.py)."""
+    """dx_out/dy_out: fp32 grads of the two outputs.  after_layer(bufs, grads, kind) is called with the flat
+    gradient buffers and the {parameter: gradient} map of a layer ("dec" | "kv" | "enc") as soon as its
+    kernels are enqueued (hook for the overlapped gradient all-reduce in dp.py, or for the overlapped
+    optimiser step on a single GPU, optim.EarlyStep)."""
     H = m.hidden_size
     L = len(m.dec_list)
     B, Sx, Sy = ctx.B, ctx.Sx, ctx.Sy
@@ -755,7 +756,7 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
             pending.append((rt.deferred, rt.drain()))
             rt.deferred = None
         elif after_layer is not None and not DP_DELAY_DECODER:
-            after_layer(rt.drain())
+            after_layer(rt.drain(), g, "dec")
     dx = dx_out
     if L > 0:
         gkv = GradBuf(rt, ctx.lpkv)
@@ -772,7 +773,7 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
             pending.append((rt.deferred, rt.drain()))
             rt.deferred = None
         elif after_layer is not None:
-            after_layer(rt.drain())
+            after_layer(rt.drain(), gk, "kv")
     side = None
     if overlap:
         # fork: everything the deferred work reads has been produced on the current stream
@@ -792,7 +793,7 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
             dx, g = sa_bwd(rt, m.enc_list[i], ctx.enc[i], dx)
             grads.update(g)
             if after_layer is not None:
-                after_layer(rt.drain())
+                after_layer(rt.drain(), g, "enc")
     if side is not None:
         torch.cuda.current_stream().wait_stream(side)    # join; `pending` kept every operand alive until here
         del pending

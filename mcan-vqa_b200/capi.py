@@ -123,7 +123,7 @@ SYMBOLS = {
     "mcan_cast_multi": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_void_p]),
     "mcan_gemm_plan": (ctypes.c_int, [c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "mcan_adamw_multi": (ctypes.c_int, [c_void_p, c_int32, c_int64, c_void_p, c_void_p, c_float, c_float, c_float,
-                                        c_float, c_void_p]),
+                                        c_float, c_int32, c_void_p]),
     "mcan_debug_hog": (ctypes.c_int, [c_int32, c_int64, c_int32, c_void_p]),
     "mcan_gate_bf16": (ctypes.c_int, [c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "mcan_colsum_bf16": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p]),

@@ -135,14 +135,18 @@ using namespace mcan;
 
 extern "C" int mcan_adamw_multi(const void* seg_table_dev, int32_t num_segments, int64_t total_chunks,
                                 const float* lr_dev, const float* step_dev, float beta1, float beta2,
-                                float eps, float weight_decay, void* stream) {
+                                float eps, float weight_decay, int32_t flags, void* stream) {
     MCAN_REQUIRE(seg_table_dev && lr_dev && step_dev && num_segments > 0 && total_chunks > 0,
                  "mcan_adamw_multi: bad args");
     MCAN_REQUIRE(beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f,
                  "mcan_adamw_multi: betas (%f, %f) eps %g", beta1, beta2, eps);
     const int sms = device_num_sms();
     MCAN_REQUIRE(sms > 0, "mcan_adamw_multi: no CUDA device");
-    long long blocks = total_chunks < 16LL * sms ? total_chunks : 16LL * sms;
+    // flags bit 0: one 4096-element chunk per CTA (short-lived CTAs) instead of a persistent grid -- for an update
+    // that runs on a low-priority stream NEXT TO latency-bound kernels (the encoder backward): those get an SM
+    // as soon as any of these CTAs retires, instead of waiting behind a grid that owns every SM to its end
+    long long blocks = (flags & 1) ? total_chunks : (total_chunks < 16LL * sms ? total_chunks : 16LL * sms);
+    MCAN_REQUIRE(blocks < (1LL << 31), "mcan_adamw_multi: too many chunks");
     MCAN_CHECK_CUDA(launch_kernel(adamw_multi_kernel, dim3((unsigned)blocks), dim3(256), 0,
                                   reinterpret_cast<cudaStream_t>(stream),
                                   reinterpret_cast<const AdamSeg*>(seg_table_dev), (int)num_segments,

@@ -98,7 +98,7 @@ class GradSync(object):
         self.ready.append(p.grad)
         self._ensure_final_callback()
 
-    def on_bufs(self, bufs):
+    def on_bufs(self, bufs, grads=None, kind=None):
         """Called inside MCA_ED.backward with the flat fp32 gradient buffers of one layer."""
         self.acc += self.ready + list(bufs)
         self.ready = []

@@ -17,7 +17,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from . import blocks, dp, ops  # noqa: E402
-from .optim import FusedAdamW  # noqa: E402
+from . import optim as _optim  # noqa: E402
+from .optim import EarlyStep, FusedAdamW  # noqa: E402
 
 
 def warmup_rate(step, lr_base, data_size, batch_size):
@@ -59,6 +60,14 @@ class Trainer(object):
         self.bucketed = self.sync is not None and self.sync.world > 1 and isinstance(self.opt, FusedAdamW)
         if self.bucketed:
             self.sync.defer_wait = True
+        # single GPU: the optimiser update of finished layers overlaps the encoder half of the backward pass
+        self.early = None
+        if (isinstance(self.opt, FusedAdamW) and not self.bucketed and (self.sync is None or self.sync.world == 1)
+                and os.environ.get("MCAN_EARLY_STEP", "1") != "0"):
+            self.early = EarlyStep(self.opt)
+            _optim.set_early(self.early)
+        # kernels of the step run on a HIGH-priority stream so that they win SMs from the overlapped update
+        self.main_stream = torch.cuda.Stream(device=device, priority=-1)
         self.graph = None
         self.static = None
         self.loss = None
@@ -83,6 +92,8 @@ class Trainer(object):
             self._advance_seed()
         probs = self.net(img, ques)[0]
         loss = self.loss_fn(probs, ans)
+        if self.early is not None:
+            self.early.begin()
         loss.backward()
         if self.bucketed:
             self.opt.step_buckets(self.sync.take_buckets())
@@ -102,7 +113,7 @@ class Trainer(object):
     def capture(self, img, ques, ans, warmup=3):
         """Warm up on a side stream, then capture one full training step."""
         self.static = (img.clone(), ques.clone(), ans.clone())
-        s = torch.cuda.Stream()
+        s = self.main_stream
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
@@ -114,7 +125,7 @@ class Trainer(object):
         self._set_lr()
         self.opt.zero_grad(set_to_none=True)
         # thread_local: the NCCL watchdog thread polls CUDA events while we capture (data parallel)
-        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+        with torch.cuda.graph(self.graph, stream=self.main_stream, capture_error_mode="thread_local"):
             self.loss = self._raw_step(*self.static)
         self._step -= 1          # capturing records the step, it does not execute it
         torch.cuda.synchronize()
@@ -138,3 +149,5 @@ class Trainer(object):
             ops.set_seed_tensor(None)
         if self.sync is not None:
             dp.detach()
+        if self.early is not None:
+            _optim.set_early(None)
