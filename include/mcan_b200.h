@@ -123,6 +123,40 @@ typedef struct mcan_gemm_args {
 
 int mcan_gemm(const mcan_gemm_args* args);
 
+/* -- G2: GEMM with residual add + MCAN LayerNorm fused into the epilogue ----------------------------
+ * Replaces, for the sub-layer outputs of SA / SGA (mca.py:119-125, 152-162), the chain
+ *   GEMM[+bias, dropout, +resid] -> s -> LayerNorm(s) (net_utils.py:56-60):
+ *   s[m,:] = resid[m,:] + dropout(A[m,:] W^T + bias)          A: bf16 [M,K] (lda), W: bf16 [N,K] (ldb)
+ *   y[m,:] = ln_a2 * (s - mean) / (std_unbiased + eps) + ln_b2
+ * One thread-block cluster owns 256 complete rows (N = 512: one CTA pair; N = 1024: two pairs that share the A
+ * tile by TMA multicast and exchange the row statistics through distributed shared memory), so N must be 512
+ * or 1024.  Outputs (all row-major with leading dimension N): s_f32 (optional; the LayerNorm input, saved for the
+ * backward kernel), y_f32 / y_bf16 (at least one), mean / sigma [M] (optional).  Dropout uses the same
+ * (seed, m*N+n) hash as mcan_gemm, so the backward kernels regenerate the mask. */
+typedef struct mcan_gemm_ln_args {
+    const void* a;
+    const void* b;
+    int64_t m, n, k;
+    int64_t lda, ldb;
+    const float* bias;
+    float dropout_p;
+    uint32_t dropout_seed;
+    const uint32_t* dropout_seed_dev;
+    const float* resid;
+    int64_t ldr;
+    const float* ln_a2;
+    const float* ln_b2;
+    float eps;
+    float* s_f32;
+    float* y_f32;
+    void* y_bf16;
+    float* mean;
+    float* sigma;
+    void* stream;
+} mcan_gemm_ln_args;
+
+int mcan_gemm_ln(const mcan_gemm_ln_args* args);
+
 /* -- A1: fused masked-softmax attention, one CTA per (batch, head) -------------------
  * Replaces MHAtt.att (mca.py:65-78) plus the head split/merge transposes (mca.py:33-59):
  *   P = softmax(masked_fill(Q K^T * scale, key_mask, -1e9)); P = dropout(P); O = P V

@@ -376,6 +376,36 @@ class refresh_scope(object):
 
 
 # ------------------------------------------------------------------------------------------
+# GEMM with residual add + LayerNorm fused into the epilogue (mcan_gemm_ln, csrc/gemm_ln.cu)
+# ------------------------------------------------------------------------------------------
+# "1": every eligible sub-layer output; "0" (default): GEMM -> s -> LayerNorm kernel.  One cluster owns whole rows,
+# so the hidden size must be 512 or 1024; split-precision inference and split-K GEMMs keep the unfused chain.
+# Opt-in because at batch 64 it is SLOWER (one wave of 25 clusters: the two-pass epilogue is fully exposed --
+# measurements in csrc/gemm_ln.cu and DESIGN.md): 8.46 / 8.85 ms per step with it vs 8.28 ms without.
+FUSE_LN = os.environ.get("MCAN_FUSE_LN", "0") != "0"
+FUSE_LN_MIN_ROWS = int(os.environ.get("MCAN_FUSE_LN_MIN_ROWS", "1"))
+
+
+def _can_fuse_ln(rt, rows, n, lp):
+    return (FUSE_LN and not rt.split and n in (512, 1024) and rows >= FUSE_LN_MIN_ROWS and lp.k % 8 == 0
+            and lp.w.stride(0) == lp.k)
+
+
+def gemm_ln_fwd(a_bf, lp, norm, resid, p, seed):
+    """LN(resid + dropout(a W^T + b)) -> (Act(y_f32, y_bf), s_f32, mean, sigma) in one launch."""
+    dev = a_bf.device
+    M, N = a_bf.shape[0], lp.n
+    s = _empty(M, N, _F32, dev)
+    y32 = _empty(M, N, _F32, dev)
+    ybf = _empty(M, N, _BF16, dev)
+    mean = torch.empty(M, dtype=_F32, device=dev)
+    sigma = torch.empty(M, dtype=_F32, device=dev)
+    ops.gemm_ln(a_bf, lp.w, bias=lp.b, resid=resid, ln_a2=norm.a_2.detach(), ln_b2=norm.b_2.detach(), eps=norm.eps,
+                dropout_p=p, seed=seed, s_f32=s, y_f32=y32, y_bf16=ybf, mean=mean, sigma=sigma)
+    return Act(y32, ybf), s, mean, sigma
+
+
+# ------------------------------------------------------------------------------------------
 # LayerNorm
 # ------------------------------------------------------------------------------------------
 def ln_fwd(norm, s_f32, want_bf=True, split=False):
@@ -468,12 +498,16 @@ def att_fwd(rt, mh, x, B, Sq, kv_src=None, Sk=None, key_mask=None, kv=None, norm
     c.att = att
     lpm = mh.lp_merge().get(_force(rt.p > 0 or torch.is_grad_enabled()), rt.split)
     c.lpm = lpm
-    s = _empty(M, H, _F32, dev)
     atta = Act(None, att, att_lo)
     if norm is None:
+        s = _empty(M, H, _F32, dev)
         _mm(rt, atta, lpm, 0, 1, out_f32=s)
         return s, c
     c.seed_out = rt.seed()
+    if _can_fuse_ln(rt, M, H, lpm):
+        out, c.s, c.mean, c.sigma = gemm_ln_fwd(att, lpm, norm, x.f32, rt.p, c.seed_out)
+        return out, c
+    s = _empty(M, H, _F32, dev)
     _mm(rt, atta, lpm, 0, 1, dropout_p=rt.p, seed=c.seed_out, resid=x.f32, out_f32=s)
     out, c.mean, c.sigma = ln_fwd(norm, s, split=rt.split)
     c.s = s
@@ -587,8 +621,11 @@ def mlp_fwd(rt, mlp, x, norm=None):
     # split-K (see _resid_gemm) only when training: fp32 atomics make the result depend on the
     # arrival order (1e-7 relative), and inference must stay bit-reproducible run to run
     use_sk = SPLITK_MIN_K > 0 and M <= SPLITK_MAX_ROWS and lp1.n >= SPLITK_MIN_K and torch.is_grad_enabled()
-    s = torch.zeros((M, lp2.n), dtype=_F32, device=dev) if use_sk else _empty(M, lp2.n, _F32, dev)
     c.seed_out = rt.seed()
+    if not use_sk and _can_fuse_ln(rt, M, lp2.n, lp2):
+        out, c.s, c.mean, c.sigma = gemm_ln_fwd(hmid, lp2, norm, x.f32, rt.p, c.seed_out)
+        return out, c
+    s = torch.zeros((M, lp2.n), dtype=_F32, device=dev) if use_sk else _empty(M, lp2.n, _F32, dev)
     _mm(rt, ha, lp2, 0, 1, dropout_p=rt.p, seed=c.seed_out, resid=x.f32, out_f32=s, accumulate=use_sk)
     out, c.mean, c.sigma = ln_fwd(norm, s, split=rt.split)
     c.s = s

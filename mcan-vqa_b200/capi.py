@@ -55,6 +55,33 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+class GemmLnArgs(ctypes.Structure):
+    _fields_ = [
+        ("a", c_void_p),
+        ("b", c_void_p),
+        ("m", c_int64),
+        ("n", c_int64),
+        ("k", c_int64),
+        ("lda", c_int64),
+        ("ldb", c_int64),
+        ("bias", c_void_p),
+        ("dropout_p", c_float),
+        ("dropout_seed", c_uint32),
+        ("dropout_seed_dev", c_void_p),
+        ("resid", c_void_p),
+        ("ldr", c_int64),
+        ("ln_a2", c_void_p),
+        ("ln_b2", c_void_p),
+        ("eps", c_float),
+        ("s_f32", c_void_p),
+        ("y_f32", c_void_p),
+        ("y_bf16", c_void_p),
+        ("mean", c_void_p),
+        ("sigma", c_void_p),
+        ("stream", c_void_p),
+    ]
+
+
 class AttnArgs(ctypes.Structure):
     _fields_ = [
         ("q", c_void_p),
@@ -106,6 +133,7 @@ SYMBOLS = {
     "mcan_set_gemm_schedule": (ctypes.c_int, [ctypes.c_int]),
     "mcan_set_pdl": (ctypes.c_int, [ctypes.c_int]),
     "mcan_gemm": (ctypes.c_int, [ctypes.POINTER(GemmArgs)]),
+    "mcan_gemm_ln": (ctypes.c_int, [ctypes.POINTER(GemmLnArgs)]),
     "mcan_attn_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs)]),
     "mcan_attn_bwd": (ctypes.c_int, [ctypes.POINTER(AttnBwdArgs)]),
     "mcan_layernorm_fwd": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float,

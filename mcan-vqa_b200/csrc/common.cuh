@@ -430,4 +430,39 @@ __device__ __forceinline__ float bf16_hi_to_f(uint32_t packed) {
     return __uint_as_float(packed & 0xFFFF0000U);
 }
 
+// ---- accumulator fragment layouts (tcgen05.ld 16x256b.x8: [16 rows x 64 columns] per warp) ----
+// direct: thread (g = lane/4, t = lane%4) holds r[4k + 2h + c] = D[g + 8h][8k + 2t + c]  (k < 8, h < 2, c < 2)
+// T8    : after quad_transpose, v[16q + 4p + 2h + c] = D[g + 8h][32q + 8t + 2p + c]: eight consecutive columns
+//         per (q, h), so that every global access of an epilogue is a 16-byte vector
+// 4 x 4 transpose inside every quad of lanes, on each of the 8 groups {q, h, c} of four registers
+// v[16q + 4kk + 2h + c] (kk < 4): afterwards register kk holds what lane (t & ~3) + kk held in register t,
+// i.e. v[16q + 4p + 2h + c] = D[row0 + g + 8h][col0 + 32q + 8t + 2p + c].
+__device__ __forceinline__ void quad_transpose(float (&v)[32], int t) {
+    const bool odd = (t & 1) != 0, hi = (t & 2) != 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+#pragma unroll
+        for (int hc = 0; hc < 4; ++hc) {
+            const int b = 16 * q + hc;
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) {          // exchange with lane ^ 1
+                const float x = v[b + 4 * i], y = v[b + 4 * (i + 1)];
+                const float recv = __shfl_xor_sync(0xffffffffU, odd ? x : y, 1);
+                v[b + 4 * i] = odd ? recv : x;
+                v[b + 4 * (i + 1)] = odd ? y : recv;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {             // exchange with lane ^ 2
+                const float x = v[b + 4 * i], y = v[b + 4 * (i + 2)];
+                const float recv = __shfl_xor_sync(0xffffffffU, hi ? x : y, 2);
+                v[b + 4 * i] = hi ? recv : x;
+                v[b + 4 * (i + 2)] = hi ? y : recv;
+            }
+        }
+    }
+}
+// element e (< 8) of column group q, row half h in the T8 layout
+#define T8(v, q, h, e) v[16 * (q) + 4 * ((e) >> 1) + 2 * (h) + ((e) & 1)]
+
+
 }  // namespace mcan

@@ -163,36 +163,6 @@ __device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const flo
     }
 }
 
-// 4 x 4 transpose inside every quad of lanes, on each of the 8 groups {q, h, c} of four registers
-// v[16q + 4kk + 2h + c] (kk < 4): afterwards register kk holds what lane (t & ~3) + kk held in register t,
-// i.e. v[16q + 4p + 2h + c] = D[row0 + g + 8h][col0 + 32q + 8t + 2p + c].
-__device__ __forceinline__ void quad_transpose(float (&v)[32], int t) {
-    const bool odd = (t & 1) != 0, hi = (t & 2) != 0;
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-#pragma unroll
-        for (int hc = 0; hc < 4; ++hc) {
-            const int b = 16 * q + hc;
-#pragma unroll
-            for (int i = 0; i < 4; i += 2) {          // exchange with lane ^ 1
-                const float x = v[b + 4 * i], y = v[b + 4 * (i + 1)];
-                const float recv = __shfl_xor_sync(0xffffffffU, odd ? x : y, 1);
-                v[b + 4 * i] = odd ? recv : x;
-                v[b + 4 * (i + 1)] = odd ? y : recv;
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {             // exchange with lane ^ 2
-                const float x = v[b + 4 * i], y = v[b + 4 * (i + 2)];
-                const float recv = __shfl_xor_sync(0xffffffffU, hi ? x : y, 2);
-                v[b + 4 * i] = hi ? recv : x;
-                v[b + 4 * (i + 2)] = hi ? y : recv;
-            }
-        }
-    }
-}
-// element e (< 8) of column group q, row half h in the T8 layout
-#define T8(v, q, h, e) v[16 * (q) + 4 * ((e) >> 1) + 2 * (h) + ((e) & 1)]
-
 // Residual / gate operands of one fragment (T8 layout), fetched from global memory one fragment AHEAD
 // of their use so that the ~1 us load latency overlaps the previous fragment's work (and, for the
 // first fragment of a tile, the wait for the accumulator).
@@ -957,8 +927,8 @@ struct TmapKeyHash {
 
 // bf16 2-D tensor map over a row-major [outer, inner] array with leading dimension ld
 // (elements); box = {64 inner elements (=128 B, the swizzle span), box_rows}.
-static int make_tmap(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-                     uint32_t box_rows) {
+int make_tmap_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                   uint32_t box_rows) {
     static std::mutex mu;
     static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
     TmapKey key{ptr, inner, outer, ld, box_rows};
@@ -1266,17 +1236,17 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
         MCAN_REQUIRE(a->a[s] && a->b[s], "mcan_gemm: null operand in segment %d", s);
         int rc;
         if (a->a_layout == 0)
-            rc = make_tmap(&p.tma_a[s], a->a[s], (uint64_t)a->k, (uint64_t)a->m, (uint64_t)a->lda, BLOCK_M);
+            rc = make_tmap_bf16(&p.tma_a[s], a->a[s], (uint64_t)a->k, (uint64_t)a->m, (uint64_t)a->lda, BLOCK_M);
         else
-            rc = make_tmap(&p.tma_a[s], a->a[s], (uint64_t)a->m, (uint64_t)a->k, (uint64_t)a->lda, 64);
+            rc = make_tmap_bf16(&p.tma_a[s], a->a[s], (uint64_t)a->m, (uint64_t)a->k, (uint64_t)a->lda, 64);
         if (rc) return rc;
         if (a->b_layout == 0) {
-            rc = make_tmap(&p.tma_b[s], a->b[s], (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)(block_n / cl));
+            rc = make_tmap_bf16(&p.tma_b[s], a->b[s], (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)(block_n / cl));
             if (rc) return rc;
             if (p.full_tiles < p.m_tiles * p.n_tiles)
-                rc = make_tmap(&p.tma_b_half[s], a->b[s], (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)(block_n / cl / 2));
+                rc = make_tmap_bf16(&p.tma_b_half[s], a->b[s], (uint64_t)a->k, (uint64_t)a->n, (uint64_t)a->ldb, (uint32_t)(block_n / cl / 2));
         } else
-            rc = make_tmap(&p.tma_b[s], a->b[s], (uint64_t)a->n, (uint64_t)a->k, (uint64_t)a->ldb, 64);
+            rc = make_tmap_bf16(&p.tma_b[s], a->b[s], (uint64_t)a->n, (uint64_t)a->k, (uint64_t)a->ldb, 64);
         if (rc) return rc;
     }
 

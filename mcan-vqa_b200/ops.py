@@ -189,6 +189,40 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, 
     capi.check(lib.mcan_gemm(ctypes.byref(args)), "mcan_gemm")
 
 
+def gemm_ln(a, w, *, bias, resid, ln_a2, ln_b2, eps, dropout_p=0.0, seed=0, s_f32=None, y_f32=None, y_bf16=None,
+            mean=None, sigma=None):
+    """y = LayerNorm(resid + dropout(a w^T + bias)) in ONE kernel (see include/mcan_b200.h, mcan_gemm_ln).
+    a: bf16 [M,K]; w: bf16 [N,K] with N in {512, 1024}; outputs contiguous [M,N]."""
+    lib = capi.load()
+    _req2d(a, _BF16, "gemm_ln a")
+    _req2d(w, _BF16, "gemm_ln w")
+    _req2d(resid, _F32, "gemm_ln resid")
+    m, k = a.shape
+    n = w.shape[0]
+    if w.shape[1] != k or resid.shape != (m, n):
+        raise capi.McanError("gemm_ln: shape mismatch")
+    args = capi.GemmLnArgs()
+    args.a, args.b = a.data_ptr(), w.data_ptr()
+    args.m, args.n, args.k = m, n, k
+    args.lda, args.ldb = a.stride(0), w.stride(0)
+    _req(bias, _F32, "gemm_ln bias")
+    args.bias = bias.data_ptr()
+    args.dropout_p = float(dropout_p)
+    args.dropout_seed = int(seed) & 0xFFFFFFFF
+    args.dropout_seed_dev = _seed_ptr()
+    args.resid, args.ldr = resid.data_ptr(), resid.stride(0)
+    args.ln_a2, args.ln_b2, args.eps = ln_a2.data_ptr(), ln_b2.data_ptr(), float(eps)
+    for t, dt, nm in ((s_f32, _F32, "s_f32"), (y_f32, _F32, "y_f32"), (y_bf16, _BF16, "y_bf16")):
+        if t is not None:
+            _req(t, dt, "gemm_ln " + nm)
+            if t.shape != (m, n) or not t.is_contiguous():
+                raise capi.McanError("gemm_ln: %s must be contiguous [M,N]" % nm)
+    args.s_f32, args.y_f32, args.y_bf16 = _ptr(s_f32), _ptr(y_f32), _ptr(y_bf16)
+    args.mean, args.sigma = _ptr(mean), _ptr(sigma)
+    args.stream = _stream()
+    capi.check(lib.mcan_gemm_ln(ctypes.byref(args)), "mcan_gemm_ln")
+
+
 def _attn_args(q, k, v, key_mask, batch, heads, sq, sk, head_dim, scale, dropout_p, seed):
     for t, nm in ((q, "q"), (k, "k"), (v, "v")):
         _req2d(t, _BF16, "attn " + nm)

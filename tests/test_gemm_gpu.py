@@ -325,3 +325,66 @@ def test_gemm_epilogue_colsum_of_gated_output(m, n, k, cta_group):
     ref = torch.where(gate.float() > 0, (a.float() @ w.float()) * 1.25, torch.zeros((), device="cuda"))
     _close(out, ref, 6e-3, "gate")
     _close(cs, ref.sum(0) + 0.5, 2e-5 * (m ** 0.5), "colsum")
+
+
+@pytest.mark.parametrize("m,n,k", [(256, 512, 512), (6400, 512, 2048), (100, 512, 192), (256, 1024, 1024), (6400, 1024, 1024),
+                                   (896, 1024, 4096), (300, 1024, 512), (6400, 1024, 4096)])
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_gemm_ln_fused_epilogue(m, n, k, p_drop):
+    """mcan_gemm_ln: LayerNorm(resid + dropout(a W^T + b)) in one kernel (cluster owns whole rows; N = 1024 exchanges
+    the row statistics through DSMEM) vs torch fp64 math with the identical dropout mask, and vs the unfused chain."""
+    ops = _ops()
+    a, w = _rand((m, k), 41), _rand((n, k), 42, 0.05)
+    g = torch.Generator(device="cpu").manual_seed(43)
+    bias = torch.randn(n, generator=g).cuda()
+    resid = (torch.randn(m, n, generator=g) * 1.5 + 0.3).cuda()
+    a2 = (1.0 + 0.1 * torch.randn(n, generator=g)).cuda()
+    b2 = (0.1 * torch.randn(n, generator=g)).cuda()
+    eps, seed = 1e-6, 777
+    s = torch.full((m, n), float("nan"), device="cuda")
+    y32 = torch.full((m, n), float("nan"), device="cuda")
+    ybf = torch.empty((m, n), device="cuda", dtype=torch.bfloat16)
+    mean = torch.empty(m, device="cuda")
+    sigma = torch.empty(m, device="cuda")
+    ops.gemm_ln(a, w, bias=bias, resid=resid, ln_a2=a2, ln_b2=b2, eps=eps, dropout_p=p_drop, seed=seed, s_f32=s, y_f32=y32,
+                y_bf16=ybf, mean=mean, sigma=sigma)
+    torch.cuda.synchronize()
+    acc = a.double() @ w.double().t() + bias.double()
+    if p_drop > 0:
+        keep = ops.dropout_keep_mask(m * n, p_drop, seed).view(m, n).cuda()
+        acc = torch.where(keep, acc / (1 - p_drop), torch.zeros((), device="cuda", dtype=torch.float64))
+    s_ref = acc + resid.double()
+    mu = s_ref.mean(-1, keepdim=True)
+    sd = s_ref.std(-1, keepdim=True)            # unbiased, like the reference
+    y_ref = a2.double() * (s_ref - mu) / (sd + eps) + b2.double()
+    _close(s, s_ref.float(), 2e-5, "s")
+    _close(mean, mu.squeeze(-1).float(), 2e-5, "mean")
+    _close(sigma, sd.squeeze(-1).float(), 2e-5, "sigma")
+    _close(y32, y_ref.float(), 3e-5, "y fp32")
+    assert torch.equal(ybf, y32.to(torch.bfloat16))
+    # the unfused chain produces the same numbers (same dropout hash)
+    s2 = torch.empty((m, n), device="cuda")
+    ops.gemm(a, w, bias=bias, dropout_p=p_drop, seed=seed, resid=resid, out_f32=s2)
+    y2 = torch.empty((m, n), device="cuda")
+    ops.layernorm_fwd(s2, a2, b2, eps, y_f32=y2)
+    torch.cuda.synchronize()
+    _close(s, s2, 1e-6, "s vs unfused")
+    _close(y32, y2, 2e-5, "y vs unfused")
+
+
+def test_gemm_ln_large_mean_rows_are_stable():
+    """Rows whose mean dwarfs their spread: the per-fragment exact statistics merged with Chan's formula must not
+    lose the variance (a one-pass sum / sum-of-squares would)."""
+    ops = _ops()
+    m, n, k = 256, 1024, 64
+    a = torch.zeros((m, k), device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros((n, k), device="cuda", dtype=torch.bfloat16)
+    g = torch.Generator(device="cpu").manual_seed(5)
+    resid = (1000.0 + 0.01 * torch.randn(m, n, generator=g)).cuda()
+    y = torch.empty((m, n), device="cuda")
+    ops.gemm_ln(a, w, bias=torch.zeros(n, device="cuda"), resid=resid, ln_a2=torch.ones(n, device="cuda"),
+                ln_b2=torch.zeros(n, device="cuda"), eps=1e-6, y_f32=y)
+    torch.cuda.synchronize()
+    r = resid.double()
+    ref = (r - r.mean(-1, keepdim=True)) / (r.std(-1, keepdim=True) + 1e-6)
+    assert (y.double() - ref).abs().max().item() < 2e-2      # fp32 input quantisation of 1000 + 0.01 x is 6e-5 / 0.01
