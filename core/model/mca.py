@@ -112,6 +112,10 @@ class SGA(nn.Module):
 class MCA_ED(nn.Module):
     """Encoder-decoder cascade (mca.py:171-186): L x SA on x, then L x SGA on y guided by the final x."""
 
+    # its backward hands the gradients of each finished layer to dp.layer_hook() (overlapped all-reduce); every
+    # other backbone is reduced through per-parameter hooks (mcan_vqa_b200/dp.py GradSync)
+    reports_layers = True
+
     def __init__(self, opt):
         super(MCA_ED, self).__init__()
         self.hidden_size = cfg_get(opt, "hidden_size")

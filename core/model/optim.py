@@ -27,6 +27,8 @@ class WarmupOptimizer(object):
         sync = dp.active()
         if sync is None or not sync.overlap:
             dp.sync_all_grads([p for g in self.optimizer.param_groups for p in g['params']])
+        else:
+            sync.step_done()
         self._rate = self.rate()
         for group in self.optimizer.param_groups:
             group['lr'] = self._rate

@@ -88,9 +88,15 @@ class GradSync(object):
         self.compress = os.environ.get("MCAN_DP_COMPRESS", "")      # "" (fp32 exchange) | "bf16"
         self.launches = 0
         self.hooks = []
+        self._backwards = 0     # backward passes since the last optimiser step (overlap mode allows exactly one)
+        # Only MCA_ED's backward hands its gradients over layer by layer (autograd._MCAEDRunner -> layer_hook);
+        # every other backbone (MCAClassifier, stand-alone SA / SGA stacks) is reduced through parameter hooks.
+        net = model.module if hasattr(model, "module") else model
+        backbone = getattr(net, backbone_prefix.rstrip("."), None)
+        self.layerwise = bool(getattr(backbone, "reports_layers", False))       # set by core/model/mca.py MCA_ED
         if self.world > 1 and overlap:
             for name, p in model.named_parameters():
-                if p.requires_grad and not name.startswith(backbone_prefix):
+                if p.requires_grad and not (self.layerwise and name.startswith(backbone_prefix)):
                     self.hooks.append(p.register_post_accumulate_grad_hook(self._param_ready))
 
     # -- overlap mode ---------------------------------------------------------------------
@@ -140,6 +146,13 @@ class GradSync(object):
     def _final(self):
         self._flush_ready()
         self._queued = False
+        self._backwards += 1
+        if self._backwards > 1 and self.world > 1:
+            # a second backward before the optimiser step would make autograd run `p.grad += new` on gradients that
+            # are being all-reduced in place (and reduce already-reduced sums again): refuse instead of racing
+            self._backwards = 0
+            raise RuntimeError("mcan dp: overlap mode needs exactly one backward per optimiser step "
+                               "(grad_accu_steps == 1); use dp.attach(model, overlap=False) for gradient accumulation")
         if self.defer_wait:
             return            # the optimiser consumes the buckets one by one (take_buckets)
         for w, _ in self.pending:
@@ -151,7 +164,12 @@ class GradSync(object):
         it touches that bucket's gradients (FusedAdamW.step_buckets: the parameter update of the
         first buckets overlaps the all-reduce of the last ones)."""
         out, self.pending = self.pending, []
+        self._backwards = 0
         return out
+
+    def step_done(self):
+        """The optimiser consumed this step's gradients (called by the overlay WarmupOptimizer / Trainer)."""
+        self._backwards = 0
 
     def remove(self):
         for h in self.hooks:

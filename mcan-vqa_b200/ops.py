@@ -26,6 +26,12 @@ def _ptr(t):
 def _req(t, dtype, name):
     if not t.is_cuda:
         raise capi.McanError("%s must be a CUDA tensor (the MCAN hot path has no CPU fallback)" % name)
+    if t.device.index != torch.cuda.current_device():
+        # kernels are enqueued on the CURRENT device's current stream (one process per GPU; nn.DataParallel
+        # replicas on other devices are not supported -- use torch.distributed + dp.attach)
+        raise capi.McanError("%s lives on %s but the current CUDA device is %d (one process per GPU: call "
+                             "torch.cuda.set_device first; nn.DataParallel is not supported)" %
+                             (name, t.device, torch.cuda.current_device()))
     if t.dtype != dtype:
         raise capi.McanError("%s must be %s, got %s" % (name, dtype, t.dtype))
 

@@ -56,6 +56,7 @@ class FusedAdamW(object):
         self._pinned = [torch.empty((len(self.params), _WORDS), dtype=torch.int64).pin_memory() for _ in range(8)]
         self.epoch = 0          # bumped on every step (and by note_replay): low-order copies go stale
         self._index = {id(p): i for i, p in enumerate(self.params)}
+        self._touched = set()   # indices of the parameters that have been updated at least once (state_dict emits only these)
         self._early_done = None  # ids of the parameters already updated in this step by an EarlyStep (None: no early step)
 
     # -- operand copies ------------------------------------------------------------------------
@@ -157,6 +158,7 @@ class FusedAdamW(object):
             return
         g0 = self.param_groups[0]
         table, _host, nseg, chunks = self._table(active)
+        self._touched.update(i for i, _ in active)
         b1, b2 = g0["betas"]
         lib = capi.load()
         capi.check(lib.mcan_adamw_multi(table.data_ptr(), nseg, chunks, self.lr_t.data_ptr(), self.step_t.data_ptr(),
@@ -207,7 +209,8 @@ class FusedAdamW(object):
         step = self.step_t.detach().clone().cpu()
         state = {}
         if float(step) > 0:
-            for i in range(len(self.params)):
+            # like torch.optim.AdamW: no state for a parameter that never received a gradient
+            for i in sorted(self._touched):
                 m, v = self._views(i)
                 state[i] = {"step": step.clone(), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
         g0 = self.param_groups[0]
@@ -225,6 +228,7 @@ class FusedAdamW(object):
                 self.param_groups[0][k] = tuple(groups[0][k]) if k == "betas" else groups[0][k]
         order = groups[0]["params"]
         steps = [0.0]
+        self._touched = set()
         for pos, idx in enumerate(order):
             st = sd["state"].get(idx)
             m, v = self._views(pos)
@@ -235,6 +239,11 @@ class FusedAdamW(object):
             m.copy_(st["exp_avg"])
             v.copy_(st["exp_avg_sq"])
             steps.append(float(st["step"]))
+            self._touched.add(pos)
+        if len(set(steps[1:])) > 1:
+            import warnings
+            warnings.warn("FusedAdamW.load_state_dict: per-parameter step counts differ (%s .. %s); this optimiser keeps ONE "
+                          "step counter and continues from the largest" % (min(steps[1:]), max(steps[1:])))
         self.step_t.fill_(max(steps))
 
 

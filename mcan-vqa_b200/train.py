@@ -99,6 +99,8 @@ class Trainer(object):
             self.opt.step_buckets(self.sync.take_buckets())
         else:
             self.opt.step()
+            if self.sync is not None:
+                self.sync.step_done()
         return loss.detach()
 
     def _set_lr(self):

@@ -34,18 +34,21 @@ class _LayerFn(torch.autograd.Function):
         g2 = flat[w1.numel():].view_as(w2)
         g1.copy_(((g * w2) * x).sum(0))
         g2.copy_((g * s).sum(0))
-        hook = dp.layer_hook()
+        hook = dp.layer_hook() if _Toy.use_hook else None
         if hook is not None:
             hook([flat])
         return (g * w2) * w1, g1, g2
 
 
 class _Toy(torch.nn.Module):
+    use_hook = True
+
     def __init__(self):
         super().__init__()
         g = torch.Generator().manual_seed(3)
         self.pre = torch.nn.Linear(6, 5)
         self.backbone = torch.nn.Module()
+        self.backbone.reports_layers = True      # like MCA_ED: its backward calls dp.layer_hook()
         self.backbone.w1 = torch.nn.Parameter(torch.randn(5, generator=g))
         self.backbone.w2 = torch.nn.Parameter(torch.randn(1, generator=g))
         self.post = torch.nn.Linear(1, 3)
@@ -101,6 +104,23 @@ def _worker(rank, world, port, mode, out):
                         assert n not in seen
                         seen.add(n)
         assert seen == {n for n, _ in model.named_parameters()}
+    elif mode == "plain_backbone":
+        # a backbone whose backward does NOT report its layers (MCAClassifier, stand-alone SA / SGA stacks):
+        # every parameter, backbone included, must be reduced through the parameter hooks
+        model.backbone.reports_layers = False
+        sync = dp.attach(model, overlap=True)
+        assert not sync.layerwise and len(sync.hooks) == len(list(model.parameters()))
+        _Toy.use_hook = False
+        loss_fn(model(xs), ys).backward()
+    elif mode == "second_backward":
+        # overlap mode reduces gradient buffers in place: a second backward before the optimiser step must be refused
+        sync = dp.attach(model, overlap=True)
+        loss_fn(model(xs), ys).backward()
+        with pytest.raises(RuntimeError, match="one backward per optimiser step"):
+            loss_fn(model(xs), ys).backward()
+        model.zero_grad(set_to_none=True)
+        sync.pending = []
+        loss_fn(model(xs), ys).backward()      # after the refusal the counter restarts: a normal step works again
     else:
         dp.attach(model, overlap=False)
         sys.path.insert(0, ROOT)
@@ -124,9 +144,9 @@ def _worker(rank, world, port, mode, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["overlap", "merged", "bf16", "buckets", "at_step"])
+@pytest.mark.parametrize("mode", ["overlap", "merged", "bf16", "buckets", "at_step", "plain_backbone", "second_backward"])
 def test_two_rank_sum_allreduce_equals_global_batch_gradient(mode, tmp_path):
     out = str(tmp_path / "ok.txt")
-    port = 29500 + (os.getpid() % 2000) + {"overlap": 0, "at_step": 1, "buckets": 2, "merged": 3, "bf16": 4}[mode]
+    port = 29500 + (os.getpid() % 2000) + {"overlap": 0, "at_step": 1, "buckets": 2, "merged": 3, "bf16": 4, "plain_backbone": 5, "second_backward": 6}[mode]
     mp.spawn(_worker, args=(2, port, mode, out), nprocs=2, join=True)
     assert open(out).read() == "ok"

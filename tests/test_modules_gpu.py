@@ -338,3 +338,37 @@ def test_classifier_net_against_oracle():
     # ... and directly against what the unmodified reference computed for these weights and inputs
     assert _rel_max(probs, torch.from_numpy(g["probs"])) < TOL_OUT
     assert abs(loss.item() - float(g["loss"])) < 2e-3 * abs(float(g["loss"]))
+
+
+def test_fused_gemm_layernorm_path_matches_unfused_chain():
+    """blocks.FUSE_LN (mcan_gemm_ln: residual add + LayerNorm in the GEMM epilogue, opt-in) through the whole Net at
+    MCAN-small width: probabilities and every parameter gradient equal the unfused chain up to summation order."""
+    from core.model.net import Net
+    from mcan_vqa_b200 import blocks
+    cfg = orc.Cfg(dropout_rate=0.1, **orc.SMALL)
+    T, A, B = 200, 64, 5
+    sd = orc.synth_state_dict(cfg, T, A, seed=5)
+    v, q, a = (t.cuda() for t in orc.synth_batch(cfg, B, 100, 14, T, A, seed=6, ragged="prefix"))
+    res = {}
+    saved = blocks.FUSE_LN
+    try:
+        for fuse in (False, True):
+            blocks.FUSE_LN = fuse
+            torch.manual_seed(3)
+            blocks._seed_counter[0] = 0
+            net = Net(cfg, None, T, A)
+            net.load_state_dict(sd)
+            net = net.cuda().train()
+            from mcan_vqa_b200 import capi
+            c0 = capi.launch_count
+            probs = net(v, q)[0]
+            torch.nn.BCELoss(reduction="sum")(probs, a).backward()
+            torch.cuda.synchronize()
+            res[fuse] = (probs.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters()}, capi.launch_count - c0)
+    finally:
+        blocks.FUSE_LN = saved
+    assert res[True][2] < res[False][2]          # the LayerNorm launches of the decoder / encoder sub-layers are gone
+    assert (res[True][0] - res[False][0]).abs().max().item() < 2e-3
+    for n, g in res[False][1].items():
+        err = (res[True][1][n] - g).norm().item()
+        assert err < 2e-2 * g.norm().item() + 1e-6, (n, err, g.norm().item())
