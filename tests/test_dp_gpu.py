@@ -48,10 +48,11 @@ def _worker(rank, world, port, model, out):
         full_loss.backward()
         torch.cuda.synchronize()
         worst = (0.0, "")
+        total = torch.sqrt(sum(p.grad.double().pow(2).sum() for p in net.parameters())).item()
         for n, p in net.named_parameters():
             ref = p.grad
-            if ref.norm().item() == 0.0:
-                assert grads[n].norm().item() == 0.0, n
+            if ref.norm().item() < 1e-6 * total:      # mathematically zero (linear_k biases: softmax shift invariance)
+                assert grads[n].norm().item() < 1e-5 * total, n
                 continue
             err = ((grads[n] - ref).norm() / ref.norm()).item()
             worst = max(worst, (err, n))
