@@ -4,8 +4,9 @@ Class names, constructor signatures, forward arity (Net: 8 outputs, Net2 / Class
 state_dict keys follow /root/reference/core/model/net.py:20-381, so core/exec.py trains,
 evaluates, checkpoints and visualises unchanged.  The co-attention backbone (MCA_ED), both
 AttFlat poolings, proj_norm and the two big projections (img_feat_linear, proj) run on the
-hand-written sm_100a kernels; embedding + LSTM, the mask test and the final sigmoid stay stock
-PyTorch (rows "next" in SURVEY.md 8f).
+hand-written sm_100a kernels; so do the zero-row mask of the image features (computed in the pass that
+casts them to the GEMM operand) and the output head proj_norm -> proj -> sigmoid (-> BCE(sum) through
+`forward_with_loss`, what core/exec.py:178 computes with loss_fn).  Embedding + LSTM stay stock PyTorch.
 """
 import torch
 import torch.nn as nn
@@ -73,25 +74,31 @@ class _VQABase(nn.Module):
         return (self.backbone.all_lps() + self.attflat_img.all_lps() + self.attflat_lang.all_lps() +
                 [self.img_feat_linear.lp(), self.proj.lp()])
 
-    def _features(self, v, ques_ix):
-        with refresh_scope(self.all_lps(), self.training or torch.is_grad_enabled()):
-            return self._features_impl(v, ques_ix)
-
     def _features_impl(self, v, ques_ix):
         q_mask = _make_mask(ques_ix.unsqueeze(2))
-        v_mask = _make_mask(v)
         if _blocks.PRECISION == "fp32" and not torch.is_grad_enabled():
             # fp32-grade inference: cuDNN's RNN GEMMs default to TF32 (1e-3); switch that off
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 q, _ = self.lstm(self.embedding(ques_ix))
         else:
             q, _ = self.lstm(self.embedding(ques_ix))
-        v = self.img_feat_linear(v)
+        v, v_mask = _ag.linear_mask(self.img_feat_linear, v)      # img_feat_linear + make_mask(v) in one pass
         q, v = self.backbone(q, v, q_mask, v_mask)
         lang, q_w = self.attflat_lang(q, q_mask)
         img, v_w = self.attflat_img(v, v_mask)
-        a = self.proj_norm(lang + img)
-        return q, v, q_mask, v_mask, q_w, v_w, a, self.proj(a)
+        return q, v, q_mask, v_mask, q_w, v_w, lang, img
+
+    def _features(self, v, ques_ix, target=None):
+        with refresh_scope(self.all_lps(), self.training or torch.is_grad_enabled()):
+            q, v, q_mask, v_mask, q_w, v_w, lang, img = self._features_impl(v, ques_ix)
+            head = _ag.head(self.proj_norm, self.proj, lang, img, target)
+        return (q, v, q_mask, v_mask, q_w, v_w) + tuple(head)
+
+    def forward_with_loss(self, v, ques_ix, ans):
+        """(BCELoss(reduction='sum')(probs, ans), probs): the loss core/exec.py:178 computes from forward()'s first
+        output, fused with the sigmoid (forward) and with the proj gradient operand (backward)."""
+        out = self._features(v, ques_ix, ans)
+        return out[8], out[7]
 
     def make_mask(self, feature):
         return _make_mask(feature)
@@ -105,8 +112,7 @@ class Net(_VQABase):
         self._build(opt, pretrained_emb, token_size, answer_size, {})
 
     def forward(self, v, ques_ix):
-        q, v, q_mask, v_mask, q_w, v_w, a, logits = self._features(v, ques_ix)
-        probs = torch.sigmoid(logits)
+        q, v, q_mask, v_mask, q_w, v_w, a, probs = self._features(v, ques_ix)
         return probs, v, v_mask, v_w, q, q_mask, q_w, a
 
 
@@ -121,8 +127,7 @@ class Net2(_VQABase):
             self._build(opt, pretrained_emb, token_size, answer_size, {"dropout": cfg_get(opt, "dropout_rate")})
 
     def forward(self, v, ques_ix):
-        q, v, q_mask, v_mask, _, _, a, logits = self._features(v, ques_ix)
-        probs = torch.sigmoid(logits)
+        q, v, q_mask, v_mask, _, _, a, probs = self._features(v, ques_ix)
         return probs, v, v_mask, q, q_mask
 
 
@@ -139,11 +144,12 @@ class ClassifierNet(nn.Module):
         self.proj = TCLinear(cfg_get(opt, "flat_out_size"), answer_size)
 
     def forward(self, v):
-        v_mask = _make_mask(v)
-        v = self.backbone(self.img_feat_linear(v), v_mask)
-        img, v_w = self.attflat_img(v, v_mask)
-        a = self.proj_norm(img)
-        probs = torch.sigmoid(self.proj(a))
+        lps = self.backbone.all_lps() + self.attflat_img.all_lps() + [self.img_feat_linear.lp(), self.proj.lp()]
+        with refresh_scope(lps, self.training or torch.is_grad_enabled()):
+            v, v_mask = _ag.linear_mask(self.img_feat_linear, v)
+            v = self.backbone(v, v_mask)
+            img, v_w = self.attflat_img(v, v_mask)
+            a, probs = _ag.head(self.proj_norm, self.proj, img)
         return probs, v, v_mask, v_w, a
 
     def make_mask(self, feature):

@@ -214,6 +214,12 @@ int mcan_layernorm_fwd(const float* x, int64_t rows, int64_t h, const float* a2,
                        float eps, float* y_f32, void* y_bf16, void* y_bf16_lo, float* mean,
                        float* sigma, void* stream);
 
+/* Same, for a row that is the SUM of two inputs (proj_norm(lang_feat + img_feat), net.py:125-126):
+ * s = x + x2 is normalised; s_out (optional) receives s for the backward pass. */
+int mcan_layernorm_add_fwd(const float* x, const float* x2, float* s_out, int64_t rows, int64_t h,
+                           const float* a2, const float* b2, float eps, float* y_f32, void* y_bf16,
+                           void* y_bf16_lo, float* mean, float* sigma, void* stream);
+
 /* dx = LayerNorm backward, plus:
  *   dx_bf16 (optional) = bf16( dropout_mask(seed)[r,c] * dx / (1-p) )  -- the gradient that flows
  *       into the GEMM whose epilogue produced x = resid + dropout(gemm), ready as a GEMM operand;
@@ -247,6 +253,29 @@ int mcan_attflat_pool_bwd(const float* dpooled, const void* hmid, const float* w
                           const uint8_t* mask, const float* x, const float* att_w, int32_t batch,
                           int32_t s, int32_t h, int32_t mlp, int32_t glimpses, float gate_scale,
                           float* dx, void* dhmid, float* dw2, float* db2, void* stream);
+
+/* -- the two ends of the path ---------------------------------------
+ * Image-side input (net.py:100,107,135-137): one pass over the fp32 region features x [rows, cols]
+ * writes the bf16 operand of img_feat_linear (hi [+ lo], leading dimension ld >= cols) AND
+ * mask[row] = 1 iff every feature of the row is zero  (== (sum(|x|, -1) == 0) of make_mask). */
+int mcan_rowmask_cast(const float* x, int64_t rows, int64_t cols, void* hi, void* lo, int64_t ld,
+                      uint8_t* mask, void* stream);
+
+/* Output head (net.py:127-129, exec.py:67,178): probs = sigmoid(logits) (logits fp32 [rows, ld], probs
+ * contiguous [rows, cols]); with target != NULL also *loss = BCELoss(reduction='sum')(probs, target),
+ * torch semantics (log terms clamped at -100), summed in a fixed order (bit-reproducible).
+ * workspace: >= 1025 floats of device memory, zero before the first call (the kernel leaves it ready for
+ * the next call); needed only with loss. */
+int mcan_sigmoid_bce_fwd(const float* logits, int64_t ld, const float* target, int32_t rows, int32_t cols,
+                         float* probs, float* loss, float* workspace, void* stream);
+
+/* Backward into the bf16 operand dz [rows, ld] (pad columns zeroed) of the proj wgrad / dgrad GEMMs, and
+ * dbias[c] += sum_r dz[r, c] (optional; fp32 atomics on a zeroed buffer).
+ *   target != NULL: dz = g (p - t) / max(p (1-p), 1e-12) * p (1-p),  g = *gscale_dev (1 if NULL)  -- BCE(sum) + sigmoid
+ *   gout   != NULL: dz = gout * p (1-p)                                                        -- sigmoid only
+ * Exactly one of target / gout is given. */
+int mcan_sigmoid_bce_bwd(const float* probs, const float* target, const float* gout, const float* gscale_dev,
+                         int32_t rows, int32_t cols, void* dz_bf16, int64_t ld, float* dbias, void* stream);
 
 /* -- small memory-bound helpers -------------------------------------------------------- */
 /* hi = bf16(x); lo (optional) = bf16(x - hi).  n elements. */

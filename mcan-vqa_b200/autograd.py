@@ -32,10 +32,21 @@ def _as_f32_2d(x, feat):
 
 
 def _mask_u8(mask, B, S):
-    """bool [B,1,1,S] (True = masked, net.py:135-137) -> contiguous uint8 [B,S]; None passes through."""
+    """bool [B,1,1,S] (True = masked, net.py:135-137) -> contiguous uint8 [B,S]; None passes through.
+    A mask produced by the library (linear_mask / the question encoder) carries its uint8 storage along."""
     if mask is None:
         return None
+    u8 = getattr(mask, "_mcan_u8", None)
+    if u8 is not None and u8.numel() == B * S:
+        return u8.view(B, S)
     return mask.reshape(B, S).to(torch.uint8).contiguous()
+
+
+def mask_from_u8(u8, B, S):
+    """uint8 [B*S] written by a kernel -> the reference's bool mask [B,1,1,S] (a view of the same bytes)."""
+    m = u8.view(torch.bool).view(B, 1, 1, S)
+    m._mcan_u8 = u8
+    return m
 
 
 class _Chain(torch.autograd.Function):
@@ -44,6 +55,8 @@ class _Chain(torch.autograd.Function):
         ctx.runner = runner
         ctx.n_act = n_act
         ctx.act_needs = [t is not None and t.requires_grad for t in tensors[:n_act]]
+        if runner.sparse_grads:
+            ctx.set_materialize_grads(False)    # unused outputs arrive as None instead of zero tensors
         outs = runner.forward(tensors[:n_act])
         for t in runner.non_differentiable:
             ctx.mark_non_differentiable(t)
@@ -60,6 +73,7 @@ class _Chain(torch.autograd.Function):
 
 class _Runner(object):
     non_differentiable = ()
+    sparse_grads = False
 
     def __init__(self, module, params):
         self.module = module
@@ -355,3 +369,79 @@ class _LinearRunner(_Runner):
 
 def linear(module, x):
     return _run(_LinearRunner(module, [module.weight, module.bias]), [x])
+
+
+class _LinearMaskRunner(_LinearRunner):
+    """img_feat_linear together with make_mask of its input (net.py:100,107,135-137): the fp32 features are read once."""
+
+    def forward(self, acts):
+        (x,) = acts
+        lin = self.module
+        self.shape = x.shape
+        lp = lin.lp().get(blocks._force(torch.is_grad_enabled()), self.rt.split)
+        x2 = _as_f32_2d(x, lp.k)
+        mask = torch.empty(x2.shape[0], dtype=torch.uint8, device=x.device)
+        out, self.c = blocks.linear_fwd(lp, x2, self.rt.split, mask_out=mask)
+        self.non_differentiable = (mask,)
+        out = out.contiguous().view(self.shape[:-1] + (lp.n,)) if out.stride(0) != lp.n else out.view(self.shape[:-1] + (lp.n,))
+        return out, mask
+
+
+def linear_mask(module, x):
+    """-> (module(x), bool mask [B,1,1,S] of all-zero rows of x)."""
+    out, u8 = _run(_LinearMaskRunner(module, [module.weight, module.bias]), [x])
+    return out, mask_from_u8(u8, x.shape[0], x.shape[1])
+
+
+# ------------------------------------------------------------------------------------------
+class _HeadRunner(_Runner):
+    """proj_norm(lang [+ img]) -> proj -> sigmoid [-> BCELoss(reduction='sum')] as one kernel chain
+    (net.py:125-129 / 182-184; the loss of exec.py:67,178 when a target is given)."""
+    sparse_grads = True
+
+    def __init__(self, norm, proj):
+        _Runner.__init__(self, proj, [norm.a_2, norm.b_2, proj.weight, proj.bias])
+        self.norm = norm
+
+    def forward(self, acts):
+        x, x2, target = acts
+        proj = self.module
+        lp = proj.lp().get(blocks._force(torch.is_grad_enabled()), self.rt.split)
+        self.shape = x.shape
+        xs = _as_f32_2d(x, lp.k)
+        x2s = _as_f32_2d(x2, lp.k) if x2 is not None else None
+        tg = None
+        if target is not None:
+            tg = _as_f32_2d(target, lp.n)
+        a, probs, loss, self.c = blocks.head_fwd(self.rt, self.norm, lp, xs, x2s, tg)
+        self.has_x2 = x2 is not None
+        lead = self.shape[:-1]
+        a, probs = a.view(lead + (lp.k,)), probs.view(lead + (lp.n,))
+        if loss is None:
+            return a, probs
+        self.non_differentiable = (probs,)
+        return a, probs, loss
+
+    def backward(self, gouts, needs):
+        proj = self.module
+        lp = self.c.lp
+        g_a = _as_f32_2d(gouts[0], lp.k) if gouts[0] is not None else None
+        if self.c.target is not None:
+            g_probs, g_loss = None, gouts[2]
+            if g_loss is None:
+                g_loss = torch.zeros((), dtype=torch.float32, device=self.c.probs.device)
+            g_loss = g_loss.detach().float().contiguous()
+        else:
+            g_loss = None
+            g_probs = gouts[1]
+            if g_probs is None:
+                g_probs = torch.zeros_like(self.c.probs)
+            g_probs = _as_f32_2d(g_probs, lp.n)
+        ds, gw, gb, da2, db2 = blocks.head_bwd(self.rt, self.norm, self.c, g_a, g_probs, g_loss)
+        ds = ds.view(self.shape)
+        return [ds, ds if self.has_x2 else None, None], {self.norm.a_2: da2, self.norm.b_2: db2, proj.weight: gw, proj.bias: gb}
+
+
+def head(norm, proj, x, x2=None, target=None):
+    """-> (proj_feat, probs) or, with a target, (proj_feat, probs, BCE-sum loss)."""
+    return _run(_HeadRunner(norm, proj), [x, x2, target])

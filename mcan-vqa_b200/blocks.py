@@ -907,18 +907,20 @@ def attflat_bwd(rt, af, c, dout, need_dx=True):
 # ------------------------------------------------------------------------------------------
 # plain linear on the tcgen05 GEMM (img_feat_linear / proj: the rows next to the hot path)
 # ------------------------------------------------------------------------------------------
-def linear_fwd(lp, x32, split=False):
+def linear_fwd(lp, x32, split=False, mask_out=None):
+    """mask_out (uint8 [rows], optional): also receives the reference's zero-row mask of x32 (net.py:135-137),
+    computed in the same pass that casts x32 to the bf16 GEMM operand."""
     dev = x32.device
     M = x32.shape[0]
     c = Bag()
     xbf = _bf_padded(M, lp.k, dev)
     xlo = _bf_padded(M, lp.k, dev) if split else None
-    if xbf.stride(0) == lp.k:
+    if mask_out is not None:
+        ops.rowmask_cast(x32.contiguous(), xbf, xlo, mask_out)
+    elif xbf.stride(0) == lp.k:
         ops.cast_bf16(x32.contiguous(), xbf, xlo)
     else:
-        xbf.copy_(x32)
-        if split:
-            xlo.copy_(x32 - xbf.float())
+        ops.rowmask_cast(x32.contiguous(), xbf, xlo)
     ldo = (lp.n + 3) // 4 * 4
     out = torch.empty((M, ldo), dtype=_F32, device=dev)[:, :lp.n]
     if split:
@@ -947,3 +949,58 @@ def linear_bwd(rt, c, dout, need_dx=True):
         ops.gemm(dbf, lp.w, b_layout=1, out_f32=dx)
     (gw, gb), = g.per_param()
     return dx, gw, gb
+
+
+# ------------------------------------------------------------------------------------------
+# output head: proj_norm(lang [+ img]) -> proj -> sigmoid [-> BCELoss(sum)]
+# (net.py:125-129, 182-184; exec.py:67,178)
+# ------------------------------------------------------------------------------------------
+def head_fwd(rt, norm, lp, x, x2, target):
+    """x, x2 (or None): fp32 [B, O]; target fp32 [B, A] or None.
+    Returns (a fp32 [B,O], probs fp32 [B,A], loss 0-dim or None, ctx)."""
+    dev = x.device
+    B, O = x.shape
+    c = Bag()
+    y32 = _empty(B, O, _F32, dev)
+    ybf = _empty(B, O, _BF16, dev)
+    ylo = _empty(B, O, _BF16, dev) if rt.split else None
+    c.mean = torch.empty(B, dtype=_F32, device=dev)
+    c.sigma = torch.empty(B, dtype=_F32, device=dev)
+    if x2 is None:
+        c.s = x
+        ops.layernorm_fwd(x, norm.a_2.detach(), norm.b_2.detach(), norm.eps, y_f32=y32, y_bf16=ybf, y_lo=ylo,
+                          mean=c.mean, sigma=c.sigma)
+    else:
+        c.s = _empty(B, O, _F32, dev)
+        ops.layernorm_add_fwd(x, x2, norm.a_2.detach(), norm.b_2.detach(), norm.eps, s_out=c.s, y_f32=y32,
+                              y_bf16=ybf, y_lo=ylo, mean=c.mean, sigma=c.sigma)
+    ldo = (lp.n + 3) // 4 * 4
+    logits = torch.empty((B, ldo), dtype=_F32, device=dev)[:, :lp.n]
+    if rt.split:
+        ops.gemm([ybf, ybf, ylo], [lp.w, lp.w_lo, lp.w], bias=lp.b, out_f32=logits)
+    else:
+        ops.gemm(ybf, lp.w, bias=lp.b, out_f32=logits)
+    probs = _empty(B, lp.n, _F32, dev)
+    loss = torch.empty((), dtype=_F32, device=dev) if target is not None else None
+    ops.sigmoid_bce_fwd(logits, probs, target, loss)
+    c.abf, c.lp, c.probs, c.target = ybf, lp, probs, target
+    return y32, probs, loss, c
+
+
+def head_bwd(rt, norm, c, g_a, g_probs, g_loss):
+    """Returns (ds fp32 [B,O] -- the gradient of both summands --, {parameter-role: gradient})."""
+    lp = c.lp
+    dev = c.probs.device
+    B = c.probs.shape[0]
+    g = GradBuf(rt, lp)
+    dz = torch.empty((B, (lp.n + 7) // 8 * 8), dtype=_BF16, device=dev)[:, :lp.n]     # the kernel zeroes the pad columns
+    if c.target is not None:
+        ops.sigmoid_bce_bwd(c.probs, dz, target=c.target, gscale=g_loss, dbias=g.b)
+    else:
+        ops.sigmoid_bce_bwd(c.probs, dz, gout=g_probs.contiguous(), dbias=g.b)
+    ops.gemm(dz, c.abf, a_layout=1, b_layout=1, out_f32=g.w, accumulate=True)
+    da = _empty(B, lp.k, _F32, dev)
+    ops.gemm(dz, lp.w, b_layout=1, out_f32=da, resid=g_a)
+    ds, _, da2, db2 = ln_bwd(rt, norm, da, c.s, c.mean, c.sigma, want_bf=False)
+    (gw, gb), = g.per_param()
+    return ds, gw, gb, da2, db2

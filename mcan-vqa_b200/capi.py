@@ -138,6 +138,13 @@ SYMBOLS = {
     "mcan_attn_bwd": (ctypes.c_int, [ctypes.POINTER(AttnBwdArgs)]),
     "mcan_layernorm_fwd": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcan_layernorm_add_fwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float,
+                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "mcan_rowmask_cast": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "mcan_sigmoid_bce_fwd": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
+                                            c_void_p]),
+    "mcan_sigmoid_bce_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int64,
+                                            c_void_p, c_void_p]),
     "mcan_layernorm_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                           c_int64, c_int64, c_void_p, c_void_p, c_float, c_uint32,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

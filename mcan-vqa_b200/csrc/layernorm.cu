@@ -29,7 +29,8 @@ __device__ __forceinline__ float bf16_round(float v) {
 // MAXV = float4 slots per lane; h <= MAXV * 128, h % 4 == 0.
 template <int MAXV>
 __global__ void __launch_bounds__(kLnWarps * 32)
-ln_fwd_kernel(const float* __restrict__ x, long long rows, int h, const float* __restrict__ a2,
+ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ x2, float* __restrict__ s_out,
+              long long rows, int h, const float* __restrict__ a2,
               const float* __restrict__ b2, float eps, float* __restrict__ y32,
               bf16* __restrict__ ybf, bf16* __restrict__ ylo, float* __restrict__ mean_out,
               float* __restrict__ sigma_out) {
@@ -46,6 +47,11 @@ ln_fwd_kernel(const float* __restrict__ x, long long rows, int h, const float* _
     for (int j = 0; j < MAXV; ++j) {
         const int i = lane + 32 * j;
         v[j] = (i < nv) ? xr[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (x2 != nullptr && i < nv) {      // the normalised row is the sum of two inputs (proj_norm(lang + img))
+            const float4 w = reinterpret_cast<const float4*>(x2 + row * h)[i];
+            v[j].x += w.x; v[j].y += w.y; v[j].z += w.z; v[j].w += w.w;
+            if (s_out != nullptr) reinterpret_cast<float4*>(s_out + row * h)[i] = v[j];
+        }
         sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
     }
     const float mean = warp_sum(sum) / (float)h;
@@ -225,10 +231,11 @@ int device_num_sms();
 
 using namespace mcan;
 
-extern "C" int mcan_layernorm_fwd(const float* x, int64_t rows, int64_t h, const float* a2,
-                                  const float* b2, float eps, float* y_f32, void* y_bf16,
-                                  void* y_bf16_lo, float* mean, float* sigma, void* stream) {
+static int layernorm_fwd_impl(const float* x, const float* x2, float* s_out, int64_t rows, int64_t h, const float* a2,
+                              const float* b2, float eps, float* y_f32, void* y_bf16,
+                              void* y_bf16_lo, float* mean, float* sigma, void* stream) {
     MCAN_REQUIRE(x && a2 && b2, "mcan_layernorm_fwd: null input");
+    MCAN_REQUIRE((((uintptr_t)x2 | (uintptr_t)s_out) & 15) == 0, "mcan_layernorm_add_fwd: alignment");
     MCAN_REQUIRE(rows > 0 && h >= 8 && h % 4 == 0 && h <= 2048, "mcan_layernorm_fwd: rows=%lld h=%lld (h%%4==0, 8..2048)",
                  (long long)rows, (long long)h);
     MCAN_REQUIRE(rows * h < (1LL << 32), "mcan_layernorm_fwd: too large");
@@ -239,13 +246,26 @@ extern "C" int mcan_layernorm_fwd(const float* x, int64_t rows, int64_t h, const
     const int grid = (int)((rows + kLnWarps - 1) / kLnWarps);
     bf16* ybf = reinterpret_cast<bf16*>(y_bf16);
     bf16* ylo = reinterpret_cast<bf16*>(y_bf16_lo);
-#define LN_FWD(MV) MCAN_CHECK_CUDA(launch_kernel(ln_fwd_kernel<MV>, dim3(grid), dim3(kLnWarps * 32), 0, st, x, (long long)rows, (int)h, a2, b2, eps, y_f32, ybf, ylo, mean, sigma))
+#define LN_FWD(MV) MCAN_CHECK_CUDA(launch_kernel(ln_fwd_kernel<MV>, dim3(grid), dim3(kLnWarps * 32), 0, st, x, x2, s_out, (long long)rows, (int)h, a2, b2, eps, y_f32, ybf, ylo, mean, sigma))
     if (h <= 512) LN_FWD(4);
     else if (h <= 1024) LN_FWD(8);
     else LN_FWD(16);
 #undef LN_FWD
     MCAN_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int mcan_layernorm_fwd(const float* x, int64_t rows, int64_t h, const float* a2,
+                                  const float* b2, float eps, float* y_f32, void* y_bf16,
+                                  void* y_bf16_lo, float* mean, float* sigma, void* stream) {
+    return layernorm_fwd_impl(x, nullptr, nullptr, rows, h, a2, b2, eps, y_f32, y_bf16, y_bf16_lo, mean, sigma, stream);
+}
+
+extern "C" int mcan_layernorm_add_fwd(const float* x, const float* x2, float* s_out, int64_t rows, int64_t h,
+                                      const float* a2, const float* b2, float eps, float* y_f32, void* y_bf16,
+                                      void* y_bf16_lo, float* mean, float* sigma, void* stream) {
+    MCAN_REQUIRE(x2 != nullptr, "mcan_layernorm_add_fwd: null x2");
+    return layernorm_fwd_impl(x, x2, s_out, rows, h, a2, b2, eps, y_f32, y_bf16, y_bf16_lo, mean, sigma, stream);
 }
 
 extern "C" int mcan_layernorm_bwd(const float* dy, const float* x, const float* mean,

@@ -292,6 +292,89 @@ def layernorm_fwd(x, a2, b2, eps, *, y_f32=None, y_bf16=None, y_lo=None, mean=No
                                       _stream()), "mcan_layernorm_fwd")
 
 
+def layernorm_add_fwd(x, x2, a2, b2, eps, *, s_out=None, y_f32=None, y_bf16=None, y_lo=None, mean=None, sigma=None):
+    """MCAN LayerNorm of the sum x + x2 (both fp32 [rows, h], contiguous); s_out receives the sum."""
+    lib = capi.load()
+    _req(x, _F32, "layernorm x")
+    _req(x2, _F32, "layernorm x2")
+    if not (x.is_contiguous() and x2.is_contiguous()) or x.shape != x2.shape:
+        raise capi.McanError("layernorm_add_fwd: x and x2 must be contiguous and of equal shape")
+    h = x.shape[-1]
+    rows = x.numel() // h
+    capi.check(lib.mcan_layernorm_add_fwd(x.data_ptr(), x2.data_ptr(), _ptr(s_out), rows, h, a2.data_ptr(), b2.data_ptr(),
+                                          float(eps), _ptr(y_f32), _ptr(y_bf16), _ptr(y_lo), _ptr(mean), _ptr(sigma),
+                                          _stream()), "mcan_layernorm_add_fwd")
+
+
+def rowmask_cast(x, hi, lo=None, mask=None):
+    """hi (bf16 [rows, cols], row-strided) = bf16(x), lo = bf16(x - hi), mask[row] = 1 iff the fp32 row x[row] is all zero
+    (net.py:135-137) -- one pass over x (fp32 [rows, cols], contiguous)."""
+    lib = capi.load()
+    _req(x, _F32, "rowmask_cast x")
+    _req2d(hi, _BF16, "rowmask_cast hi")
+    if x.dim() != 2 or not x.is_contiguous() or hi.shape != x.shape:
+        raise capi.McanError("rowmask_cast: x must be contiguous 2-D and hi of the same shape")
+    if lo is not None:
+        _req2d(lo, _BF16, "rowmask_cast lo")
+        if lo.stride(0) != hi.stride(0):
+            raise capi.McanError("rowmask_cast: lo must share hi's leading dimension")
+    if mask is not None:
+        _req(mask, torch.uint8, "rowmask_cast mask")
+        if mask.numel() != x.shape[0] or not mask.is_contiguous():
+            raise capi.McanError("rowmask_cast: mask must be contiguous uint8 [rows]")
+    capi.check(lib.mcan_rowmask_cast(x.data_ptr(), x.shape[0], x.shape[1], hi.data_ptr(), _ptr(lo), hi.stride(0),
+                                     _ptr(mask), _stream()), "mcan_rowmask_cast")
+
+
+_head_ws = {}
+
+
+def _head_workspace(device):
+    ws = _head_ws.get(device)
+    if ws is None:
+        ws = _head_ws[device] = torch.zeros(1032, dtype=_F32, device=device)
+    return ws
+
+
+def sigmoid_bce_fwd(logits, probs, target=None, loss=None):
+    """probs = sigmoid(logits); with target and loss: loss[()] = BCELoss(reduction='sum')(probs, target)."""
+    lib = capi.load()
+    _req2d(logits, _F32, "sigmoid_bce logits")
+    _req(probs, _F32, "sigmoid_bce probs")
+    rows, cols = logits.shape
+    if probs.shape != (rows, cols) or not probs.is_contiguous():
+        raise capi.McanError("sigmoid_bce: probs must be contiguous [rows, cols]")
+    ws = None
+    if target is not None:
+        _req(target, _F32, "sigmoid_bce target")
+        if target.shape != (rows, cols) or not target.is_contiguous():
+            raise capi.McanError("sigmoid_bce: target must be contiguous [rows, cols]")
+    if loss is not None:
+        _req(loss, _F32, "sigmoid_bce loss")
+        ws = _head_workspace(logits.device)
+    capi.check(lib.mcan_sigmoid_bce_fwd(logits.data_ptr(), logits.stride(0), _ptr(target), rows, cols, probs.data_ptr(),
+                                        _ptr(loss), _ptr(ws), _stream()), "mcan_sigmoid_bce_fwd")
+
+
+def sigmoid_bce_bwd(probs, dz, *, target=None, gout=None, gscale=None, dbias=None):
+    """dz (bf16 [rows, cols] view of a padded buffer) = gradient w.r.t. the logits; see include/mcan_b200.h."""
+    lib = capi.load()
+    _req(probs, _F32, "sigmoid_bce probs")
+    _req2d(dz, _BF16, "sigmoid_bce dz")
+    rows, cols = probs.shape
+    for t, nm in ((target, "target"), (gout, "gout")):
+        if t is not None:
+            _req(t, _F32, "sigmoid_bce " + nm)
+            if t.shape != (rows, cols) or not t.is_contiguous():
+                raise capi.McanError("sigmoid_bce: %s must be contiguous [rows, cols]" % nm)
+    if gscale is not None:
+        _req(gscale, _F32, "sigmoid_bce gscale")
+    if dbias is not None:
+        _req(dbias, _F32, "sigmoid_bce dbias")
+    capi.check(lib.mcan_sigmoid_bce_bwd(probs.data_ptr(), _ptr(target), _ptr(gout), _ptr(gscale), rows, cols,
+                                        dz.data_ptr(), dz.stride(0), _ptr(dbias), _stream()), "mcan_sigmoid_bce_bwd")
+
+
 def layernorm_bwd(dy, x, mean, sigma, a2, eps, *, dx_f32=None, dx_bf16=None, dropout_p=0.0, seed=0,
                   da2=None, db2=None, dbias=None):
     lib = capi.load()

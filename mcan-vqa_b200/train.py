@@ -55,6 +55,7 @@ class Trainer(object):
             self.opt = torch.optim.AdamW(params, lr=self.lr_t if use_graph else 0.0, weight_decay=1e-4,
                                          fused=True, capturable=use_graph)
         self.loss_fn = torch.nn.BCELoss(reduction="sum")
+        self.fused_loss = hasattr(self.net, "forward_with_loss") and os.environ.get("MCAN_FUSED_LOSS", "1") != "0"
         self.sync = dp.attach(self.net, overlap=True) if data_parallel else None
         # data parallel + fused optimiser: update bucket by bucket as the all-reduces finish
         self.bucketed = self.sync is not None and self.sync.world > 1 and isinstance(self.opt, FusedAdamW)
@@ -90,8 +91,10 @@ class Trainer(object):
         self.opt.zero_grad(set_to_none=True)
         if self.use_graph:
             self._advance_seed()
-        probs = self.net(img, ques)[0]
-        loss = self.loss_fn(probs, ans)
+        if self.fused_loss:
+            loss = self.net.forward_with_loss(img, ques, ans)[0]     # sigmoid + BCE(sum) as kernels of the library
+        else:
+            loss = self.loss_fn(self.net(img, ques)[0], ans)
         if self.early is not None:
             self.early.begin()
         loss.backward()

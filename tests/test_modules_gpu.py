@@ -375,3 +375,38 @@ def test_fused_gemm_layernorm_path_matches_unfused_chain():
         # two bf16 paths against each other: the documented weight-gradient tolerance (6e-2 rel-L2);
         # (linear_k biases have a mathematically zero gradient: pure rounding noise, compared on the global scale)
         assert err < 6e-2 * g.norm().item() + 1e-5 * total, (n, err, g.norm().item())
+
+
+@pytest.mark.parametrize("model", ["small", "large"])
+def test_fused_head_loss_matches_forward_plus_torch_bce(model):
+    """forward_with_loss (sigmoid + BCE(sum) as library kernels, exec.py:178 fused into the head) against the reference
+    loop's spelling: loss_fn(net(v, q)[0], ans) with torch's BCELoss -- same loss, same probabilities, same gradients;
+    and the image mask computed in the cast pass equals make_mask (net.py:135-137)."""
+    from core.model.net import Net
+    cfgd = orc.SMALL if model == "small" else orc.LARGE
+    cfg = orc.Cfg(dropout_rate=0.0, **cfgd)
+    token_size, answer_size, B = 500, 3129, 8
+    sd = orc.synth_state_dict(cfg, token_size, answer_size, seed=3)
+    v, q, ans = orc.synth_batch(cfg, B, 100, 14, token_size, answer_size, seed=99, ragged="random")
+    v, q, ans = v.cuda(), q.cuda(), ans.cuda()
+    res = {}
+    for fused in (False, True):
+        net = _load_params(Net(cfg, None, token_size, answer_size), sd).train()
+        if fused:
+            loss, probs = net.forward_with_loss(v, q, ans)
+        else:
+            out = net(v, q)
+            probs = out[0]
+            assert torch.equal(out[2], net.make_mask(v))                       # v_mask from the kernel == reference rule
+            assert out[2].dtype == torch.bool and out[2].shape == (B, 1, 1, 100)
+            loss = torch.nn.BCELoss(reduction="sum")(probs, ans)
+        (loss * 0.5).backward()
+        torch.cuda.synchronize()
+        res[fused] = (loss.item(), probs.detach().clone(), {n: p.grad.clone() for n, p in net.named_parameters()})
+    assert abs(res[True][0] - res[False][0]) <= 1e-5 * abs(res[False][0])
+    # (not bit-equal: the 896-row split-K GEMMs of a training forward accumulate with fp32 atomics)
+    assert (res[True][1] - res[False][1]).abs().max().item() < 1e-5
+    total = max(g.norm().item() for g in res[False][2].values())
+    for n, g in res[False][2].items():
+        err = (res[True][2][n] - g).norm().item()
+        assert err <= 1e-2 * g.norm().item() + 1e-6 * total, (n, err, g.norm().item())

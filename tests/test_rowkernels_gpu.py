@@ -273,3 +273,103 @@ def test_attention_fwd_split_precision(batch, heads, sq, sk, d):
     got = _heads(out, batch, sq, heads, d).double() + _heads(out_lo, batch, sq, heads, d).double()
     err = (got - ref).abs().max().item() / ref.abs().max().item()
     assert err < 5e-5, err
+
+
+# ---- the two ends of the path: zero-row mask + cast, LayerNorm of a sum, sigmoid + BCE(sum) ----------------
+@pytest.mark.parametrize("rows,cols", [(6400, 2048), (300, 2048), (37, 300), (5, 7), (64, 1026)])
+def test_rowmask_cast(rows, cols):
+    """reference net.py:135-137: mask = (sum(|x|, -1) == 0); the same pass writes the bf16 operand (hi, lo)."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows * 7 + cols)
+    x = torch.randn(rows, cols, generator=g)
+    zero_rows = torch.rand(rows, generator=g) < 0.3
+    x[zero_rows] = 0.0
+    x[0] = 0.0
+    x[0, cols - 1] = 1e-30 if rows > 1 else 0.0          # a single tiny entry: NOT a padded row
+    if rows > 2:
+        x[2] = 0.0
+        x[2, 0] = -0.0                                    # negative zero is zero
+    x = x.cuda()
+    ld = (cols + 7) // 8 * 8
+    hi = torch.zeros(rows, ld, device="cuda", dtype=torch.bfloat16)[:, :cols]
+    lo = torch.zeros(rows, ld, device="cuda", dtype=torch.bfloat16)[:, :cols]
+    mask = torch.full((rows,), 7, device="cuda", dtype=torch.uint8)
+    ops.rowmask_cast(x, hi, lo, mask)
+    torch.cuda.synchronize()
+    ref_mask = (x.abs().sum(-1) == 0)
+    assert torch.equal(mask.bool(), ref_mask)
+    assert torch.equal(hi, x.to(torch.bfloat16))
+    assert torch.equal(lo, (x - hi.float()).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("rows,h", [(64, 1024), (64, 2048), (3, 512)])
+def test_layernorm_of_a_sum(rows, h):
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows + h)
+    x = torch.randn(rows, h, generator=g).cuda()
+    x2 = (torch.randn(rows, h, generator=g) * 3).cuda()
+    a = (torch.rand(h, generator=g) + 0.5).cuda()
+    b = torch.randn(h, generator=g).cuda()
+    s = torch.empty(rows, h, device="cuda")
+    y32 = torch.empty(rows, h, device="cuda")
+    ybf = torch.empty(rows, h, device="cuda", dtype=torch.bfloat16)
+    mean = torch.empty(rows, device="cuda")
+    sigma = torch.empty(rows, device="cuda")
+    ops.layernorm_add_fwd(x, x2, a, b, 1e-6, s_out=s, y_f32=y32, y_bf16=ybf, mean=mean, sigma=sigma)
+    torch.cuda.synchronize()
+    assert torch.equal(s, x + x2)
+    ref = _ln_ref((x + x2).double(), a.double(), b.double())
+    assert (y32 - ref.float()).abs().max() < 3e-5
+    assert torch.equal(ybf, y32.to(torch.bfloat16))
+    assert (sigma - (x + x2).double().std(-1).float()).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("rows,cols", [(64, 3129), (8, 3129), (64, 100), (1, 5), (300, 777)])
+def test_sigmoid_bce_sum_fwd_bwd(rows, cols):
+    """reference net.py:129 (sigmoid) + exec.py:67,178 (BCELoss(reduction='sum')) and their autograd backward."""
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows * 31 + cols)
+    ld = (cols + 3) // 4 * 4
+    z = (torch.randn(rows, cols, generator=g) * 4)
+    z[0, 0] = 60.0          # saturated: p == 1, log(1 - p) clamps at -100
+    z[-1, -1] = -120.0      # p == 0 (denormal underflow), log p clamps at -100
+    t = torch.rand(rows, cols, generator=g)
+    t[torch.rand(rows, cols, generator=g) < 0.8] = 0.0
+    zbuf = torch.zeros(rows, ld, device="cuda")
+    zbuf[:, :cols] = z.cuda()
+    logits = zbuf[:, :cols]
+    tc = t.cuda()
+    probs = torch.empty(rows, cols, device="cuda")
+    loss = torch.full((), -1.0, device="cuda")
+    for _ in range(2):      # twice: the ticket in the workspace must be left ready for the next call
+        ops.sigmoid_bce_fwd(logits, probs, tc, loss)
+    zr = z.cuda().requires_grad_(True)
+    pr = torch.sigmoid(zr)
+    lr = torch.nn.BCELoss(reduction="sum")(pr, tc)
+    (lr * 0.37).backward()
+    torch.cuda.synchronize()
+    assert (probs - pr.detach()).abs().max() < 2e-7
+    ref64 = torch.nn.BCELoss(reduction="sum")(torch.sigmoid(z.double()).float().double(), t.double())
+    assert abs(loss.item() - lr.item()) <= 2e-6 * abs(lr.item()) + 1e-4, (loss.item(), lr.item(), ref64.item())
+    ldz = (cols + 7) // 8 * 8
+    dz = torch.full((rows, ldz), 3.0, device="cuda", dtype=torch.bfloat16)
+    dbias = torch.zeros(cols, device="cuda")
+    gs = torch.full((), 0.37, device="cuda")
+    ops.sigmoid_bce_bwd(probs, dz[:, :cols], target=tc, gscale=gs, dbias=dbias)
+    torch.cuda.synchronize()
+    assert torch.equal(dz[:, cols:], torch.zeros_like(dz[:, cols:]))
+    ref = zr.grad
+    assert (dz[:, :cols].float() - ref).abs().max() <= 2 ** -8 * ref.abs().max() + 1e-6
+    assert (dbias - dz[:, :cols].float().sum(0)).abs().max() < 1e-4 * max(1.0, dz.float().abs().max().item()) * rows ** 0.5
+    # plain sigmoid backward of an element-wise gradient (the reference loop: torch's BCELoss on forward()'s probs)
+    gout = torch.randn(rows, cols, generator=g).cuda()
+    zr.grad = None
+    (torch.sigmoid(zr) * gout).sum().backward()
+    ops.sigmoid_bce_bwd(probs, dz[:, :cols], gout=gout)
+    torch.cuda.synchronize()
+    assert (dz[:, :cols].float() - zr.grad).abs().max() <= 2 ** -8 * zr.grad.abs().max() + 1e-6
+    # probabilities only (no target, no loss)
+    probs2 = torch.empty_like(probs)
+    ops.sigmoid_bce_fwd(logits, probs2)
+    torch.cuda.synchronize()
+    assert torch.equal(probs, probs2)
