@@ -235,7 +235,8 @@ int mcan_layernorm_bwd(const float* dy, const float* x, const float* mean, const
  * Input hmid = dropout(relu(x W1^T + b1)) comes from mcan_gemm (bf16 [batch*s, mlp]).
  *   logit[b,s,g] = hmid[b,s,:] . w2[g,:] + b2[g];  masked_fill(mask, -1e9)
  *   att_w = softmax over s;  pooled[b, g*h : (g+1)*h] = sum_s att_w[b,s,g] * x[b,s,:]
- * pooled is written as fp32 and bf16 (operand of linear_merge).  One CTA per sample.
+ * pooled is written as fp32 (the backward reads it) and bf16 (operand of linear_merge).  Grid = (slices, batch):
+ * a sample is worked on by up to 8 CTAs (column slices of the pooled sums) so that a batch of 64 fills 148 SMs.
  * hmid_lo (optional): low-order bf16 half of hmid (split precision).
  */
 int mcan_attflat_pool_fwd(const void* hmid, const void* hmid_lo, const float* w2, const float* b2,
@@ -243,13 +244,13 @@ int mcan_attflat_pool_fwd(const void* hmid, const void* hmid_lo, const float* w2
                           int32_t mlp, int32_t glimpses, float* att_w, float* pooled_f32,
                           void* pooled_bf16, void* stream);
 
-/* backward: dpooled fp32 [batch, g*h] ->
+/* backward: dpooled fp32 [batch, g*h], pooled = the forward's fp32 output ->
  *   dx[b,s,:]  = sum_g att_w[b,s,g] * dpooled[b,g,:]                       (fp32, overwritten)
  *   dlogit     = softmax backward of d att_w[b,s,g] = dpooled[b,g,:] . x[b,s,:]; 0 where masked
  *   dhmid      = bf16( (hmid > 0) * gate_scale * sum_g dlogit[.,g] * w2[g,:] )  (through ReLU+dropout)
  *   dw2 += dlogit^T hmid, db2 += sum dlogit                                 (fp32 atomics)
  */
-int mcan_attflat_pool_bwd(const float* dpooled, const void* hmid, const float* w2,
+int mcan_attflat_pool_bwd(const float* dpooled, const float* pooled, const void* hmid, const float* w2,
                           const uint8_t* mask, const float* x, const float* att_w, int32_t batch,
                           int32_t s, int32_t h, int32_t mlp, int32_t glimpses, float gate_scale,
                           float* dx, void* dhmid, float* dw2, float* db2, void* stream);

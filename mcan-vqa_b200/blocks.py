@@ -860,16 +860,16 @@ def attflat_fwd(rt, af, x, B, S, mask):
     w2 = af.mlp.linear.weight.detach()
     b2 = af.mlp.linear.bias.detach()
     out = _empty(B, lpm.n, _F32, dev)
+    p32 = _empty(B, G * H, _F32, dev)          # fp32 pooled sums: the backward's softmax term is dpooled . pooled
     if rt.split:
-        p32 = _empty(B, G * H, _F32, dev)
         ops.attflat_pool_fwd(hmid, w2, b2, mask, x.f32, batch=B, s=S, h=H, mlp=M, glimpses=G, att_w=att_w,
                              pooled_f32=p32, hmid_lo=hlo)
         _mm(rt, act_from_f32(p32, True), lpm, 0, 1, out_f32=out)
     else:
         ops.attflat_pool_fwd(hmid, w2, b2, mask, x.f32, batch=B, s=S, h=H, mlp=M, glimpses=G, att_w=att_w,
-                             pooled_bf16=pooled)
+                             pooled_f32=p32, pooled_bf16=pooled)
         ops.gemm(pooled, lpm.w, bias=lpm.b, out_f32=out)
-    c.hmid, c.att_w, c.pooled = hmid, att_w, pooled
+    c.hmid, c.att_w, c.pooled, c.pooled32 = hmid, att_w, pooled, p32
     return out, att_w, c
 
 
@@ -889,7 +889,7 @@ def attflat_bwd(rt, af, c, dout, need_dx=True):
     dx = _empty(B * S, H, _F32, dev)
     dh = _empty(B * S, M, _BF16, dev)
     gw2 = rt.zeros(G * M + G, dev)
-    ops.attflat_pool_bwd(dpooled, c.hmid, af.mlp.linear.weight.detach(), c.mask, c.x.f32, c.att_w, batch=B,
+    ops.attflat_pool_bwd(dpooled, c.pooled32, c.hmid, af.mlp.linear.weight.detach(), c.mask, c.x.f32, c.att_w, batch=B,
                          s=S, h=H, mlp=M, glimpses=G, gate_scale=1.0 / (1.0 - c.p_mid) if c.p_mid > 0 else 1.0,
                          dx=dx, dhmid=dh, dw2=gw2[: G * M], db2=gw2[G * M:])
     ops.colsum(dh, g1.b)

@@ -151,7 +151,7 @@ SYMBOLS = {
     "mcan_attflat_pool_fwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                              c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                              c_void_p, c_void_p]),
-    "mcan_attflat_pool_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    "mcan_attflat_pool_bwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                              c_int32, c_int32, c_int32, c_int32, c_int32, c_float,
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcan_cast_bf16": (ctypes.c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),

@@ -83,8 +83,15 @@ class GradSync(object):
         # gradients take 1.98 ms as one call (712 GB/s bus bandwidth, NVLS) but 3.37 ms as 13 per-layer
         # calls of 62 MB -- per-call ramp-up dominates below ~100 MB.
         self.bucket_bytes = int(float(os.environ.get("MCAN_DP_BUCKET_MB", "192")) * 1e6)
+        # The encoder half of the backward pass is a chain of latency-bound kernels on 896 rows: all-reduces issued
+        # there cost the GEMMs nothing, so buckets are cut smaller (one encoder layer), which leaves only the image
+        # projection, LSTM and embedding gradients for the exposed last exchange after the backward pass.
+        self.enc_bucket_bytes = int(float(os.environ.get("MCAN_DP_ENC_BUCKET_MB", "40")) * 1e6)
         self.acc = []
+        self.acc_pairs = []     # (parameter, gradient tensor) of everything in `acc`, for the bucket-wise optimiser
+        self.ready_pairs = []
         self.acc_bytes = 0
+        self.early = None       # optim.EarlyStep: updates the parameters of finished buckets next to the encoder backward
         self.compress = os.environ.get("MCAN_DP_COMPRESS", "")      # "" (fp32 exchange) | "bf16"
         self.launches = 0
         self.hooks = []
@@ -102,40 +109,47 @@ class GradSync(object):
     # -- overlap mode ---------------------------------------------------------------------
     def _param_ready(self, p):
         self.ready.append(p.grad)
+        self.ready_pairs.append((p, p.grad))
         self._ensure_final_callback()
 
     def on_bufs(self, bufs, grads=None, kind=None):
-        """Called inside MCA_ED.backward with the flat fp32 gradient buffers of one layer."""
+        """Called inside MCA_ED.backward with the flat fp32 gradient buffers of one layer (and, for the bucket-wise
+        optimiser, the {parameter: gradient view} map of that layer; kind = "dec" | "kv" | "enc")."""
         self.acc += self.ready + list(bufs)
-        self.ready = []
+        self.acc_pairs += self.ready_pairs + (list(grads.items()) if grads else [])
+        self.ready, self.ready_pairs = [], []
         self.acc_bytes = sum(t.numel() * t.element_size() for t in self.acc)
-        if self.acc_bytes >= self.bucket_bytes:
+        if self.acc_bytes >= (self.bucket_bytes if kind in (None, "dec") else min(self.bucket_bytes, self.enc_bucket_bytes)):
             self._flush_acc()
         self._ensure_final_callback()
+        if self.early is not None:
+            self.early.on_dp_layer(self, kind)
 
     def _flush_acc(self):
         if self.acc:
-            self._launch(self.acc)
-            self.acc, self.acc_bytes = [], 0
+            self._launch(self.acc, self.acc_pairs)
+            self.acc, self.acc_pairs, self.acc_bytes = [], [], 0
 
     def _flush_ready(self):
         # end of backward: whatever is still waiting goes out as the last bucket
         self.acc += self.ready
-        self.ready = []
+        self.acc_pairs += self.ready_pairs
+        self.ready, self.ready_pairs = [], []
         self._flush_acc()
 
-    def _launch(self, tensors):
+    def _launch(self, tensors, pairs=None):
         if self.world == 1 or not tensors:
             return
+        pairs = list(pairs) if pairs else []
         if self.compress == "bf16" and all(t.dtype == torch.float32 and t.is_contiguous() for t in tensors):
-            self.pending.append((_CompressedWork(tensors, self.group), list(tensors)))
+            self.pending.append((_CompressedWork(tensors, self.group), list(tensors), pairs))
             self.launches += 1
             return
         works = _all_reduce_sum_async(tensors, self.group)
         if len(works) == len(tensors):      # one handle per tensor (backends without coalescing)
-            self.pending.extend((w, [t]) for w, t in zip(works, tensors))
+            self.pending.extend((w, [t], pairs if i == len(works) - 1 else []) for i, (w, t) in enumerate(zip(works, tensors)))
         else:
-            self.pending.extend((w, tensors) for w in works)
+            self.pending.extend((w, tensors, pairs) for w in works)
         self.launches += 1
 
     def _ensure_final_callback(self):
@@ -155,12 +169,12 @@ class GradSync(object):
                                "(grad_accu_steps == 1); use dp.attach(model, overlap=False) for gradient accumulation")
         if self.defer_wait:
             return            # the optimiser consumes the buckets one by one (take_buckets)
-        for w, _ in self.pending:
-            w.wait()          # current stream waits for the NCCL stream; no host sync
+        for entry in self.pending:
+            entry[0].wait()   # current stream waits for the NCCL stream; no host sync
         self.pending = []
 
     def take_buckets(self):
-        """[(work, tensors)] of this backward in launch order; the caller waits on each work before
+        """[(work, tensors, [(parameter, gradient)])] of this backward in launch order; the caller waits on each work before
         it touches that bucket's gradients (FusedAdamW.step_buckets: the parameter update of the
         first buckets overlaps the all-reduce of the last ones)."""
         out, self.pending = self.pending, []

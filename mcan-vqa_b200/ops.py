@@ -404,11 +404,12 @@ def attflat_pool_fwd(hmid, w2, b2, mask, x, *, batch, s, h, mlp, glimpses, att_w
                "mcan_attflat_pool_fwd")
 
 
-def attflat_pool_bwd(dpooled, hmid, w2, mask, x, att_w, *, batch, s, h, mlp, glimpses, gate_scale, dx,
+def attflat_pool_bwd(dpooled, pooled, hmid, w2, mask, x, att_w, *, batch, s, h, mlp, glimpses, gate_scale, dx,
                      dhmid, dw2=None, db2=None):
     lib = capi.load()
     _req(dpooled, _F32, "attflat dpooled")
-    capi.check(lib.mcan_attflat_pool_bwd(dpooled.data_ptr(), hmid.data_ptr(), w2.data_ptr(), _ptr(mask),
+    _req(pooled, _F32, "attflat pooled")
+    capi.check(lib.mcan_attflat_pool_bwd(dpooled.data_ptr(), pooled.data_ptr(), hmid.data_ptr(), w2.data_ptr(), _ptr(mask),
                                          x.data_ptr(), att_w.data_ptr(), batch, s, h, mlp, glimpses,
                                          float(gate_scale), dx.data_ptr(), dhmid.data_ptr(), _ptr(dw2),
                                          _ptr(db2), _stream()), "mcan_attflat_pool_bwd")

@@ -184,7 +184,10 @@ class FusedAdamW(object):
         overlaps the all-reduce of the late ones (encoder, LSTM, embedding) instead of waiting behind
         them.  Every gradient must belong to some bucket."""
         remaining = self._begin_step()
-        for work, tensors in buckets:
+        for entry in buckets:
+            work, tensors = entry[0], entry[1]
+            if len(entry) > 3 and entry[3]:
+                continue      # already waited for and applied next to the encoder backward (EarlyStep.on_dp_layer)
             work.wait()       # the current stream waits for this all-reduce; no host sync
             spans = [(t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()) for t in tensors]
             mine, rest = [], []
@@ -196,6 +199,9 @@ class FusedAdamW(object):
         if remaining:
             raise capi.McanError("FusedAdamW.step_buckets: %d gradients were not part of any all-reduce bucket"
                                  % len(remaining))
+        if self._early_done is not None:
+            self._early_done = None
+            _early.join()
         self.epoch += 1
         return None
 
@@ -269,6 +275,8 @@ class EarlyStep(object):
         self.opt._prepare()
         self.opt._early_done = set()
         self.waiting = []
+        self.dp_done = 0
+        self.forked = False
 
     def on_layer(self, bufs, grads=None, kind="enc"):
         if grads is None or self.opt._early_done is None:
@@ -291,6 +299,37 @@ class EarlyStep(object):
         for i, _ in self.waiting:
             self.opt._early_done.add(id(self.opt.params[i]))
         self.waiting = []
+
+    def on_dp_layer(self, sync, kind):
+        """Data parallel (called by dp.GradSync.on_bufs after every layer): once the encoder chain has started, every
+        bucket whose all-reduce has been launched is applied on the side stream as soon as that all-reduce finishes
+        -- the update of the decoder layers no longer waits for the end of the backward pass."""
+        if kind == "dec" or self.opt._early_done is None:
+            return
+        todo = [k for k in range(self.dp_done, len(sync.pending)) if len(sync.pending[k]) == 3]
+        if not todo:
+            return
+        if not self.forked:
+            self.side.wait_stream(torch.cuda.current_stream())     # lr / step scalars of this step
+            self.forked = True
+        with torch.cuda.stream(self.side):
+            for k in todo:
+                work, tensors, pairs = sync.pending[k]
+                active = []
+                for prm, g in pairs:
+                    i = self.opt._index.get(id(prm))
+                    if i is None or g is None or g.dtype != _F32 or not g.is_contiguous():
+                        active = None
+                        break
+                    active.append((i, g))
+                if active is None:
+                    continue          # left to step_buckets
+                work.wait()           # the side stream waits for this all-reduce
+                self.opt._launch(sorted(active, key=lambda t: t[0]), short_ctas=True)
+                for i, _ in active:
+                    self.opt._early_done.add(id(self.opt.params[i]))
+                sync.pending[k] = (work, tensors, pairs, True)
+        self.dp_done = len(sync.pending)
 
     def join(self):
         torch.cuda.current_stream().wait_stream(self.side)

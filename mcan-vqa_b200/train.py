@@ -67,6 +67,11 @@ class Trainer(object):
                 and os.environ.get("MCAN_EARLY_STEP", "1") != "0"):
             self.early = EarlyStep(self.opt)
             _optim.set_early(self.early)
+        elif self.bucketed and os.environ.get("MCAN_EARLY_STEP", "1") != "0":
+            # data parallel: finished buckets are applied next to the encoder backward as their all-reduces complete
+            self.early = EarlyStep(self.opt)
+            _optim.set_early(self.early)
+            self.sync.early = self.early
         # kernels of the step run on a HIGH-priority stream so that they win SMs from the overlapped update
         self.main_stream = torch.cuda.Stream(device=device, priority=-1)
         self.graph = None

@@ -95,7 +95,7 @@ def _worker(rank, world, port, mode, out):
         buckets = sync.take_buckets()
         assert len(buckets) >= 2 and sync.pending == []
         seen = set()
-        for work, tensors in buckets:
+        for work, tensors, _pairs in buckets:
             work.wait()
             for t in tensors:
                 lo, hi = t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()

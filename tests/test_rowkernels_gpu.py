@@ -186,7 +186,9 @@ def test_attention_dropout_matches_host_hash():
         assert err < 3e-2 * max(1.0, rf.abs().max().item())
 
 
-@pytest.mark.parametrize("batch,s,h,mlp,glimpses", [(8, 100, 512, 512, 1), (4, 14, 1024, 512, 1), (3, 60, 512, 512, 2), (2, 100, 512, 256, 3)])
+@pytest.mark.parametrize("batch,s,h,mlp,glimpses", [(8, 100, 512, 512, 1), (4, 14, 1024, 512, 1), (3, 60, 512, 512, 2), (2, 100, 512, 256, 3),
+                                                    (64, 100, 1024, 512, 1), (64, 14, 1024, 512, 1), (1, 100, 2048, 512, 2),
+                                                    (5, 3, 40, 16, 5), (300, 100, 512, 512, 1), (2, 1, 8, 8, 1)])
 def test_attflat_pool_fwd_bwd(batch, s, h, mlp, glimpses):
     ops = _ops()
     g = torch.Generator().manual_seed(batch * 7 + s)
@@ -218,7 +220,7 @@ def test_attflat_pool_fwd_bwd(batch, s, h, mlp, glimpses):
     dx = torch.empty(batch * s, h, device="cuda")
     dh = torch.empty(batch * s, mlp, device="cuda", dtype=torch.bfloat16)
     dw2 = torch.zeros(glimpses, mlp, device="cuda"); db2 = torch.zeros(glimpses, device="cuda")
-    ops.attflat_pool_bwd(dpooled, hmid, w2.detach(), mu8, x.detach(), att_w, batch=batch, s=s, h=h, mlp=mlp,
+    ops.attflat_pool_bwd(dpooled, p32, hmid, w2.detach(), mu8, x.detach(), att_w, batch=batch, s=s, h=h, mlp=mlp,
                          glimpses=glimpses, gate_scale=1.0, dx=dx, dhmid=dh, dw2=dw2, db2=db2)
     torch.cuda.synchronize()
     assert (dx - x.grad).abs().max() < 1e-4 * max(1.0, x.grad.abs().max().item())
