@@ -83,10 +83,11 @@ class GradSync(object):
         # gradients take 1.98 ms as one call (712 GB/s bus bandwidth, NVLS) but 3.37 ms as 13 per-layer
         # calls of 62 MB -- per-call ramp-up dominates below ~100 MB.
         self.bucket_bytes = int(float(os.environ.get("MCAN_DP_BUCKET_MB", "192")) * 1e6)
-        # The encoder half of the backward pass is a chain of latency-bound kernels on 896 rows: all-reduces issued
-        # there cost the GEMMs nothing, so buckets are cut smaller (one encoder layer), which leaves only the image
-        # projection, LSTM and embedding gradients for the exposed last exchange after the backward pass.
-        self.enc_bucket_bytes = int(float(os.environ.get("MCAN_DP_ENC_BUCKET_MB", "40")) * 1e6)
+        # Bucket threshold while the encoder half of the backward pass runs (MCAN_DP_ENC_BUCKET_MB).  Measured at
+        # 2 x B200, MCAN-large: 40 MB (one all-reduce per encoder layer, a smaller exposed last exchange) 9.04 ms/step,
+        # 192 MB 8.93 ms/step -- every extra NCCL launch pins SMs the persistent GEMMs of the chain want, so the
+        # same threshold is used throughout.
+        self.enc_bucket_bytes = int(float(os.environ.get("MCAN_DP_ENC_BUCKET_MB", "192")) * 1e6)
         self.acc = []
         self.acc_pairs = []     # (parameter, gradient tensor) of everything in `acc`, for the bucket-wise optimiser
         self.ready_pairs = []
@@ -116,7 +117,9 @@ class GradSync(object):
         """Called inside MCA_ED.backward with the flat fp32 gradient buffers of one layer (and, for the bucket-wise
         optimiser, the {parameter: gradient view} map of that layer; kind = "dec" | "kv" | "enc")."""
         self.acc += self.ready + list(bufs)
-        self.acc_pairs += self.ready_pairs + (list(grads.items()) if grads else [])
+        # (fresh view objects: holding the layer's own gradient tensors would raise their reference count and make
+        #  autograd's AccumulateGrad CLONE them into .grad instead of adopting the arena views being reduced in place)
+        self.acc_pairs += self.ready_pairs + ([(p, g.detach()) for p, g in grads.items() if g is not None] if grads else [])
         self.ready, self.ready_pairs = [], []
         self.acc_bytes = sum(t.numel() * t.element_size() for t in self.acc)
         if self.acc_bytes >= (self.bucket_bytes if kind in (None, "dec") else min(self.bucket_bytes, self.enc_bucket_bytes)):

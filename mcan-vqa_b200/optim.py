@@ -288,7 +288,7 @@ class EarlyStep(object):
                 continue
             if g.dtype != _F32 or not g.is_contiguous():
                 continue
-            pairs.append((i, g))
+            pairs.append((i, g.detach()))      # a fresh view: never keep autograd's own gradient tensor alive (see dp.on_bufs)
         self.waiting += pairs
         if kind == "dec":
             return          # the decoder backward saturates the GPU by itself: hold the update back
