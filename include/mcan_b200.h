@@ -123,6 +123,30 @@ typedef struct mcan_gemm_args {
 
 int mcan_gemm(const mcan_gemm_args* args);
 
+/* Grouped weight-gradient GEMM: up to MCAN_MAX_GEMM_GROUPS independent problems that share the contraction length k,
+ *   out_g[M_g, N_g] += A_g^T B_g,   A_g = bf16 [k, M_g] (lda), B_g = bf16 [k, N_g] (ldb), out_g fp32 (ldo),
+ * as ONE persistent launch (the wgrads dW = dY^T X of one MCAN layer: mca.py:33-61, net_utils.py:26,45 backward).
+ * Same arithmetic as one mcan_gemm(a_layout=1, b_layout=1, accumulate=1) per group: fp32 atomics into out_g, which
+ * the caller zero-initialises.  split_k: 0 = choose automatically. */
+#define MCAN_MAX_GEMM_GROUPS 8
+typedef struct mcan_gemm_group {
+    const void* a;
+    const void* b;
+    int64_t m, n, lda, ldb;
+    float* out;
+    int64_t ldo;
+} mcan_gemm_group;
+
+typedef struct mcan_gemm_grouped_args {
+    mcan_gemm_group g[MCAN_MAX_GEMM_GROUPS];
+    int32_t num_groups;
+    int32_t split_k;
+    int64_t k;
+    void* stream;
+} mcan_gemm_grouped_args;
+
+int mcan_gemm_grouped(const mcan_gemm_grouped_args* args);
+
 /* -- G2: GEMM with residual add + MCAN LayerNorm fused into the epilogue ----------------------------
  * Replaces, for the sub-layer outputs of SA / SGA (mca.py:119-125, 152-162), the chain
  *   GEMM[+bias, dropout, +resid] -> s -> LayerNorm(s) (net_utils.py:56-60):

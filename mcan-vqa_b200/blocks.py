@@ -82,6 +82,7 @@ class Runtime(object):
         self.arena_off = 0
         self.arena_mark = 0
         self.deferred = None   # list of (fn, args, kwargs) while weight-gradient work is being deferred
+        self.group = None      # list of (dy, x, out) weight-gradient GEMMs of the layer being back-propagated
 
     def wgrad(self, fn, *args, **kw):
         """Weight-gradient work (wgrad GEMMs, bias column sums): nothing downstream in the backward
@@ -90,6 +91,37 @@ class Runtime(object):
             self.deferred.append((fn, args, kw))
         else:
             fn(*args, **kw)
+
+    def wgrad_gemm(self, dy, x, out):
+        """out[M,N] (fp32, zero-initialised) += dy[K,M]^T x[K,N] -- a weight gradient.  While a layer's backward is
+        collecting (begin_group), the GEMM is queued and launched together with the layer's other weight gradients
+        as one grouped kernel (end_group)."""
+        if self.deferred is not None:
+            self.deferred.append((ops.gemm, (dy, x), dict(a_layout=1, b_layout=1, out_f32=out, accumulate=True)))
+        elif self.group is not None:
+            self.group.append((dy, x, out))
+        else:
+            ops.gemm(dy, x, a_layout=1, b_layout=1, out_f32=out, accumulate=True)
+
+    def begin_group(self):
+        if GROUP_WGRADS and self.deferred is None:
+            self.group = []
+
+    def end_group(self):
+        """Launches the queued weight-gradient GEMMs: one grouped launch per contraction length (<= 8 problems each)."""
+        todo, self.group = self.group, None
+        if not todo:
+            return
+        by_k = {}
+        for item in todo:
+            by_k.setdefault(item[0].shape[0], []).append(item)
+        for items in by_k.values():
+            for i in range(0, len(items), ops.capi.MAX_GROUPS):
+                chunk = items[i:i + ops.capi.MAX_GROUPS]
+                if len(chunk) == 1:
+                    ops.gemm(chunk[0][0], chunk[0][1], a_layout=1, b_layout=1, out_f32=chunk[0][2], accumulate=True)
+                else:
+                    ops.gemm_grouped(chunk)
 
     def use_arena(self, numel, device):
         """One memset instead of one per gradient tensor; contiguous per-layer slices for dp.py."""
@@ -151,6 +183,13 @@ def _mm(rt, a, lp, i0, i1, out_bf16=None, out_lo=None, **kw):
         ops.gemm([a.bf, a.bf, a.lo], [w, wl, w], bias=b, out_bf16=out_bf16, out_lo=out_lo, **kw)
     else:
         ops.gemm(a.bf, w, bias=b, out_bf16=out_bf16, **kw)
+
+
+# The weight-gradient GEMMs of one SA / SGA layer feed nothing in the backward chain: they are queued while the layer's
+# chain is enqueued and run as ONE grouped launch per contraction length (mcan_gemm_grouped).  Alone, each of them
+# pays the fixed ~8-10 us of a launch and fills the 74 CTA pairs only partly (1024 x 1024 x 6400: 16 tiles; the
+# 896-row encoder wgrads: 12-20 us for 2-7 GFLOP each); together their tiles form full waves.  MCAN_GROUP_WGRADS=0: off.
+GROUP_WGRADS = os.environ.get("MCAN_GROUP_WGRADS", "1") != "0"
 
 
 # Short-M GEMMs with a long contraction (the 896-row question side: FFN2 forward, the dgrads of
@@ -535,7 +574,7 @@ def att_bwd(rt, mh, c, dout, norm=None, dkv=None, need_dx=True):
         ds_f32, ds_bf, da2, db2 = ln_bwd(rt, norm, dout, c.s, c.mean, c.sigma, p=rt.p, seed=c.seed_out, dbias=gm.b)
         grads[norm.a_2], grads[norm.b_2] = da2, db2
     # merge linear: wgrad + dgrad
-    rt.wgrad(ops.gemm, ds_bf, c.att, a_layout=1, b_layout=1, out_f32=gm.w, accumulate=True)
+    rt.wgrad_gemm(ds_bf, c.att, gm.w)
     datt = _empty(M, H, _BF16, dev)
     ops.gemm(ds_bf, c.lpm.w, b_layout=1, out_bf16=datt)
     (wm, bm), = gm.per_param()
@@ -559,12 +598,12 @@ def att_bwd(rt, mh, c, dout, norm=None, dkv=None, need_dx=True):
     dx = None
     if c.mode == "self":
         rt.wgrad(ops.colsum, dqkv, g.b)
-        rt.wgrad(ops.gemm, dqkv, c.x_bf, a_layout=1, b_layout=1, out_f32=g.w, accumulate=True)
+        rt.wgrad_gemm(dqkv, c.x_bf, g.w)
         if need_dx:
             dx = _resid_gemm(dqkv, lp.w, M, H, 3 * H, dev, b_layout=1, resid=ds_f32)
     else:
         rt.wgrad(ops.colsum, dq, g.rows_b(0, 1))
-        rt.wgrad(ops.gemm, dq, c.x_bf, a_layout=1, b_layout=1, out_f32=g.rows_w(0, 1), accumulate=True)
+        rt.wgrad_gemm(dq, c.x_bf, g.rows_w(0, 1))
         if need_dx:
             dx = _empty(M, H, _F32, dev)
             ops.gemm(dq, lp.rows(0, 1)[0], b_layout=1, resid=ds_f32, out_f32=dx)
@@ -573,15 +612,15 @@ def att_bwd(rt, mh, c, dout, norm=None, dkv=None, need_dx=True):
             if hasattr(c, "v_bf"):
                 rt.wgrad(ops.colsum, dk, g.rows_b(1, 2))
                 rt.wgrad(ops.colsum, dv, g.rows_b(2, 3))
-                rt.wgrad(ops.gemm, dk, c.kv_bf, a_layout=1, b_layout=1, out_f32=g.rows_w(1, 2), accumulate=True)
-                rt.wgrad(ops.gemm, dv, c.v_bf, a_layout=1, b_layout=1, out_f32=g.rows_w(2, 3), accumulate=True)
+                rt.wgrad_gemm(dk, c.kv_bf, g.rows_w(1, 2))
+                rt.wgrad_gemm(dv, c.v_bf, g.rows_w(2, 3))
                 dkv_src = _empty(Mk, H, _F32, dev)
                 dv_src = _empty(Mk, H, _F32, dev)
                 ops.gemm(dk, lp.rows(1, 2)[0], b_layout=1, out_f32=dkv_src)
                 ops.gemm(dv, lp.rows(2, 3)[0], b_layout=1, out_f32=dv_src)
             else:
                 rt.wgrad(ops.colsum, dkvb, g.rows_b(1, 3))
-                rt.wgrad(ops.gemm, dkvb, c.kv_bf, a_layout=1, b_layout=1, out_f32=g.rows_w(1, 3), accumulate=True)
+                rt.wgrad_gemm(dkvb, c.kv_bf, g.rows_w(1, 3))
                 dkv_src = _empty(Mk, H, _F32, dev)
                 ops.gemm(dkvb, lp.rows(1, 3)[0], b_layout=1, out_f32=dkv_src)
     # (in "kv" mode the K/V weights belong to the caller's batched projection)
@@ -649,7 +688,7 @@ def mlp_bwd(rt, mlp, c, dout, norm=None, need_dx=True):
     else:
         ds_f32, ds_bf, da2, db2 = ln_bwd(rt, norm, dout, c.s, c.mean, c.sigma, p=rt.p, seed=c.seed_out, dbias=g2.b)
         grads[norm.a_2], grads[norm.b_2] = da2, db2
-    rt.wgrad(ops.gemm, ds_bf, c.hmid, a_layout=1, b_layout=1, out_f32=g2.w, accumulate=True)
+    rt.wgrad_gemm(ds_bf, c.hmid, g2.w)
     dh = _empty(M, c.lp1.n, _BF16, dev)
     gate = c.hmid if (mlp.fc.use_relu or c.p_mid > 0) else None
     gate_scale = 1.0 / (1.0 - c.p_mid) if c.p_mid > 0 else 1.0
@@ -657,7 +696,7 @@ def mlp_bwd(rt, mlp, c, dout, norm=None, need_dx=True):
         raise ops.capi.McanError("dropout without ReLU in FC is not supported by the fused gate")
     # the FFN1 bias gradient (column sums of dh) comes out of the same epilogue, from the fp32 values
     ops.gemm(ds_bf, c.lp2.w, b_layout=1, gate=gate, gate_scale=gate_scale, out_bf16=dh, colsum=g1.b)
-    rt.wgrad(ops.gemm, dh, c.x_bf, a_layout=1, b_layout=1, out_f32=g1.w, accumulate=True)
+    rt.wgrad_gemm(dh, c.x_bf, g1.w)
     dx = None
     if need_dx:
         dx = _resid_gemm(dh, c.lp1.w, M, c.lp1.k, c.lp1.n, dev, b_layout=1, resid=ds_f32)
@@ -679,8 +718,10 @@ def sa_fwd(rt, sa, x, B, S, mask):
 
 def sa_bwd(rt, sa, ctx, dz):
     c1, c2 = ctx
+    rt.begin_group()
     dy, grads = mlp_bwd(rt, sa.ffn.mlp, c2, dz, norm=sa.norm2)
     dx, _, _, g1 = att_bwd(rt, sa.mhatt, c1, dy, norm=sa.norm1)
+    rt.end_group()
     grads.update(g1)
     return dx, grads
 
@@ -698,9 +739,11 @@ def sga_fwd(rt, sga, x, y, B, Sx, Sy, x_mask, y_mask, kv=None):
 
 def sga_bwd(rt, sga, ctx, dz, dkv=None):
     c1, c2, c3 = ctx
+    rt.begin_group()
     db, grads = mlp_bwd(rt, sga.ffn.mlp, c3, dz, norm=sga.norm3)
     da, dy, _, g2 = att_bwd(rt, sga.mhatt2, c2, db, norm=sga.norm2, dkv=dkv)
     dx, _, _, g1 = att_bwd(rt, sga.mhatt1, c1, da, norm=sga.norm1)
+    rt.end_group()
     grads.update(g2)
     grads.update(g1)
     return dx, dy, grads
@@ -800,7 +843,7 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
         if overlap:
             rt.deferred = []
         rt.wgrad(ops.colsum, dkv_all, gkv.b)
-        rt.wgrad(ops.gemm, dkv_all, ctx.xenc_bf, a_layout=1, b_layout=1, out_f32=gkv.w, accumulate=True)
+        rt.wgrad_gemm(dkv_all, ctx.xenc_bf, gkv.w)
         dx = _resid_gemm(dkv_all, ctx.lpkv.w, B * Sx, H, 2 * H * L, dev, b_layout=1, resid=dx_out)
         gk = {}
         for (w, b), (gw, gb) in zip(ctx.lpkv.pairs, gkv.per_param()):
@@ -975,10 +1018,16 @@ def head_fwd(rt, norm, lp, x, x2, target):
         ops.layernorm_add_fwd(x, x2, norm.a_2.detach(), norm.b_2.detach(), norm.eps, s_out=c.s, y_f32=y32,
                               y_bf16=ybf, y_lo=ylo, mean=c.mean, sigma=c.sigma)
     ldo = (lp.n + 3) // 4 * 4
-    logits = torch.empty((B, ldo), dtype=_F32, device=dev)[:, :lp.n]
     if rt.split:
+        logits = torch.empty((B, ldo), dtype=_F32, device=dev)[:, :lp.n]
         ops.gemm([ybf, ybf, ylo], [lp.w, lp.w_lo, lp.w], bias=lp.b, out_f32=logits)
+    elif torch.is_grad_enabled() and SPLITK_MIN_K > 0 and B <= SPLITK_MAX_ROWS and lp.k >= SPLITK_MIN_K:
+        # 64 rows x 3129 answers x K 2048 is one wave of 49 tiles that stream the 12.8 MB weight through 49 SMs
+        # (45 us); split-K puts every SM on it (training only, like every split-K GEMM: fp32 atomics)
+        logits = torch.zeros((B, ldo), dtype=_F32, device=dev)[:, :lp.n]
+        ops.gemm(ybf, lp.w, bias=lp.b, out_f32=logits, accumulate=True)
     else:
+        logits = torch.empty((B, ldo), dtype=_F32, device=dev)[:, :lp.n]
         ops.gemm(ybf, lp.w, bias=lp.b, out_f32=logits)
     probs = _empty(B, lp.n, _F32, dev)
     loss = torch.empty((), dtype=_F32, device=dev) if target is not None else None
@@ -999,8 +1048,7 @@ def head_bwd(rt, norm, c, g_a, g_probs, g_loss):
     else:
         ops.sigmoid_bce_bwd(c.probs, dz, gout=g_probs.contiguous(), dbias=g.b)
     ops.gemm(dz, c.abf, a_layout=1, b_layout=1, out_f32=g.w, accumulate=True)
-    da = _empty(B, lp.k, _F32, dev)
-    ops.gemm(dz, lp.w, b_layout=1, out_f32=da, resid=g_a)
+    da = _resid_gemm(dz, lp.w, B, lp.k, lp.n, dev, b_layout=1, resid=g_a)
     ds, _, da2, db2 = ln_bwd(rt, norm, da, c.s, c.mean, c.sigma, want_bf=False)
     (gw, gb), = g.per_param()
     return ds, gw, gb, da2, db2

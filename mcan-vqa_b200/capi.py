@@ -55,6 +55,32 @@ class GemmArgs(ctypes.Structure):
     ]
 
 
+MAX_GROUPS = 8
+
+
+class GemmGroup(ctypes.Structure):
+    _fields_ = [
+        ("a", c_void_p),
+        ("b", c_void_p),
+        ("m", c_int64),
+        ("n", c_int64),
+        ("lda", c_int64),
+        ("ldb", c_int64),
+        ("out", c_void_p),
+        ("ldo", c_int64),
+    ]
+
+
+class GemmGroupedArgs(ctypes.Structure):
+    _fields_ = [
+        ("g", GemmGroup * MAX_GROUPS),
+        ("num_groups", c_int32),
+        ("split_k", c_int32),
+        ("k", c_int64),
+        ("stream", c_void_p),
+    ]
+
+
 class GemmLnArgs(ctypes.Structure):
     _fields_ = [
         ("a", c_void_p),
@@ -134,6 +160,7 @@ SYMBOLS = {
     "mcan_set_pdl": (ctypes.c_int, [ctypes.c_int]),
     "mcan_gemm": (ctypes.c_int, [ctypes.POINTER(GemmArgs)]),
     "mcan_gemm_ln": (ctypes.c_int, [ctypes.POINTER(GemmLnArgs)]),
+    "mcan_gemm_grouped": (ctypes.c_int, [ctypes.POINTER(GemmGroupedArgs)]),
     "mcan_attn_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs)]),
     "mcan_attn_bwd": (ctypes.c_int, [ctypes.POINTER(AttnBwdArgs)]),
     "mcan_layernorm_fwd": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float,

@@ -52,10 +52,25 @@ constexpr int kProducerWarp = kEpilogueWarps + 1;
 constexpr int kMmaWarp = kEpilogueWarps + 2;
 constexpr int kGemmThreads = 32 * (kMmaWarp + 1);
 
+// Grouped launch (mcan_gemm_grouped): up to kMaxGroups independent problems D_g[M_g,N_g] += A_g B_g^T that share
+// K and the operand layouts run as ONE persistent grid -- the weight-gradient GEMMs of one layer, which feed
+// nothing in the backward chain.  Every launch costs ~8-10 us of fixed overhead (launch, prologue, pipeline
+// fill, last epilogue) and each small problem alone fills only part of the machine; together their tiles
+// form full waves.  Work unit -> (group, tile of the group, K split); operand maps and output per group.
+constexpr int kMaxGroups = 8;
+constexpr int kMaxTmaps = kMaxGroups > MCAN_MAX_GEMM_SEGMENTS ? kMaxGroups : MCAN_MAX_GEMM_SEGMENTS;
+struct GroupDesc {
+    int m, n, n_tiles, tile_start;     // tile_start: index of the group's first tile in the launch
+    float* out;
+    long long ldo;
+};
+
 struct alignas(64) GemmParams {
-    CUtensorMap tma_a[MCAN_MAX_GEMM_SEGMENTS];
-    CUtensorMap tma_b[MCAN_MAX_GEMM_SEGMENTS];
+    CUtensorMap tma_a[kMaxTmaps];      // per segment, or per group in a grouped launch
+    CUtensorMap tma_b[kMaxTmaps];
     CUtensorMap tma_b_half[MCAN_MAX_GEMM_SEGMENTS];   // K-major B, box of half as many rows (tail splitting)
+    int num_groups;                    // 0: one problem
+    GroupDesc grp[kMaxGroups];
     int num_seg;
     int m, n, k;
     int m_tiles, n_tiles, splits, kblocks;
@@ -132,9 +147,16 @@ __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
 // (ncu: stall_no_inst on every line).
 constexpr int kChunkN = 64;
 
+// the problem a work unit belongs to (a grouped launch has one per group)
+struct EpiDims {
+    int m, n;
+    float* out_f32;
+    long long ldo_f32;
+};
+
 // generic (slow) path for chunks that cross the N boundary or odd N: per element, rolled loops, on the
 // UNtransposed fragment
-__device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const float* v, int lane,
+__device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const EpiDims& d, const float* v, int lane,
                                                   long long row0, int col0, uint32_t drop_seed, bool addends) {
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll 1
@@ -142,18 +164,18 @@ __device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const flo
         const int k = i >> 2, h = (i >> 1) & 1, c = i & 1;
         const long long row = row0 + g + 8 * h;
         const int col = col0 + 8 * k + 2 * t + c;
-        if (row >= p.m || col >= p.n) continue;
+        if (row >= d.m || col >= d.n) continue;
         float x = v[i];
         if (p.bias != nullptr && addends) x += __ldg(p.bias + col);
         if (p.relu) x = fmaxf(x, 0.f);
         if (p.drop_thr != 0)
-            x = dropout_u16((uint32_t)(row * (long long)p.n + col), drop_seed) >= p.drop_thr ? x * p.drop_scale : 0.f;
+            x = dropout_u16((uint32_t)(row * (long long)d.n + col), drop_seed) >= p.drop_thr ? x * p.drop_scale : 0.f;
         if (p.gate != nullptr) x = __bfloat162float(p.gate[row * p.ldg + col]) > 0.f ? x * p.gate_scale : 0.f;
         if (p.resid != nullptr && addends) x += p.resid[row * p.ldr + col];
         if (p.colsum != nullptr) atomicAdd(p.colsum + col, x);
-        if (p.out_f32 != nullptr) {
-            if (p.accumulate) atomicAdd(p.out_f32 + row * p.ldo_f32 + col, x);
-            else p.out_f32[row * p.ldo_f32 + col] = x;
+        if (d.out_f32 != nullptr) {
+            if (p.accumulate) atomicAdd(d.out_f32 + row * d.ldo_f32 + col, x);
+            else d.out_f32[row * d.ldo_f32 + col] = x;
         }
         if (p.out_bf16 != nullptr) {
             const bf16 hi = __float2bfloat16_rn(x);
@@ -170,14 +192,14 @@ struct EpiPrefetch {
     uint4 gt[4];      // [2h + q]: 8 bf16 of the gate operand
 };
 
-__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPrefetch& pf, int lane,
+__device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, const EpiDims& d, EpiPrefetch& pf, int lane,
                                                   long long row0, int col0) {
-    if (col0 + kChunkN > p.n || ((p.n & 1) && p.drop_thr != 0)) return;   // ragged chunks use the slow path
+    if (col0 + kChunkN > d.n || ((d.n & 1) && p.drop_thr != 0)) return;   // ragged chunks use the slow path
     const int g = lane >> 2, t = lane & 3;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const long long row = row0 + g + 8 * h;
-        if (row < p.m) {
+        if (row < d.m) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int col = col0 + 32 * q + 8 * t;
@@ -192,20 +214,20 @@ __device__ __forceinline__ void epilogue_prefetch(const GemmParams& p, EpiPrefet
 // with a fused LINEAR epilogue: out = resid + keep*scale*(sum_s acc_s + bias), every split scales
 // its partial sum, only split 0 contributes the addends; all through red.global.add).
 template <bool PF>
-__device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_t (&r)[32], int lane,
+__device__ __forceinline__ void epilogue_frag(const GemmParams& p, const EpiDims& d, const uint32_t (&r)[32], int lane,
                                               long long row0, int col0, uint32_t drop_seed,
                                               const EpiPrefetch& pf, bool addends, float (&cs)[16], bool cs_first,
                                               bool cs_flush) {
     const int g = lane >> 2, t = lane & 3;
     // (odd N: only the dropout pair index needs N even; every other access is addressed through the
     // 16-byte aligned leading dimensions)
-    if (col0 + kChunkN > p.n || ((p.n & 1) && p.drop_thr != 0)) {
+    if (col0 + kChunkN > d.n || ((d.n & 1) && p.drop_thr != 0)) {
         // only this copy has its address taken; v[] below must stay in registers (an escaping v[]
         // made the compiler mirror it to local memory after every pass: +15 us per epilogue stage)
         float tmp[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) tmp[i] = __uint_as_float(r[i]);
-        epilogue_frag_ragged(p, tmp, lane, row0, col0, drop_seed, addends);
+        epilogue_frag_ragged(p, d, tmp, lane, row0, col0, drop_seed, addends);
         return;
     }
     float v[32];
@@ -214,7 +236,7 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_
     quad_transpose(v, t);
     const int col = col0 + 8 * t;   // + 32q + e
     const long long rows[2] = {row0 + g, row0 + g + 8};
-    const bool ok[2] = {rows[0] < p.m, rows[1] < p.m};
+    const bool ok[2] = {rows[0] < d.m, rows[1] < d.m};
 
     if (p.bias != nullptr && addends) {
 #pragma unroll
@@ -239,7 +261,7 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_
         for (int h = 0; h < 2; ++h) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const uint32_t base = (uint32_t)(rows[h] * (long long)p.n + col + 32 * q) >> 1;   // pair index (n even)
+                const uint32_t base = (uint32_t)(rows[h] * (long long)d.n + col + 32 * q) >> 1;   // pair index (n even)
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
                     const uint32_t rnd = dropout_bits_pair(base + (e >> 1), drop_seed);
@@ -271,7 +293,7 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const uint32_
         float acc = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc += v[i];
-        if (acc == 123.456f && p.out_f32 != nullptr) p.out_f32[0] = acc;
+        if (acc == 123.456f && d.out_f32 != nullptr) d.out_f32[0] = acc;
         return;
     }
     if (p.colsum != nullptr) {
@@ -342,15 +364,15 @@ struct EpiPrefetchDirect {
     uint32_t gt[16];
 };
 
-__device__ __forceinline__ void epilogue_prefetch_direct(const GemmParams& p, EpiPrefetchDirect& pf, int lane,
+__device__ __forceinline__ void epilogue_prefetch_direct(const GemmParams& p, const EpiDims& d, EpiPrefetchDirect& pf, int lane,
                                                   long long row0, int col0) {
-    if (col0 + kChunkN > p.n || ((p.n & 1) && p.drop_thr != 0)) return;   // ragged chunks use the slow path
+    if (col0 + kChunkN > d.n || ((d.n & 1) && p.drop_thr != 0)) return;   // ragged chunks use the slow path
     const int g = lane >> 2, t = lane & 3;
     const int col = col0 + 2 * t;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const long long row = row0 + g + 8 * h;
-        if (row < p.m) {
+        if (row < d.m) {
             if (p.resid != nullptr) {
                 const float2* rp = reinterpret_cast<const float2*>(p.resid + row * p.ldr + col);
 #pragma unroll
@@ -369,19 +391,19 @@ __device__ __forceinline__ void epilogue_prefetch_direct(const GemmParams& p, Ep
 // with a fused LINEAR epilogue: out = resid + keep*scale*(sum_s acc_s + bias), every split scales
 // its partial sum, only split 0 contributes the addends; all through red.global.add).
 template <bool PF>
-__device__ __forceinline__ void epilogue_frag_direct(const GemmParams& p, const uint32_t (&r)[32], int lane,
+__device__ __forceinline__ void epilogue_frag_direct(const GemmParams& p, const EpiDims& d, const uint32_t (&r)[32], int lane,
                                               long long row0, int col0, uint32_t drop_seed,
                                               const EpiPrefetchDirect& pf, bool addends) {
     const int g = lane >> 2, t = lane & 3;
     // (odd N: only the dropout pair index needs N even; every other access is addressed through the
     // 16-byte aligned leading dimensions)
-    if (col0 + kChunkN > p.n || ((p.n & 1) && p.drop_thr != 0)) {
+    if (col0 + kChunkN > d.n || ((d.n & 1) && p.drop_thr != 0)) {
         // only this copy has its address taken; v[] below must stay in registers (an escaping v[]
         // made the compiler mirror it to local memory after every pass: +15 us per epilogue stage)
         float tmp[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) tmp[i] = __uint_as_float(r[i]);
-        epilogue_frag_ragged(p, tmp, lane, row0, col0, drop_seed, addends);
+        epilogue_frag_ragged(p, d, tmp, lane, row0, col0, drop_seed, addends);
         return;
     }
     float v[32];
@@ -389,7 +411,7 @@ __device__ __forceinline__ void epilogue_frag_direct(const GemmParams& p, const 
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
     const int col = col0 + 2 * t;   // + 8k
     const long long rows[2] = {row0 + g, row0 + g + 8};
-    const bool ok[2] = {rows[0] < p.m, rows[1] < p.m};
+    const bool ok[2] = {rows[0] < d.m, rows[1] < d.m};
 
     if (p.bias != nullptr && addends) {
 #pragma unroll
@@ -407,7 +429,7 @@ __device__ __forceinline__ void epilogue_frag_direct(const GemmParams& p, const 
         const float sc = p.drop_scale;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-            const uint32_t base = (uint32_t)(rows[h] * (long long)p.n + col) >> 1;   // pair index (n even)
+            const uint32_t base = (uint32_t)(rows[h] * (long long)d.n + col) >> 1;   // pair index (n even)
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const uint32_t rnd = dropout_bits_pair(base + 4 * k, drop_seed);
@@ -446,14 +468,14 @@ __device__ __forceinline__ void epilogue_frag_direct(const GemmParams& p, const 
         float acc = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; ++i) acc += v[i];
-        if (acc == 123.456f && p.out_f32 != nullptr) p.out_f32[0] = acc;
+        if (acc == 123.456f && d.out_f32 != nullptr) d.out_f32[0] = acc;
         return;
     }
-    if (p.out_f32 != nullptr) {
+    if (d.out_f32 != nullptr) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (ok[h]) {
-                float* o = p.out_f32 + rows[h] * p.ldo_f32 + col;
+                float* o = d.out_f32 + rows[h] * d.ldo_f32 + col;
                 if (p.accumulate) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) red_add_v2(o + 8 * k, v[4 * k + 2 * h], v[4 * k + 2 * h + 1]);
@@ -492,18 +514,18 @@ __device__ __forceinline__ void epilogue_frag_direct(const GemmParams& p, const 
 // operands are prefetched one fragment ahead (separate instantiation so that plain epilogues do
 // not carry the prefetch registers).
 template <int CG, bool PF, bool T8L>
-__device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int chunk_par,
+__device__ __forceinline__ void epilogue_tile(const GemmParams& p, const EpiDims& d, int lane, int chunk_par,
                                               long long row0, int n0, int width, uint32_t taddr,
                                               uint64_t* full_bar, uint64_t* empty_bar,
                                               uint32_t acc_phase, uint32_t drop_seed, uint32_t lead_rank,
                                               bool addends) {
     using Pref = typename std::conditional<T8L, EpiPrefetch, EpiPrefetchDirect>::type;
-    const int nchunks = min(width / kChunkN, (p.n - n0 + kChunkN - 1) / kChunkN);
+    const int nchunks = min(width / kChunkN, (d.n - n0 + kChunkN - 1) / kChunkN);
     const int last_c = ((nchunks - 1 - chunk_par) & ~1) + chunk_par;   // this warp's last chunk (< 0: none)
     Pref pf_next;
     if (PF && last_c >= 0) {   // operands of the first fragment, before waiting for the MMAs
-        if constexpr (T8L) epilogue_prefetch(p, pf_next, lane, row0, n0 + chunk_par * kChunkN);
-        else epilogue_prefetch_direct(p, pf_next, lane, row0, n0 + chunk_par * kChunkN);
+        if constexpr (T8L) epilogue_prefetch(p, d, pf_next, lane, row0, n0 + chunk_par * kChunkN);
+        else epilogue_prefetch_direct(p, d, pf_next, lane, row0, n0 + chunk_par * kChunkN);
     }
     mbar_wait(full_bar, acc_phase);
     tc_fence_after();
@@ -526,9 +548,9 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int
             if (PF) {
                 pf = pf_next;
                 const int nc = hb ? c + 2 : c, nhb = hb ^ 1;    // next fragment of this tile
-                if (nc < nchunks && row0 + nhb * 16 < p.m) {
-                    if constexpr (T8L) epilogue_prefetch(p, pf_next, lane, row0 + nhb * 16, n0 + nc * kChunkN);
-                    else epilogue_prefetch_direct(p, pf_next, lane, row0 + nhb * 16, n0 + nc * kChunkN);
+                if (nc < nchunks && row0 + nhb * 16 < d.m) {
+                    if constexpr (T8L) epilogue_prefetch(p, d, pf_next, lane, row0 + nhb * 16, n0 + nc * kChunkN);
+                    else epilogue_prefetch_direct(p, d, pf_next, lane, row0 + nhb * 16, n0 + nc * kChunkN);
                 }
             }
             tmem_ld_wait();
@@ -541,11 +563,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int
                     else mbar_arrive(empty_bar);
                 }
             }
-            if (row0 + hb * 16 < p.m) {
+            if (row0 + hb * 16 < d.m) {
                 if constexpr (T8L)
-                    epilogue_frag<PF>(p, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed, pf, addends, cs, hb == 0,
-                                      hb == 1 || row0 + 16 >= p.m);
-                else epilogue_frag_direct<PF>(p, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed, pf, addends);
+                    epilogue_frag<PF>(p, d, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed, pf, addends, cs, hb == 0,
+                                      hb == 1 || row0 + 16 >= d.m);
+                else epilogue_frag_direct<PF>(p, d, r, lane, row0 + hb * 16, n0 + c * kChunkN, drop_seed, pf, addends);
             }
         }
     }
@@ -557,10 +579,11 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, int lane, int
 // other pair: L2 -> shared-memory traffic per CTA drops from 32 KB to 24 KB per k-block, and that
 // traffic (not the tensor pipe) is what bounds this kernel.
 // work unit -> (output tile, K split, first column offset inside the tile, width in columns)
-struct UnitInfo { int tile, split, ncol, width; };
+struct UnitInfo { int tile, split, ncol, width, group, mt, nt; };    // (mt, nt): tile coordinates inside its problem
 template <int BLOCK_N>
 __device__ __forceinline__ UnitInfo decode_unit(const GemmParams& p, int unit, int tiles) {
     UnitInfo u;
+    u.group = 0;
     if (p.full_tiles >= tiles) {
         u.tile = unit % tiles;
         u.split = unit / tiles;
@@ -577,6 +600,17 @@ __device__ __forceinline__ UnitInfo decode_unit(const GemmParams& p, int unit, i
         u.split = 0;
         u.ncol = (r & 1) * (BLOCK_N / 2);
         u.width = BLOCK_N / 2;
+    }
+    if (p.num_groups > 0) {
+        int g = 0;
+        while (g + 1 < p.num_groups && u.tile >= p.grp[g + 1].tile_start) ++g;
+        const int local = u.tile - p.grp[g].tile_start;
+        u.group = g;
+        u.mt = local / p.grp[g].n_tiles;
+        u.nt = local - u.mt * p.grp[g].n_tiles;
+    } else {
+        u.mt = u.tile / p.n_tiles;
+        u.nt = u.tile - u.mt * p.n_tiles;
     }
     return u;
 }
@@ -625,7 +659,8 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
     const bool cl_leader = (crank == 0);                          // runs the dynamic tile scheduler
 
     if (warp == kProducerWarp && lane == 0) {
-        for (int s = 0; s < p.num_seg; ++s) {
+        const int nmaps = p.num_groups > 0 ? p.num_groups : p.num_seg;
+        for (int s = 0; s < nmaps; ++s) {
             prefetch_tmap(&p.tma_a[s]);
             prefetch_tmap(&p.tma_b[s]);
         }
@@ -703,19 +738,19 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             const int unit = next_unit();
             if (unit >= units) break;
             const UnitInfo ui = decode_unit<BLOCK_N>(p, unit, tiles);
-            const int tile = ui.tile, split = ui.split;
+            const int split = ui.split;
             const bool half = ui.width != BLOCK_N;          // half-width unit: this CTA stages kBRows / 2 rows of B
             const int brows = half ? kBRows / 2 : kBRows;
             const uint32_t stage_tx = Cfg::kABytes + (uint32_t)brows * BLOCK_K * 2;
-            const int m0 = (tile / p.n_tiles) * (BLOCK_M * CL) + (int)crank * BLOCK_M;
+            const int m0 = ui.mt * (BLOCK_M * CL) + (int)crank * BLOCK_M;
             // MC == 2: this CTA fetches rows [pair*64, pair*64+64) of its half of B for both pairs
-            const int n0 = (tile % p.n_tiles) * BLOCK_N + ui.ncol + (int)rank * brows + (MC == 2 ? (int)pair * (kBRows / 2) : 0);
+            const int n0 = ui.nt * BLOCK_N + ui.ncol + (int)rank * brows + (MC == 2 ? (int)pair * (kBRows / 2) : 0);
             const uint16_t mc_mask = (uint16_t)((1U << rank) | (1U << (CG + rank)));
             const int kb0 = (int)((long long)p.kblocks * split / p.splits);
             const int kb1 = (int)((long long)p.kblocks * (split + 1) / p.splits);
             for (int seg = 0; seg < p.num_seg; ++seg) {
-                const CUtensorMap* ta = &p.tma_a[seg];
-                const CUtensorMap* tb = (half && !B_MN) ? &p.tma_b_half[seg] : &p.tma_b[seg];
+                const CUtensorMap* ta = &p.tma_a[seg + ui.group];      // (a grouped launch has one segment)
+                const CUtensorMap* tb = (half && !B_MN) ? &p.tma_b_half[seg] : &p.tma_b[seg + ui.group];
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (p.debug & 2) {
@@ -856,12 +891,18 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
         while (unit < units) {
             const int unit_after = next_unit();     // published one tile ahead
             const UnitInfo ui = decode_unit<BLOCK_N>(p, unit, tiles);
-            const int tile = ui.tile;
-            const int m0 = (tile / p.n_tiles) * (BLOCK_M * CL) + (int)crank * BLOCK_M;
-            const int n0 = (tile % p.n_tiles) * BLOCK_N + ui.ncol;
+            const int m0 = ui.mt * (BLOCK_M * CL) + (int)crank * BLOCK_M;
+            const int n0 = ui.nt * BLOCK_N + ui.ncol;
             const long long row0 = m0 + quad * 32;
+            EpiDims d;
+            if (p.num_groups > 0) {
+                d.m = p.grp[ui.group].m; d.n = p.grp[ui.group].n;
+                d.out_f32 = p.grp[ui.group].out; d.ldo_f32 = p.grp[ui.group].ldo;
+            } else {
+                d.m = p.m; d.n = p.n; d.out_f32 = p.out_f32; d.ldo_f32 = p.ldo_f32;
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
-#define MCAN_EPI_TILE(PF, T8L) epilogue_tile<CG, PF, T8L>(p, lane, chunk_par, row0, n0, ui.width, taddr, &tmem_full_bar[acc], \
+#define MCAN_EPI_TILE(PF, T8L) epilogue_tile<CG, PF, T8L>(p, d, lane, chunk_par, row0, n0, ui.width, taddr, &tmem_full_bar[acc], \
                                                           &tmem_empty_bar[acc], acc_phase, drop_seed, lead_rank, ui.split == 0)
             if (EPI == 1) {
                 if (p.gate != nullptr) MCAN_EPI_TILE(true, true); else MCAN_EPI_TILE(false, true);
@@ -1295,3 +1336,59 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     set_last_error("mcan_gemm: no kernel for block_n=%d", block_n);
     return -1;
 }
+
+// Grouped weight-gradient launch: D_g[M_g,N_g] += A_g^T B_g for up to MCAN_MAX_GEMM_GROUPS problems that share K,
+// A_g = bf16 [K, M_g] and B_g = bf16 [K, N_g] read MN-major straight from the activation buffers (dW = dY^T X).
+extern "C" int mcan_gemm_grouped(const mcan_gemm_grouped_args* a) {
+    MCAN_REQUIRE(a != nullptr, "mcan_gemm_grouped: null args");
+    MCAN_REQUIRE(a->num_groups >= 1 && a->num_groups <= MCAN_MAX_GEMM_GROUPS && a->num_groups <= kMaxGroups,
+                 "mcan_gemm_grouped: num_groups=%d", a->num_groups);
+    MCAN_REQUIRE(a->k > 0 && a->k < (1LL << 31), "mcan_gemm_grouped: k=%lld", (long long)a->k);
+    const int sms = device_num_sms();
+    MCAN_REQUIRE(sms >= 2, "mcan_gemm_grouped: no CUDA device");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.num_seg = 1;
+    p.num_groups = a->num_groups;
+    p.k = (int)a->k;
+    p.kblocks = (int)((a->k + BLOCK_K - 1) / BLOCK_K);
+    int tiles = 0;
+    for (int g = 0; g < a->num_groups; ++g) {
+        const mcan_gemm_group& q = a->g[g];
+        MCAN_REQUIRE(q.a && q.b && q.out && q.m > 0 && q.n > 0 && q.m < (1LL << 31) && q.n < (1LL << 31) &&
+                         q.m * q.n < (1LL << 32),
+                     "mcan_gemm_grouped: bad group %d", g);
+        MCAN_REQUIRE(q.ldo % 4 == 0 && ((uintptr_t)q.out & 15) == 0, "mcan_gemm_grouped: out alignment (group %d)", g);
+        if (int rc = make_tmap_bf16(&p.tma_a[g], q.a, (uint64_t)q.m, (uint64_t)a->k, (uint64_t)q.lda, 64)) return rc;
+        if (int rc = make_tmap_bf16(&p.tma_b[g], q.b, (uint64_t)q.n, (uint64_t)a->k, (uint64_t)q.ldb, 64)) return rc;
+        p.grp[g].m = (int)q.m;
+        p.grp[g].n = (int)q.n;
+        p.grp[g].n_tiles = (int)((q.n + 255) / 256);
+        p.grp[g].tile_start = tiles;
+        p.grp[g].out = q.out;
+        p.grp[g].ldo = q.ldo;
+        tiles += (int)((q.m + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * p.grp[g].n_tiles;
+    }
+    p.m = p.grp[0].m;
+    p.n = p.grp[0].n;
+    p.out_f32 = p.grp[0].out;
+    p.ldo_f32 = p.grp[0].ldo;
+    p.m_tiles = tiles;
+    p.n_tiles = 1;
+    const int slots = sms / 2;
+    int splits = a->split_k > 0 ? a->split_k : pick_splits(tiles, p.kblocks, slots);
+    if (splits > p.kblocks) splits = p.kblocks;
+    p.splits = splits;
+    p.full_tiles = tiles;
+    p.units = tiles * splits;
+    p.drop_scale = 1.0f;
+    p.gate_scale = 1.0f;
+    p.accumulate = 1;
+    p.tile_counter = nullptr;
+    if (g_dynamic_schedule.load(std::memory_order_relaxed)) {
+        if (int rc = next_tile_counter(&p.tile_counter)) return rc;
+    }
+    { const char* d = getenv("MCAN_GEMM_DEBUG"); p.debug = d ? atoi(d) : 0; }
+    return launch_gemm<256, 1, 1, 2, 1, 0>(p, p.units, sms, reinterpret_cast<cudaStream_t>(a->stream));
+}
+

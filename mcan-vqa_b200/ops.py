@@ -195,6 +195,31 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, 
     capi.check(lib.mcan_gemm(ctypes.byref(args)), "mcan_gemm")
 
 
+def gemm_grouped(problems, split_k=0):
+    """problems = [(a bf16 [K, M_g], b bf16 [K, N_g], out fp32 [M_g, N_g])]: out_g += a_g^T b_g for every group in ONE
+    launch (the weight gradients dW = dY^T X of one layer); at most capi.MAX_GROUPS groups sharing K."""
+    lib = capi.load()
+    if not 1 <= len(problems) <= capi.MAX_GROUPS:
+        raise capi.McanError("gemm_grouped: 1..%d problems" % capi.MAX_GROUPS)
+    args = capi.GemmGroupedArgs()
+    k = problems[0][0].shape[0]
+    for i, (a, b, out) in enumerate(problems):
+        _req2d(a, _BF16, "gemm_grouped a")
+        _req2d(b, _BF16, "gemm_grouped b")
+        _req2d(out, _F32, "gemm_grouped out")
+        if a.shape[0] != k or b.shape[0] != k or out.shape != (a.shape[1], b.shape[1]):
+            raise capi.McanError("gemm_grouped: problem %d: shapes %s %s %s" % (i, tuple(a.shape), tuple(b.shape), tuple(out.shape)))
+        g = args.g[i]
+        g.a, g.b, g.out = a.data_ptr(), b.data_ptr(), out.data_ptr()
+        g.m, g.n = a.shape[1], b.shape[1]
+        g.lda, g.ldb, g.ldo = a.stride(0), b.stride(0), out.stride(0)
+    args.num_groups = len(problems)
+    args.split_k = int(split_k)
+    args.k = k
+    args.stream = _stream()
+    capi.check(lib.mcan_gemm_grouped(ctypes.byref(args)), "mcan_gemm_grouped")
+
+
 def gemm_ln(a, w, *, bias, resid, ln_a2, ln_b2, eps, dropout_p=0.0, seed=0, s_f32=None, y_f32=None, y_bf16=None,
             mean=None, sigma=None):
     """y = LayerNorm(resid + dropout(a w^T + bias)) in ONE kernel (see include/mcan_b200.h, mcan_gemm_ln).

@@ -388,3 +388,62 @@ def test_gemm_ln_large_mean_rows_are_stable():
     r = resid.double()
     ref = (r - r.mean(-1, keepdim=True)) / (r.std(-1, keepdim=True) + 1e-6)
     assert (y.double() - ref).abs().max().item() < 2e-2      # fp32 input quantisation of 1000 + 0.01 x is 6e-5 / 0.01
+
+
+@pytest.mark.parametrize("rows,shapes,split_k", [
+    (6400, [(1024, 1024), (3072, 1024), (1024, 1024), (1024, 1024), (4096, 1024), (1024, 4096)], 0),   # one decoder layer (large)
+    (896, [(1024, 4096), (4096, 1024), (3072, 1024), (1024, 1024)], 0),                               # one encoder layer (large)
+    (6400, [(512, 512), (1536, 512), (2048, 512), (512, 2048)], 0),                                   # small model
+    (896, [(512, 512), (1536, 512)], 3),
+    (1000, [(100, 300), (264, 72), (520, 1032)], 0),                                                  # ragged tiles
+    (72, [(3136, 2048), (256, 256)], 1),
+    (896, [(256, 256)] * 8, 0),                                                                        # the maximum group count
+])
+def test_gemm_grouped_wgrads(rows, shapes, split_k):
+    """mcan_gemm_grouped == one mcan_gemm(a_layout=1, b_layout=1, accumulate) per group: dW_g += dY_g^T X_g; strided
+    operand views (column slices of wider activation buffers) included."""
+    ops = _ops()
+    probs, refs = [], []
+    for i, (n, k) in enumerate(shapes):
+        wide_a = _rand((rows, (n + 64 + 7) // 8 * 8), 100 + i, 0.1)      # leading dimensions: multiples of 8 (TMA)
+        wide_b = _rand((rows, (k + 8 + 7) // 8 * 8), 200 + i)
+        dy, x = wide_a[:, 32:32 + n], wide_b[:, :k]
+        out = torch.full((n, k), 0.5, device="cuda")              # += : starts from a non-zero value
+        probs.append((dy, x, out))
+        refs.append(0.5 + dy.float().t() @ x.float())
+    ops.gemm_grouped(probs, split_k=split_k)
+    torch.cuda.synchronize()
+    for (dy, x, out), ref in zip(probs, refs):
+        _close(out, ref, 5e-5, "grouped wgrad %s" % (tuple(out.shape),))
+
+
+def test_layer_backward_with_grouped_wgrads_matches_individual_launches():
+    """blocks.GROUP_WGRADS: the same gradients whether a layer's wgrads run as one grouped launch or one launch each."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import mcan_oracle as orc
+    from core.model.mca import MCA_ED
+    from mcan_vqa_b200 import blocks, capi
+    cfg = orc.Cfg(dropout_rate=0.0, **dict(orc.SMALL, layer=2))
+    torch.manual_seed(5)
+    m = MCA_ED(cfg).cuda().train()
+    x = torch.randn(8, 14, 512, device="cuda")
+    y = torch.randn(8, 100, 512, device="cuda")
+    xm = torch.zeros(8, 1, 1, 14, dtype=torch.bool, device="cuda"); xm[:, :, :, 11:] = True
+    ym = (torch.rand(8, 1, 1, 100, device="cuda") < 0.2)
+    res = {}
+    saved = blocks.GROUP_WGRADS
+    try:
+        for grouped in (False, True):
+            blocks.GROUP_WGRADS = grouped
+            m.zero_grad(set_to_none=True)
+            c0 = capi.launch_count
+            xo, yo = m(x, y, xm, ym)
+            (xo.sum() + (yo * yo).sum()).backward()
+            torch.cuda.synchronize()
+            res[grouped] = ({n: p.grad.clone() for n, p in m.named_parameters()}, capi.launch_count - c0)
+    finally:
+        blocks.GROUP_WGRADS = saved
+    assert res[True][1] < res[False][1] - 8          # 2 x (4 - 1) + 2 x (6 - 1) launches fewer
+    for n, g in res[False][0].items():
+        assert (res[True][0][n] - g).abs().max().item() <= 1e-4 * (g.abs().max().item() + 1e-6), n
