@@ -6,7 +6,8 @@ evaluates, checkpoints and visualises unchanged.  The co-attention backbone (MCA
 AttFlat poolings, proj_norm and the two big projections (img_feat_linear, proj) run on the
 hand-written sm_100a kernels; so do the zero-row mask of the image features (computed in the pass that
 casts them to the GEMM operand) and the output head proj_norm -> proj -> sigmoid (-> BCE(sum) through
-`forward_with_loss`, what core/exec.py:178 computes with loss_fn).  Embedding + LSTM stay stock PyTorch.
+`forward_with_loss`, what core/exec.py:178 computes with loss_fn), and the question encoder (embedding + LSTM +
+token mask: csrc/lstm.cu; cuDNN only for hidden sizes the kernel does not cover and for fp32-grade inference).
 """
 import torch
 import torch.nn as nn
@@ -70,18 +71,33 @@ class _VQABase(nn.Module):
         self.proj_norm = LayerNorm(cfg_get(opt, "flat_out_size"))
         self.proj = TCLinear(cfg_get(opt, "flat_out_size"), answer_size)
 
+    def lp_lstm_ih(self):
+        if getattr(self, "_lp_ih", None) is None:
+            self._lp_ih = LinearParams([(self.lstm.weight_ih_l0, self.lstm.bias_ih_l0)])
+        return self._lp_ih
+
+    def lp_lstm_hh(self):
+        if getattr(self, "_lp_hh", None) is None:
+            self._lp_hh = LinearParams([(self.lstm.weight_hh_l0, self.lstm.bias_hh_l0)])
+        return self._lp_hh
+
     def all_lps(self):
         return (self.backbone.all_lps() + self.attflat_img.all_lps() + self.attflat_lang.all_lps() +
-                [self.img_feat_linear.lp(), self.proj.lp()])
+                [self.img_feat_linear.lp(), self.proj.lp(), self.lp_lstm_ih(), self.lp_lstm_hh()])
 
     def _features_impl(self, v, ques_ix):
-        q_mask = _make_mask(ques_ix.unsqueeze(2))
-        if _blocks.PRECISION == "fp32" and not torch.is_grad_enabled():
-            # fp32-grade inference: cuDNN's RNN GEMMs default to TF32 (1e-3); switch that off
-            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-                q, _ = self.lstm(self.embedding(ques_ix))
+        split = _blocks.PRECISION == "fp32" and not torch.is_grad_enabled()
+        if ques_ix.is_cuda and _blocks.lstm_supported(self.lstm, split):
+            # embedding + LSTM + make_mask(ques_ix) on the library's persistent LSTM kernels
+            q, q_mask = _ag.question_encoder(self, ques_ix)
         else:
-            q, _ = self.lstm(self.embedding(ques_ix))
+            q_mask = _make_mask(ques_ix.unsqueeze(2))
+            if split:
+                # fp32-grade inference: cuDNN's RNN GEMMs default to TF32 (1e-3); switch that off
+                with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                    q, _ = self.lstm(self.embedding(ques_ix))
+            else:
+                q, _ = self.lstm(self.embedding(ques_ix))
         v, v_mask = _ag.linear_mask(self.img_feat_linear, v)      # img_feat_linear + make_mask(v) in one pass
         q, v = self.backbone(q, v, q_mask, v_mask)
         lang, q_w = self.attflat_lang(q, q_mask)

@@ -126,8 +126,10 @@ int mcan_gemm(const mcan_gemm_args* args);
 /* Grouped weight-gradient GEMM: up to MCAN_MAX_GEMM_GROUPS independent problems that share the contraction length k,
  *   out_g[M_g, N_g] += A_g^T B_g,   A_g = bf16 [k, M_g] (lda), B_g = bf16 [k, N_g] (ldb), out_g fp32 (ldo),
  * as ONE persistent launch (the wgrads dW = dY^T X of one MCAN layer: mca.py:33-61, net_utils.py:26,45 backward).
- * Same arithmetic as one mcan_gemm(a_layout=1, b_layout=1, accumulate=1) per group: fp32 atomics into out_g, which
- * the caller zero-initialises.  split_k: 0 = choose automatically. */
+ * accumulate != 0: same arithmetic as one mcan_gemm(a_layout=1, b_layout=1, accumulate=1) per group -- fp32 atomics
+ * into out_g, which the caller zero-initialises; split_k: 0 = choose automatically.
+ * accumulate == 0: out_g = A_g^T B_g, plain stores by exactly one work unit per element (K is not split): the
+ * outputs need no initialisation -- no zero-fill pass and no read-modify-write of the gradients. */
 #define MCAN_MAX_GEMM_GROUPS 8
 typedef struct mcan_gemm_group {
     const void* a;
@@ -141,6 +143,7 @@ typedef struct mcan_gemm_grouped_args {
     mcan_gemm_group g[MCAN_MAX_GEMM_GROUPS];
     int32_t num_groups;
     int32_t split_k;
+    int32_t accumulate;
     int64_t k;
     void* stream;
 } mcan_gemm_grouped_args;
@@ -224,6 +227,11 @@ typedef struct mcan_attn_bwd_args {
     void* dk;
     void* dv;
     int64_t lddq, lddk, lddv;
+    /* optional fp32 [heads * head_dim] each: += column sums over all rows of dq / dk / dv as stored (the bias
+     * gradients of linear_q / linear_k / linear_v, mca.py:33-55), fp32 atomics on zero-initialised buffers */
+    float* dbq;
+    float* dbk;
+    float* dbv;
 } mcan_attn_bwd_args;
 
 int mcan_attn_bwd(const mcan_attn_bwd_args* args);
@@ -301,6 +309,46 @@ int mcan_sigmoid_bce_fwd(const float* logits, int64_t ld, const float* target, i
  * Exactly one of target / gout is given. */
 int mcan_sigmoid_bce_bwd(const float* probs, const float* target, const float* gout, const float* gscale_dev,
                          int32_t rows, int32_t cols, void* dz_bf16, int64_t ld, float* dbias, void* stream);
+
+/* -- question encoder (net.py:66-78, 96-104): embedding + single-layer LSTM ---------------------
+ * Row layout of every per-token buffer below: row(b, s) = b * (steps + 1) + s, one spare slot per sample
+ * (R = batch * (steps + 1) rows), so that hbuf[b, s] = h_{s-1} sits at the row of dA[b, s = t] and x[b, s = t] and the
+ * weight gradients dW_hh = dA^T hbuf, dW_ih = dA^T x are plain GEMMs over R rows.
+ *
+ * mcan_embed_gather: x[row(b, t), :embed] = bf16(table[tokens[b, t]]) (pad columns and slot `steps` zero);
+ *   mask[b * steps + t] = (tokens[b, t] == 0)  -- make_mask(ques_ix), net.py:99,135-137.  mask may be NULL.
+ * mcan_embed_scatter_add: dtable[tokens[b, t], :] += dx[row(b, t), :embed] (fp32 atomics, dtable zero-initialised). */
+int mcan_embed_gather(const int64_t* tokens, const float* table, int32_t vocab, int32_t embed, int32_t batch,
+                      int32_t steps, void* x_bf16, int32_t ldx, uint8_t* mask, void* stream);
+int mcan_embed_scatter_add(const int64_t* tokens, const float* dx, int32_t lddx, int32_t vocab, int32_t embed,
+                           int32_t batch, int32_t steps, float* dtable, void* stream);
+
+/* nn.LSTM(num_layers=1, batch_first=True), zero initial state, gate order (i, f, g, o), as ONE persistent kernel per
+ * direction of differentiation (all time steps; W_hh slices resident in registers; grid barrier between steps).
+ * forward : xw = x W_ih^T + b_ih (fp32 [R, 4H], from mcan_gemm) -> hbuf (bf16 [R, H], slot s = h_{s-1}), h_out (fp32
+ *           [batch * steps, H], row b * steps + t: the module output), and for training cbuf (fp32 [R, H]) and gates
+ *           (fp32 [R, 4H], activated) -- both NULL for inference.
+ * backward: dout (fp32 [batch * steps, H]) + gates, cbuf, w_hh -> da (bf16 [R, 4H]: gradients of the gate
+ *           pre-activations, slot `steps` zero), from which dW_ih, dW_hh, the bias gradients and dx follow as GEMMs.
+ * batch <= 64 per launch (the host splits larger batches); hidden in {128, 256, 512, 1024}; needs >= 128 SMs.
+ * barrier: 2 words of device memory, zero before the first launch (the kernels leave them zero). */
+typedef struct mcan_lstm_args {
+    const float* xw;
+    const void* w_hh;     /* bf16 [4H, H] */
+    const float* b_hh;    /* fp32 [4H] */
+    int32_t batch, steps, hidden;
+    void* hbuf;
+    float* h_out;
+    float* cbuf;
+    float* gates;
+    const float* dout;
+    void* da;
+    uint32_t* barrier;
+    void* stream;
+} mcan_lstm_args;
+
+int mcan_lstm_fwd(const mcan_lstm_args* args);
+int mcan_lstm_bwd(const mcan_lstm_args* args);
 
 /* -- small memory-bound helpers -------------------------------------------------------- */
 /* hi = bf16(x); lo (optional) = bf16(x - hi).  n elements. */

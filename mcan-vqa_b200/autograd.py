@@ -356,7 +356,7 @@ class _LinearRunner(_Runner):
         (x,) = acts
         lin = self.module
         self.shape = x.shape
-        lp = lin.lp().get(blocks._force(torch.is_grad_enabled()), self.rt.split)
+        lp = lin.lp().get(blocks._force(self.rt.grad), self.rt.split)
         out, self.c = blocks.linear_fwd(lp, _as_f32_2d(x, lp.k), self.rt.split)
         return out.contiguous().view(self.shape[:-1] + (lp.n,)) if out.stride(0) != lp.n else out.view(self.shape[:-1] + (lp.n,))
 
@@ -378,7 +378,7 @@ class _LinearMaskRunner(_LinearRunner):
         (x,) = acts
         lin = self.module
         self.shape = x.shape
-        lp = lin.lp().get(blocks._force(torch.is_grad_enabled()), self.rt.split)
+        lp = lin.lp().get(blocks._force(self.rt.grad), self.rt.split)
         x2 = _as_f32_2d(x, lp.k)
         mask = torch.empty(x2.shape[0], dtype=torch.uint8, device=x.device)
         out, self.c = blocks.linear_fwd(lp, x2, self.rt.split, mask_out=mask)
@@ -406,7 +406,7 @@ class _HeadRunner(_Runner):
     def forward(self, acts):
         x, x2, target = acts
         proj = self.module
-        lp = proj.lp().get(blocks._force(torch.is_grad_enabled()), self.rt.split)
+        lp = proj.lp().get(blocks._force(self.rt.grad), self.rt.split)
         self.shape = x.shape
         xs = _as_f32_2d(x, lp.k)
         x2s = _as_f32_2d(x2, lp.k) if x2 is not None else None
@@ -445,3 +445,39 @@ class _HeadRunner(_Runner):
 def head(norm, proj, x, x2=None, target=None):
     """-> (proj_feat, probs) or, with a target, (proj_feat, probs, BCE-sum loss)."""
     return _run(_HeadRunner(norm, proj), [x, x2, target])
+
+
+# ------------------------------------------------------------------------------------------
+class _QuestionEncoderRunner(_Runner):
+    """embedding -> LSTM (net.py:103-104) and make_mask(ques_ix) (net.py:99) on the library's kernels (csrc/lstm.cu)."""
+
+    def __init__(self, net):
+        lstm = net.lstm
+        _Runner.__init__(self, net, [net.embedding.weight, lstm.weight_ih_l0, lstm.weight_hh_l0, lstm.bias_ih_l0,
+                                     lstm.bias_hh_l0])
+
+    def forward(self, acts):
+        (tokens,) = acts
+        net = self.module
+        force = blocks._force(self.rt.grad)
+        lp_ih, lp_hh = net.lp_lstm_ih().get(force), net.lp_lstm_hh().get(force)
+        tok = tokens.detach().to(torch.int64).contiguous()
+        q, mask, self.c = blocks.qenc_fwd(self.rt, net.embedding.weight.detach(), lp_ih, lp_hh, tok, self.rt.grad)
+        self.non_differentiable = (mask,)
+        B, T = tok.shape
+        return q.view(B, T, lp_hh.k), mask
+
+    def backward(self, gouts, needs):
+        net = self.module
+        H = self.c.lp_hh.k
+        dq = _as_f32_2d(gouts[0], H)
+        dt, dwi, dbi, dwh, dbh = blocks.qenc_bwd(self.rt, self.c, dq, net.embedding.weight.shape[0])
+        lstm = net.lstm
+        return [None], {net.embedding.weight: dt, lstm.weight_ih_l0: dwi, lstm.bias_ih_l0: dbi, lstm.weight_hh_l0: dwh,
+                        lstm.bias_hh_l0: dbh}
+
+
+def question_encoder(net, ques_ix):
+    """-> (lstm(embedding(ques_ix)) fp32 [B, T, H], bool mask [B,1,1,T] of padding tokens)."""
+    q, u8 = _run(_QuestionEncoderRunner(net), [ques_ix])
+    return q, mask_from_u8(u8, ques_ix.shape[0], ques_ix.shape[1])

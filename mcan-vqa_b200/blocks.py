@@ -77,8 +77,14 @@ class Runtime(object):
         self.base = _mix32((torch.initial_seed() & 0xFFFFFFFF) ^ (_seed_counter[0] * 0x9E3779B9))
         self.n = 0
         self.bufs = []      # loose fp32 gradient buffers produced since the last drain (for dp.py)
-        self.split = (PRECISION == "fp32") and not torch.is_grad_enabled()
+        # (a Runtime is created by the module-level wrapper, OUTSIDE autograd.Function.forward, where grad mode is
+        #  always off: this is the caller's grad mode)
+        self.grad = torch.is_grad_enabled()
+        self.split = (PRECISION == "fp32") and not self.grad
         self.arena = None   # one zero-initialised flat buffer all gradients of a backward are carved from
+        self.arena_w = None  # uninitialised flat buffer for the weight gradients that grouped launches write
+        self.arena_w_off = 0
+        self.arena_w_mark = 0
         self.arena_off = 0
         self.arena_mark = 0
         self.deferred = None   # list of (fn, args, kwargs) while weight-gradient work is being deferred
@@ -99,7 +105,7 @@ class Runtime(object):
         if self.deferred is not None:
             self.deferred.append((ops.gemm, (dy, x), dict(a_layout=1, b_layout=1, out_f32=out, accumulate=True)))
         elif self.group is not None:
-            self.group.append((dy, x, out))
+            self.group.append((dy, x, out, self.in_store_arena(out)))
         else:
             ops.gemm(dy, x, a_layout=1, b_layout=1, out_f32=out, accumulate=True)
 
@@ -108,26 +114,46 @@ class Runtime(object):
             self.group = []
 
     def end_group(self):
-        """Launches the queued weight-gradient GEMMs: one grouped launch per contraction length (<= 8 problems each)."""
+        """Launches the queued weight-gradient GEMMs: one grouped launch per contraction length (<= 8 problems each).
+        Gradients that live in the store arena are WRITTEN (K not split), the others accumulated into zeroed memory."""
         todo, self.group = self.group, None
         if not todo:
             return
-        by_k = {}
-        for item in todo:
-            by_k.setdefault(item[0].shape[0], []).append(item)
-        for items in by_k.values():
+        by_key = {}
+        for dy, x, out, store in todo:
+            by_key.setdefault((dy.shape[0], store), []).append((dy, x, out))
+        for (_, store), items in by_key.items():
             for i in range(0, len(items), ops.capi.MAX_GROUPS):
                 chunk = items[i:i + ops.capi.MAX_GROUPS]
                 if len(chunk) == 1:
-                    ops.gemm(chunk[0][0], chunk[0][1], a_layout=1, b_layout=1, out_f32=chunk[0][2], accumulate=True)
+                    ops.gemm(chunk[0][0], chunk[0][1], a_layout=1, b_layout=1, out_f32=chunk[0][2], accumulate=not store)
                 else:
-                    ops.gemm_grouped(chunk)
+                    ops.gemm_grouped(chunk, accumulate=not store)
 
-    def use_arena(self, numel, device):
-        """One memset instead of one per gradient tensor; contiguous per-layer slices for dp.py."""
+    def in_store_arena(self, t):
+        a = self.arena_w
+        return a is not None and a.data_ptr() <= t.data_ptr() < a.data_ptr() + a.numel() * 4
+
+    def empty_w(self, n, device):
+        """Uninitialised storage for a weight gradient that a grouped launch will WRITE; None when not available
+        (no layer group open, arena exhausted): the caller then takes zeroed memory and accumulates."""
+        n4 = (n + 3) // 4 * 4
+        a = self.arena_w
+        if self.group is None or a is None or a.device != device or self.arena_w_off + n4 > a.numel():
+            return None
+        v = a[self.arena_w_off:self.arena_w_off + n]
+        self.arena_w_off += n4
+        return v
+
+    def use_arena(self, numel, device, store_numel=0):
+        """One memset instead of one per gradient tensor; contiguous per-layer slices for dp.py.  store_numel > 0:
+        that many elements are an UNINITIALISED second arena for the weight gradients grouped launches write."""
         self.arena = torch.zeros(numel, dtype=_F32, device=device)
         self.arena_off = 0
         self.arena_mark = 0
+        self.arena_w = torch.empty(store_numel, dtype=_F32, device=device) if (store_numel > 0 and STORE_WGRADS) else None
+        self.arena_w_off = 0
+        self.arena_w_mark = 0
 
     def zeros(self, n, device):
         n4 = (n + 3) // 4 * 4          # keep every carve-out 16-byte aligned
@@ -146,6 +172,9 @@ class Runtime(object):
         if self.arena is not None and self.arena_off > self.arena_mark:
             out.append(self.arena[self.arena_mark:self.arena_off])
             self.arena_mark = self.arena_off
+        if self.arena_w is not None and self.arena_w_off > self.arena_w_mark:
+            out.append(self.arena_w[self.arena_w_mark:self.arena_w_off])
+            self.arena_w_mark = self.arena_w_off
         return out
 
     def seed(self):
@@ -190,6 +219,16 @@ def _mm(rt, a, lp, i0, i1, out_bf16=None, out_lo=None, **kw):
 # pays the fixed ~8-10 us of a launch and fills the 74 CTA pairs only partly (1024 x 1024 x 6400: 16 tiles; the
 # 896-row encoder wgrads: 12-20 us for 2-7 GFLOP each); together their tiles form full waves.  MCAN_GROUP_WGRADS=0: off.
 GROUP_WGRADS = os.environ.get("MCAN_GROUP_WGRADS", "1") != "0"
+# With K unsplit every element of a grouped weight gradient is produced by exactly one work unit, so it is WRITTEN
+# into uninitialised memory instead of accumulated into a zero-filled arena: for MCAN-large that removes an 0.7 GB
+# memset per step and the read-modify-write of the same bytes by the fp32 atomics.  MCAN_STORE_WGRADS=0: off.
+STORE_WGRADS = os.environ.get("MCAN_STORE_WGRADS", "1") != "0"
+# Bias gradients of the Q / K / V projections out of the attention backward kernel (column sums of dQ / dK / dV reduced
+# per warp in shared memory, one global atomic per column and CTA) instead of column-sum launches over the gradient
+# buffers.  Implemented, parity-tested and measured SLOWER: 8.01 ms/step with vs 7.94 ms without (18 fewer launches,
+# but the backward attention kernel sits at 250 registers and one CTA per SM; the extra shuffles and shared-memory
+# traffic cost more than 18 column-sum launches of 8 us that hide in the gaps of the chain).  Off by default.
+ATTN_BIAS_GRADS = os.environ.get("MCAN_ATTN_BIAS_GRADS", "0") != "0"
 
 
 # Short-M GEMMs with a long contraction (the 896-row question side: FFN2 forward, the dgrads of
@@ -198,6 +237,10 @@ GROUP_WGRADS = os.environ.get("MCAN_GROUP_WGRADS", "1") != "0"
 # (red.global.add into a zeroed fp32 output, K split 0 adds bias + residual) on all SMs instead.
 SPLITK_MAX_ROWS = 1024
 SPLITK_MIN_K = 2048
+# The forward GEMMs of this class (encoder FFN2, the 64-row answer projection) stay unsplit by default: an A/B on one
+# box gave 7.98 ms/step without vs 8.01 ms with (the zero-fill of the output eats the gain), and an unsplit forward is
+# bit-reproducible run to run.  MCAN_SPLITK_FWD=1 switches them to split-K when gradients are being recorded.
+SPLITK_FWD = os.environ.get("MCAN_SPLITK_FWD", "0") != "0"
 
 
 def _resid_gemm(a, w, M, N, K, dev, **kw):
@@ -329,9 +372,14 @@ class GradBuf(object):
         self.lp, self.i0, self.i1 = lp, i0, i1
         self.sizes = lp.sizes[i0:i1]
         n = sum(self.sizes)
-        self.flat = rt.zeros(n * lp.k + n, lp.w.device)
-        self.w = self.flat[: n * lp.k].view(n, lp.k)
-        self.b = self.flat[n * lp.k:]
+        w = rt.empty_w(n * lp.k, lp.w.device)
+        if w is None:
+            flat = rt.zeros(n * lp.k + n, lp.w.device)
+            self.w = flat[: n * lp.k].view(n, lp.k)
+            self.b = flat[n * lp.k:]
+        else:       # written (not accumulated) by the layer's grouped wgrad launch; the bias gradient needs zeros
+            self.w = w.view(n, lp.k)
+            self.b = rt.zeros(n, lp.w.device)
 
     def _range(self, j0, j1):
         r0 = sum(self.lp.sizes[self.i0:j0])
@@ -389,10 +437,13 @@ def refresh_params(lps, force=False, need_lo=False):
             entry = ops.build_cast_table(fast, fast[0][0].device)
             _cast_tables[key] = entry
         ops.cast_multi(*entry)
-    for it in slow:    # padded leading dimensions (k % 8 != 0): plumbing copies, not on the hot path
-        it[0].copy_(it[1])
-        if len(it) > 2:
-            it[2].copy_(it[1] - it[0].float())
+    for it in slow:    # padded leading dimensions (k % 8 != 0, e.g. the 300-wide LSTM input weight): strided cast
+        if it[0].dim() == 2 and it[1].dim() == 2 and it[1].is_contiguous() and it[0].dtype == _BF16 and it[0].stride(1) == 1:
+            ops.rowmask_cast(it[1], it[0], it[2] if len(it) > 2 else None)
+        else:
+            it[0].copy_(it[1])
+            if len(it) > 2:
+                it[2].copy_(it[1] - it[0].float())
 
 
 _cast_tables = {}
@@ -490,7 +541,7 @@ def att_fwd(rt, mh, x, B, Sq, kv_src=None, Sk=None, key_mask=None, kv=None, norm
     M = B * Sq
     c = Bag()
     c.B, c.Sq, c.mask = B, Sq, key_mask
-    lp = mh.lp_qkv().get(_force(rt.p > 0 or torch.is_grad_enabled()), rt.split)
+    lp = mh.lp_qkv().get(_force(rt.p > 0 or rt.grad), rt.split)
     c.lp = lp
     c.x_bf = x.bf
     c.mode = "self" if (kv_src is None and kv is None) else ("kv" if kv is not None else "cross")
@@ -535,7 +586,7 @@ def att_fwd(rt, mh, x, B, Sq, kv_src=None, Sk=None, key_mask=None, kv=None, norm
                  scale=1.0 / math.sqrt(d), dropout_p=rt.p, seed=c.seed_att,
                  q_lo=q_lo, k_lo=k_lo, v_lo=v_lo, out_lo=att_lo)
     c.att = att
-    lpm = mh.lp_merge().get(_force(rt.p > 0 or torch.is_grad_enabled()), rt.split)
+    lpm = mh.lp_merge().get(_force(rt.p > 0 or rt.grad), rt.split)
     c.lpm = lpm
     atta = Act(None, att, att_lo)
     if norm is None:
@@ -593,16 +644,26 @@ def att_bwd(rt, mh, c, dout, norm=None, dkv=None, need_dx=True):
         else:
             dkvb = _empty(B * Sk, 2 * H, _BF16, dev)
             dk, dv = dkvb[:, :H], dkvb[:, H:]
-    ops.attn_bwd(c.q, c.k, c.v, c.mask, datt, dq, dk, dv, batch=B, heads=heads, sq=Sq, sk=Sk, head_dim=d,
-                 scale=1.0 / math.sqrt(d), dropout_p=rt.p, seed=c.seed_att)
+    # the bias gradients of the projections this block owns (column sums of dq / dk / dv) come out of the attention
+    # backward kernel itself; in "kv" mode K and V belong to the caller's batched projection
+    own_kv = c.mode != "kv"
+    if ATTN_BIAS_GRADS:
+        ops.attn_bwd(c.q, c.k, c.v, c.mask, datt, dq, dk, dv, batch=B, heads=heads, sq=Sq, sk=Sk, head_dim=d,
+                     scale=1.0 / math.sqrt(d), dropout_p=rt.p, seed=c.seed_att, dbq=g.rows_b(0, 1),
+                     dbk=g.rows_b(1, 2) if own_kv else None, dbv=g.rows_b(2, 3) if own_kv else None)
+    else:
+        ops.attn_bwd(c.q, c.k, c.v, c.mask, datt, dq, dk, dv, batch=B, heads=heads, sq=Sq, sk=Sk, head_dim=d,
+                     scale=1.0 / math.sqrt(d), dropout_p=rt.p, seed=c.seed_att)
+        rt.wgrad(ops.colsum, dq, g.rows_b(0, 1))
+        if own_kv:
+            rt.wgrad(ops.colsum, dk, g.rows_b(1, 2))
+            rt.wgrad(ops.colsum, dv, g.rows_b(2, 3))
     dx = None
     if c.mode == "self":
-        rt.wgrad(ops.colsum, dqkv, g.b)
         rt.wgrad_gemm(dqkv, c.x_bf, g.w)
         if need_dx:
             dx = _resid_gemm(dqkv, lp.w, M, H, 3 * H, dev, b_layout=1, resid=ds_f32)
     else:
-        rt.wgrad(ops.colsum, dq, g.rows_b(0, 1))
         rt.wgrad_gemm(dq, c.x_bf, g.rows_w(0, 1))
         if need_dx:
             dx = _empty(M, H, _F32, dev)
@@ -610,8 +671,6 @@ def att_bwd(rt, mh, c, dout, norm=None, dkv=None, need_dx=True):
         if c.mode == "cross":
             Mk = B * Sk
             if hasattr(c, "v_bf"):
-                rt.wgrad(ops.colsum, dk, g.rows_b(1, 2))
-                rt.wgrad(ops.colsum, dv, g.rows_b(2, 3))
                 rt.wgrad_gemm(dk, c.kv_bf, g.rows_w(1, 2))
                 rt.wgrad_gemm(dv, c.v_bf, g.rows_w(2, 3))
                 dkv_src = _empty(Mk, H, _F32, dev)
@@ -619,7 +678,6 @@ def att_bwd(rt, mh, c, dout, norm=None, dkv=None, need_dx=True):
                 ops.gemm(dk, lp.rows(1, 2)[0], b_layout=1, out_f32=dkv_src)
                 ops.gemm(dv, lp.rows(2, 3)[0], b_layout=1, out_f32=dv_src)
             else:
-                rt.wgrad(ops.colsum, dkvb, g.rows_b(1, 3))
                 rt.wgrad_gemm(dkvb, c.kv_bf, g.rows_w(1, 3))
                 dkv_src = _empty(Mk, H, _F32, dev)
                 ops.gemm(dkvb, lp.rows(1, 3)[0], b_layout=1, out_f32=dkv_src)
@@ -637,7 +695,7 @@ def mlp_fwd(rt, mlp, x, norm=None):
     dev = x.bf.device
     M = x.bf.shape[0]
     c = Bag()
-    force = _force(rt.p > 0 or torch.is_grad_enabled())
+    force = _force(rt.p > 0 or rt.grad)
     lp1 = mlp.lp_fc().get(force, rt.split)
     lp2 = mlp.lp_out().get(force, rt.split)
     c.lp1, c.lp2, c.x_bf = lp1, lp2, x.bf
@@ -659,7 +717,7 @@ def mlp_fwd(rt, mlp, x, norm=None):
         return out, c
     # split-K (see _resid_gemm) only when training: fp32 atomics make the result depend on the
     # arrival order (1e-7 relative), and inference must stay bit-reproducible run to run
-    use_sk = SPLITK_MIN_K > 0 and M <= SPLITK_MAX_ROWS and lp1.n >= SPLITK_MIN_K and torch.is_grad_enabled()
+    use_sk = SPLITK_MIN_K > 0 and M <= SPLITK_MAX_ROWS and lp1.n >= SPLITK_MIN_K and rt.grad and SPLITK_FWD
     c.seed_out = rt.seed()
     if not use_sk and _can_fuse_ln(rt, M, lp2.n, lp2):
         out, c.s, c.mean, c.sigma = gemm_ln_fwd(hmid, lp2, norm, x.f32, rt.p, c.seed_out)
@@ -757,7 +815,7 @@ def mca_ed_fwd(rt, m, x32, y32, B, Sx, Sy, x_mask, y_mask):
     H = m.hidden_size
     L = len(m.dec_list)
     dev = x32.device
-    with refresh_scope(m.all_lps(), rt.p > 0 or torch.is_grad_enabled()):
+    with refresh_scope(m.all_lps(), rt.p > 0 or rt.grad):
         return _mca_ed_fwd(rt, m, x32, y32, B, Sx, Sy, x_mask, y_mask, H, L, dev)
 
 
@@ -769,7 +827,7 @@ def _mca_ed_fwd(rt, m, x32, y32, B, Sx, Sy, x_mask, y_mask, H, L, dev):
         x, c = sa_fwd(rt, enc, x, B, Sx, x_mask)
         enc_ctx.append(c)
     # K/V of the final encoder output for all decoder layers: one GEMM [B*Sx, H] x [H, L*2H]
-    lpkv = m.lp_kv_all().get(_force(rt.p > 0 or torch.is_grad_enabled()), rt.split)
+    lpkv = m.lp_kv_all().get(_force(rt.p > 0 or rt.grad), rt.split)
     kv_all = _empty(B * Sx, 2 * H * L, _BF16, dev)
     kv_lo = _empty(B * Sx, 2 * H * L, _BF16, dev) if rt.split else None
     if L > 0:
@@ -820,7 +878,12 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
     B, Sx, Sy = ctx.B, ctx.Sx, ctx.Sy
     dev = dy_out.device
     grads = {}
-    rt.use_arena(sum(p.numel() for p in m.parameters()) + 8 * len(list(m.parameters())) + 64, dev)
+    total = sum(p.numel() for p in m.parameters()) + 8 * len(list(m.parameters())) + 64
+    # weight gradients of the SA / SGA layers (all 2-D parameters except the K/V projections batched across the
+    # decoder layers) are written by grouped launches into an uninitialised arena; everything else starts from zero
+    batched = set(id(w) for w, _ in ctx.lpkv.pairs) if L > 0 else set()
+    store = sum(p.numel() + 4 for p in m.parameters() if p.dim() == 2 and id(p) not in batched) if GROUP_WGRADS else 0
+    rt.use_arena(total - store if store and STORE_WGRADS else total, dev, store_numel=store)
     dkv_all = _empty(B * Sx, 2 * H * L, _BF16, dev)
     dy = dy_out
     overlap = OVERLAP_WGRAD and L > 0 and len(m.enc_list) > 0
@@ -888,7 +951,7 @@ def attflat_fwd(rt, af, x, B, S, mask):
     H, G, M = af.hidden_size, af.flat_glimpses, af.flat_mlp_size
     dev = x.bf.device
     c = Bag()
-    force = _force(rt.p > 0 or torch.is_grad_enabled())
+    force = _force(rt.p > 0 or rt.grad)
     lp1 = af.mlp.lp_fc().get(force, rt.split)
     lpm = af.lp_merge().get(force, rt.split)
     c.lp1, c.lpm, c.x, c.B, c.S, c.mask = lp1, lpm, x, B, S, mask
@@ -1021,7 +1084,7 @@ def head_fwd(rt, norm, lp, x, x2, target):
     if rt.split:
         logits = torch.empty((B, ldo), dtype=_F32, device=dev)[:, :lp.n]
         ops.gemm([ybf, ybf, ylo], [lp.w, lp.w_lo, lp.w], bias=lp.b, out_f32=logits)
-    elif torch.is_grad_enabled() and SPLITK_MIN_K > 0 and B <= SPLITK_MAX_ROWS and lp.k >= SPLITK_MIN_K:
+    elif rt.grad and SPLITK_FWD and SPLITK_MIN_K > 0 and B <= SPLITK_MAX_ROWS and lp.k >= SPLITK_MIN_K:
         # 64 rows x 3129 answers x K 2048 is one wave of 49 tiles that stream the 12.8 MB weight through 49 SMs
         # (45 us); split-K puts every SM on it (training only, like every split-K GEMM: fp32 atomics)
         logits = torch.zeros((B, ldo), dtype=_F32, device=dev)[:, :lp.n]
@@ -1052,3 +1115,68 @@ def head_bwd(rt, norm, c, g_a, g_probs, g_loss):
     ds, _, da2, db2 = ln_bwd(rt, norm, da, c.s, c.mean, c.sigma, want_bf=False)
     (gw, gb), = g.per_param()
     return ds, gw, gb, da2, db2
+
+
+# ------------------------------------------------------------------------------------------
+# question encoder: embedding + LSTM (net.py:66-78, 99, 103-104) -- csrc/lstm.cu
+# ------------------------------------------------------------------------------------------
+LSTM_KERNEL = os.environ.get("MCAN_LSTM", "1") != "0"
+LSTM_HIDDEN = (128, 256, 512, 1024)
+LSTM_CHUNK = 64       # samples per persistent launch
+
+
+def lstm_supported(lstm, split):
+    return (LSTM_KERNEL and not split and lstm.num_layers == 1 and not lstm.bidirectional and lstm.batch_first and
+            lstm.bias and getattr(lstm, "proj_size", 0) == 0 and lstm.hidden_size in LSTM_HIDDEN and
+            ops.num_sms_physical() >= 128)
+
+
+def qenc_fwd(rt, table, lp_ih, lp_hh, tokens, training):
+    """tokens int64 [B, T] -> (q fp32 [B*T, H], mask uint8 [B*T] (token == 0), ctx)."""
+    dev = tokens.device
+    B, T = tokens.shape
+    S1 = T + 1
+    H, E = lp_hh.k, lp_ih.k
+    R = B * S1
+    c = Bag()
+    ldx = (E + 7) // 8 * 8
+    x = torch.empty((R, ldx), dtype=_BF16, device=dev)
+    mask = torch.empty(B * T, dtype=torch.uint8, device=dev)
+    ops.embed_gather(tokens, table, x, mask)
+    xw = _empty(R, 4 * H, _F32, dev)
+    ops.gemm(x[:, :E], lp_ih.w, bias=lp_ih.b, out_f32=xw)
+    hbuf = _empty(R, H, _BF16, dev)
+    q = _empty(B * T, H, _F32, dev)
+    cbuf = _empty(R, H, _F32, dev) if training else None
+    gates = _empty(R, 4 * H, _F32, dev) if training else None
+    for b0 in range(0, B, LSTM_CHUNK):
+        nb = min(LSTM_CHUNK, B - b0)
+        r0, r1 = b0 * S1, (b0 + nb) * S1
+        ops.lstm_fwd(xw[r0:r1], lp_hh.w, lp_hh.b, hbuf[r0:r1], q[b0 * T:(b0 + nb) * T],
+                     cbuf[r0:r1] if training else None, gates[r0:r1] if training else None, batch=nb, steps=T, hidden=H)
+    c.tokens, c.x, c.hbuf, c.cbuf, c.gates, c.lp_ih, c.lp_hh, c.B, c.T, c.E = tokens, x, hbuf, cbuf, gates, lp_ih, lp_hh, B, T, E
+    return q, mask, c
+
+
+def qenc_bwd(rt, c, dq, vocab):
+    """dq fp32 [B*T, H] -> (dTable [V, E], dW_ih, db_ih, dW_hh, db_hh)."""
+    dev = dq.device
+    B, T, E = c.B, c.T, c.E
+    S1 = T + 1
+    H = c.lp_hh.k
+    R = B * S1
+    da = _empty(R, 4 * H, _BF16, dev)
+    for b0 in range(0, B, LSTM_CHUNK):
+        nb = min(LSTM_CHUNK, B - b0)
+        r0, r1 = b0 * S1, (b0 + nb) * S1
+        ops.lstm_bwd(dq[b0 * T:(b0 + nb) * T], c.lp_hh.w, c.hbuf[r0:r1], c.cbuf[r0:r1], c.gates[r0:r1], da[r0:r1],
+                     batch=nb, steps=T, hidden=H)
+    g_ih, g_hh = GradBuf(rt, c.lp_ih), GradBuf(rt, c.lp_hh)
+    ops.gemm_grouped([(da, c.hbuf, g_hh.w), (da, c.x[:, :E], g_ih.w)])     # dW_hh = dA^T h_prev, dW_ih = dA^T x
+    ops.colsum(da, g_hh.b)
+    ops.colsum(da, g_ih.b)
+    dx = torch.empty((R, (E + 3) // 4 * 4), dtype=_F32, device=dev)[:, :E]
+    ops.gemm(da, c.lp_ih.w, b_layout=1, out_f32=dx)
+    dtable = rt.zeros(vocab * E, dev).view(vocab, E)
+    ops.embed_scatter_add(c.tokens, dx, dtable)
+    return dtable, g_ih.w, g_ih.b, g_hh.w, g_hh.b

@@ -76,6 +76,7 @@ class GemmGroupedArgs(ctypes.Structure):
         ("g", GemmGroup * MAX_GROUPS),
         ("num_groups", c_int32),
         ("split_k", c_int32),
+        ("accumulate", c_int32),
         ("k", c_int64),
         ("stream", c_void_p),
     ]
@@ -104,6 +105,25 @@ class GemmLnArgs(ctypes.Structure):
         ("y_bf16", c_void_p),
         ("mean", c_void_p),
         ("sigma", c_void_p),
+        ("stream", c_void_p),
+    ]
+
+
+class LstmArgs(ctypes.Structure):
+    _fields_ = [
+        ("xw", c_void_p),
+        ("w_hh", c_void_p),
+        ("b_hh", c_void_p),
+        ("batch", c_int32),
+        ("steps", c_int32),
+        ("hidden", c_int32),
+        ("hbuf", c_void_p),
+        ("h_out", c_void_p),
+        ("cbuf", c_void_p),
+        ("gates", c_void_p),
+        ("dout", c_void_p),
+        ("da", c_void_p),
+        ("barrier", c_void_p),
         ("stream", c_void_p),
     ]
 
@@ -147,6 +167,9 @@ class AttnBwdArgs(ctypes.Structure):
         ("lddq", c_int64),
         ("lddk", c_int64),
         ("lddv", c_int64),
+        ("dbq", c_void_p),
+        ("dbk", c_void_p),
+        ("dbv", c_void_p),
     ]
 
 
@@ -163,6 +186,12 @@ SYMBOLS = {
     "mcan_gemm_grouped": (ctypes.c_int, [ctypes.POINTER(GemmGroupedArgs)]),
     "mcan_attn_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs)]),
     "mcan_attn_bwd": (ctypes.c_int, [ctypes.POINTER(AttnBwdArgs)]),
+    "mcan_embed_gather": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p,
+                                         c_void_p]),
+    "mcan_embed_scatter_add": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                              c_void_p]),
+    "mcan_lstm_fwd": (ctypes.c_int, [ctypes.POINTER(LstmArgs)]),
+    "mcan_lstm_bwd": (ctypes.c_int, [ctypes.POINTER(LstmArgs)]),
     "mcan_layernorm_fwd": (ctypes.c_int, [c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mcan_layernorm_add_fwd": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_float,

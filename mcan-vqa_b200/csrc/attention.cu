@@ -45,6 +45,9 @@ struct AttnParams {
     bf16* dk;
     bf16* dv;
     long long lddq, lddk, lddv;
+    float* dbq;     // optional: += column sums of dq / dk / dv (the bias gradients of linear_q / _k / _v), fp32 [heads * D]
+    float* dbk;
+    float* dbv;
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
@@ -420,6 +423,33 @@ __global__ void __launch_bounds__(128) attn_fwd_split_kernel(const AttnParams p)
     }
 }
 
+// Column sums of one 16-row accumulator tile o[dn][0..3] (rows g / g + 8, columns dn*8 + 2t, +1), as they are stored
+// (bf16-rounded), accumulated into THIS WARP's private shared-memory vector cs[D] (no atomics: shuffles over the 8
+// row groups, then the 4 lanes of row group 0 add their 2 x D/8 columns).
+template <int D>
+__device__ __forceinline__ void tile_colsum(const float (&o)[D / 8][4], bool v0, bool v1, float* cs, int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int dn = 0; dn < D / 8; ++dn) {
+        const uint32_t lo = pack_bf16x2(o[dn][0], o[dn][1]), hi = pack_bf16x2(o[dn][2], o[dn][3]);
+        float c0 = (v0 ? bf16_lo_to_f(lo) : 0.f) + (v1 ? bf16_lo_to_f(hi) : 0.f);
+        float c1 = (v0 ? bf16_hi_to_f(lo) : 0.f) + (v1 ? bf16_hi_to_f(hi) : 0.f);
+#pragma unroll
+        for (int sh = 4; sh < 32; sh <<= 1) {
+            c0 += __shfl_xor_sync(0xffffffffU, c0, sh);
+            c1 += __shfl_xor_sync(0xffffffffU, c1, sh);
+        }
+        if (g == 0) {
+            float2* dst = reinterpret_cast<float2*>(cs + dn * 8 + 2 * t);
+            float2 v = *dst;
+            v.x += c0;
+            v.y += c1;
+            *dst = v;
+        }
+    }
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------
 template <int D, int NT, bool EXACT>
 __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
@@ -437,6 +467,14 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
     bf16* sP = sV + skp * LDS;      // dropped probabilities Pd   [sqp][ldp]
     bf16* sdS = sP + sqp * ldp;     // scale * dS                 [sqp][ldp]
     uint8_t* sMask = reinterpret_cast<uint8_t*>(sdS + sqp * ldp);
+    // column sums of this (batch, head)'s dQ / dK / dV: the bias gradients of the three projections come out of this
+    // kernel (one shared-memory reduction per CTA, then one global atomic per column) instead of a column-sum pass
+    // over the [rows, 3H] gradient buffer per attention block
+    // [warp][dq | dk | dv][column], behind the mask bytes (16-byte aligned)
+    float (*s_cs)[3][D] = reinterpret_cast<float (*)[3][D]>(sMask + ((skp + 15) & ~15));
+    const bool want_cs = p.dbq != nullptr || p.dbk != nullptr || p.dbv != nullptr;
+    if (want_cs)
+        for (int i = threadIdx.x; i < 8 * 3 * D; i += blockDim.x) (&s_cs[0][0][0])[i] = 0.f;
 
     stage_rows<D>(sQ, p.q + (long long)b * p.sq * p.ldq + h * D, p.ldq, p.sq, sqp);
     stage_rows<D>(sdO, p.dout + (long long)b * p.sq * p.lddo + h * D, p.lddo, p.sq, sqp);
@@ -542,6 +580,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
             if (v0) *reinterpret_cast<uint32_t*>(q0 + dn * 8) = pack_bf16x2(o[dn][0], o[dn][1]);
             if (v1) *reinterpret_cast<uint32_t*>(q1 + dn * 8) = pack_bf16x2(o[dn][2], o[dn][3]);
         }
+        if (p.dbq != nullptr) tile_colsum<D>(o, v0, v1, s_cs[warp][0], lane);
     }
     __syncthreads();
 
@@ -590,6 +629,20 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
                 *reinterpret_cast<uint32_t*>(dk1 + dn * 8) = pack_bf16x2(ok[dn][2], ok[dn][3]);
             }
         }
+        if (p.dbk != nullptr) tile_colsum<D>(ok, key0 < p.sk, key1 < p.sk, s_cs[warp][1], lane);
+        if (p.dbv != nullptr) tile_colsum<D>(ov, key0 < p.sk, key1 < p.sk, s_cs[warp][2], lane);
+    }
+    if (want_cs) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) {
+            float* dst = (i < D) ? p.dbq : (i < 2 * D ? p.dbk : p.dbv);
+            if (dst != nullptr) {
+                float v = 0.f;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) v += s_cs[w][i / D][i % D];
+                atomicAdd(dst + h * D + (i % D), v);
+            }
+        }
     }
 }
 
@@ -599,7 +652,7 @@ static size_t attn_fwd_smem(int sq, int sk, int d) {
 }
 static size_t attn_bwd_smem(int sq, int sk, int d) {
     const int sqp = (sq + 15) & ~15, skp = (sk + 15) & ~15;
-    return (size_t)(2 * sqp + 2 * skp) * (d + 8) * 2 + (size_t)2 * sqp * (skp + 8) * 2 + skp + 16;
+    return (size_t)(2 * sqp + 2 * skp) * (d + 8) * 2 + (size_t)2 * sqp * (skp + 8) * 2 + skp + 16 + (size_t)8 * 3 * d * 4;
 }
 
 static int check_attn(const mcan_attn_args* a, const char* who) {
@@ -722,6 +775,7 @@ extern "C" int mcan_attn_bwd(const mcan_attn_bwd_args* a) {
     p.dk = reinterpret_cast<bf16*>(a->dk);
     p.dv = reinterpret_cast<bf16*>(a->dv);
     p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
+    p.dbq = a->dbq; p.dbk = a->dbk; p.dbv = a->dbv;
     const size_t smem = attn_bwd_smem(a->fwd.sq, a->fwd.sk, a->fwd.head_dim);
     const int mtiles = (a->fwd.sq + 15) / 16, ktiles = (a->fwd.sk + 15) / 16;
     const int mx = mtiles > ktiles ? mtiles : ktiles;

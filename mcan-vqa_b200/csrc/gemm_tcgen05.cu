@@ -1376,14 +1376,17 @@ extern "C" int mcan_gemm_grouped(const mcan_gemm_grouped_args* a) {
     p.m_tiles = tiles;
     p.n_tiles = 1;
     const int slots = sms / 2;
-    int splits = a->split_k > 0 ? a->split_k : pick_splits(tiles, p.kblocks, slots);
+    // overwrite mode (accumulate == 0): every output element is written by exactly one work unit, plain stores into
+    // memory that need not be initialised -- no zero-fill pass and no read-modify-write of the gradient in L2
+    MCAN_REQUIRE(a->accumulate != 0 || a->split_k <= 1, "mcan_gemm_grouped: overwrite mode cannot split K");
+    int splits = a->accumulate == 0 ? 1 : (a->split_k > 0 ? a->split_k : pick_splits(tiles, p.kblocks, slots));
     if (splits > p.kblocks) splits = p.kblocks;
     p.splits = splits;
     p.full_tiles = tiles;
     p.units = tiles * splits;
     p.drop_scale = 1.0f;
     p.gate_scale = 1.0f;
-    p.accumulate = 1;
+    p.accumulate = a->accumulate != 0 ? 1 : 0;
     p.tile_counter = nullptr;
     if (g_dynamic_schedule.load(std::memory_order_relaxed)) {
         if (int rc = next_tile_counter(&p.tile_counter)) return rc;

@@ -195,9 +195,10 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, 
     capi.check(lib.mcan_gemm(ctypes.byref(args)), "mcan_gemm")
 
 
-def gemm_grouped(problems, split_k=0):
+def gemm_grouped(problems, split_k=0, accumulate=True):
     """problems = [(a bf16 [K, M_g], b bf16 [K, N_g], out fp32 [M_g, N_g])]: out_g += a_g^T b_g for every group in ONE
-    launch (the weight gradients dW = dY^T X of one layer); at most capi.MAX_GROUPS groups sharing K."""
+    launch (the weight gradients dW = dY^T X of one layer); at most capi.MAX_GROUPS groups sharing K.
+    accumulate=False: out_g = a_g^T b_g with plain stores (K not split), out_g may be uninitialised memory."""
     lib = capi.load()
     if not 1 <= len(problems) <= capi.MAX_GROUPS:
         raise capi.McanError("gemm_grouped: 1..%d problems" % capi.MAX_GROUPS)
@@ -215,6 +216,7 @@ def gemm_grouped(problems, split_k=0):
         g.lda, g.ldb, g.ldo = a.stride(0), b.stride(0), out.stride(0)
     args.num_groups = len(problems)
     args.split_k = int(split_k)
+    args.accumulate = 1 if accumulate else 0
     args.k = k
     args.stream = _stream()
     capi.check(lib.mcan_gemm_grouped(ctypes.byref(args)), "mcan_gemm_grouped")
@@ -292,7 +294,7 @@ def attn_fwd(q, k, v, key_mask, out, *, batch, heads, sq, sk, head_dim, scale, d
 
 
 def attn_bwd(q, k, v, key_mask, dout, dq, dk, dv, *, batch, heads, sq, sk, head_dim, scale,
-             dropout_p=0.0, seed=0):
+             dropout_p=0.0, seed=0, dbq=None, dbk=None, dbv=None):
     lib = capi.load()
     args = capi.AttnBwdArgs()
     args.fwd = _attn_args(q, k, v, key_mask, batch, heads, sq, sk, head_dim, scale, dropout_p, seed)
@@ -301,6 +303,12 @@ def attn_bwd(q, k, v, key_mask, dout, dq, dk, dv, *, batch, heads, sq, sk, head_
     args.dout, args.lddo = dout.data_ptr(), dout.stride(0)
     args.dq, args.dk, args.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
     args.lddq, args.lddk, args.lddv = dq.stride(0), dk.stride(0), dv.stride(0)
+    for t, nm in ((dbq, "dbq"), (dbk, "dbk"), (dbv, "dbv")):
+        if t is not None:
+            _req(t, _F32, "attn " + nm)
+            if t.numel() != heads * head_dim or not t.is_contiguous():
+                raise capi.McanError("attn %s must be a contiguous fp32 vector of heads * head_dim" % nm)
+    args.dbq, args.dbk, args.dbv = _ptr(dbq), _ptr(dbk), _ptr(dbv)
     capi.check(lib.mcan_attn_bwd(ctypes.byref(args)), "mcan_attn_bwd")
 
 
@@ -349,6 +357,72 @@ def rowmask_cast(x, hi, lo=None, mask=None):
             raise capi.McanError("rowmask_cast: mask must be contiguous uint8 [rows]")
     capi.check(lib.mcan_rowmask_cast(x.data_ptr(), x.shape[0], x.shape[1], hi.data_ptr(), _ptr(lo), hi.stride(0),
                                      _ptr(mask), _stream()), "mcan_rowmask_cast")
+
+
+_lstm_bar = {}
+
+
+def _lstm_barrier(device):
+    t = _lstm_bar.get(device)
+    if t is None:
+        t = _lstm_bar[device] = torch.zeros(4, dtype=torch.int32, device=device)
+    return t
+
+
+def embed_gather(tokens, table, x, mask=None):
+    """x[b * (T + 1) + t, :E] = bf16(table[tokens[b, t]]) (slot T and the pad columns zero); mask[b * T + t] = tokens == 0."""
+    lib = capi.load()
+    _req(tokens, torch.int64, "embed tokens")
+    _req(table, _F32, "embed table")
+    _req2d(x, _BF16, "embed x")
+    B, T = tokens.shape
+    if not (tokens.is_contiguous() and table.is_contiguous()) or x.shape[0] != B * (T + 1) or x.shape[1] != x.stride(0):
+        raise capi.McanError("embed_gather: tokens / table contiguous, x = full [B * (T + 1), ld] buffer")
+    if mask is not None:
+        _req(mask, torch.uint8, "embed mask")
+    capi.check(lib.mcan_embed_gather(tokens.data_ptr(), table.data_ptr(), table.shape[0], table.shape[1], B, T, x.data_ptr(),
+                                     x.stride(0), _ptr(mask), _stream()), "mcan_embed_gather")
+
+
+def embed_scatter_add(tokens, dx, dtable):
+    """dtable[tokens[b, t]] += dx[b * (T + 1) + t, :E]  (fp32; dtable zero-initialised)."""
+    lib = capi.load()
+    _req(tokens, torch.int64, "embed tokens")
+    _req2d(dx, _F32, "embed dx")
+    _req(dtable, _F32, "embed dtable")
+    B, T = tokens.shape
+    capi.check(lib.mcan_embed_scatter_add(tokens.data_ptr(), dx.data_ptr(), dx.stride(0), dtable.shape[0], dtable.shape[1],
+                                          B, T, dtable.data_ptr(), _stream()), "mcan_embed_scatter_add")
+
+
+def _lstm_args(w_hh, hbuf, batch, steps, hidden, **ptrs):
+    _req2d(w_hh, _BF16, "lstm w_hh")
+    if w_hh.shape != (4 * hidden, hidden) or not w_hh.is_contiguous():
+        raise capi.McanError("lstm: w_hh must be contiguous bf16 [4H, H]")
+    args = capi.LstmArgs()
+    args.w_hh, args.hbuf = w_hh.data_ptr(), hbuf.data_ptr()
+    args.batch, args.steps, args.hidden = batch, steps, hidden
+    for k, v in ptrs.items():
+        setattr(args, k, _ptr(v))
+    args.barrier = _lstm_barrier(w_hh.device).data_ptr()
+    args.stream = _stream()
+    return args
+
+
+def lstm_fwd(xw, w_hh, b_hh, hbuf, h_out, cbuf, gates, *, batch, steps, hidden):
+    """All `steps` time steps of nn.LSTM for `batch` (<= 64) samples in one persistent launch; buffers in the
+    row(b, s) = b * (steps + 1) + s layout of include/mcan_b200.h (cbuf / gates None for inference)."""
+    lib = capi.load()
+    _req(xw, _F32, "lstm xw")
+    args = _lstm_args(w_hh, hbuf, batch, steps, hidden, xw=xw, b_hh=b_hh, h_out=h_out, cbuf=cbuf, gates=gates)
+    capi.check(lib.mcan_lstm_fwd(ctypes.byref(args)), "mcan_lstm_fwd")
+
+
+def lstm_bwd(dout, w_hh, hbuf, cbuf, gates, da, *, batch, steps, hidden):
+    lib = capi.load()
+    _req(dout, _F32, "lstm dout")
+    args = _lstm_args(w_hh, hbuf, batch, steps, hidden, dout=dout, cbuf=cbuf, gates=gates, da=da)
+    capi.check(lib.mcan_lstm_bwd(ctypes.byref(args)), "mcan_lstm_bwd")
 
 
 _head_ws = {}

@@ -151,13 +151,19 @@ def test_attention_fwd_bwd(batch, heads, sq, sk, d, kind):
     dout = (torch.randn(batch * sq, H, device="cuda") * 0.5).to(torch.bfloat16)
     dqkv = torch.zeros(batch * max(sq, sk), 3 * H, device="cuda", dtype=torch.bfloat16)
     dq, dk, dv = dqkv[: batch * sq, :H], dqkv[: batch * sk, H:2 * H], dqkv[: batch * sk, 2 * H:]
-    ops.attn_bwd(q, k, v, mask_u8, dout, dq, dk, dv, batch=batch, heads=heads, sq=sq, sk=sk, head_dim=d, scale=scale)
+    dbq, dbk, dbv = (torch.full((H,), 0.25, device="cuda") for _ in range(3))    # += : start from a non-zero value
+    ops.attn_bwd(q, k, v, mask_u8, dout, dq, dk, dv, batch=batch, heads=heads, sq=sq, sk=sk, head_dim=d, scale=scale,
+                 dbq=dbq, dbk=dbk, dbv=dbv)
     ref.backward(_heads(dout, batch, sq, heads, d))
     torch.cuda.synchronize()
     for name, gt, rf, s in (("dq", dq, qh.grad, sq), ("dk", dk, kh.grad, sk), ("dv", dv, vh.grad, sk)):
         gt = _heads(gt, batch, s, heads, d)
         err = (gt - rf).abs().max().item()
         assert err < 3e-2 * max(1.0, rf.abs().max().item()), (name, err, rf.abs().max().item())
+    # the fused bias gradients = column sums of the stored (bf16) gradients
+    for name, db, gt, s in (("dbq", dbq, dq, sq), ("dbk", dbk, dk, sk), ("dbv", dbv, dv, sk)):
+        want = 0.25 + gt[: batch * s].float().sum(0)
+        assert (db - want).abs().max().item() < 1e-3 * max(1.0, want.abs().max().item()), name
 
 
 def test_attention_dropout_matches_host_hash():
@@ -375,3 +381,47 @@ def test_sigmoid_bce_sum_fwd_bwd(rows, cols):
     ops.sigmoid_bce_fwd(logits, probs2)
     torch.cuda.synchronize()
     assert torch.equal(probs, probs2)
+
+
+# ---- question encoder: embedding + LSTM (csrc/lstm.cu) vs torch.nn.Embedding / nn.LSTM in fp64 ------------------
+@pytest.mark.parametrize("B,T,E,H,V", [(64, 14, 300, 1024, 2000), (64, 14, 300, 512, 2000), (5, 14, 300, 128, 50),
+                                       (70, 9, 300, 256, 300), (1, 1, 64, 128, 10), (130, 14, 300, 512, 500)])
+def test_question_encoder_embedding_lstm_fwd_bwd(B, T, E, H, V):
+    """reference net.py:66-78, 99, 103-104: gates (i, f, g, o), zero initial state, pads run through the LSTM;
+    bf16 operands with fp32 accumulation and fp32 cell state (tolerances as for the other bf16 GEMM chains)."""
+    from mcan_vqa_b200 import blocks
+    from mcan_vqa_b200.blocks import LinearParams, Runtime
+    torch.manual_seed(B * 1000 + H)
+    emb = torch.nn.Embedding(V, E).cuda()
+    lstm = torch.nn.LSTM(E, H, num_layers=1, batch_first=True).cuda()
+    tokens = torch.randint(1, V, (B, T), device="cuda")
+    tokens[:, T - T // 3:] = 0                   # padding tokens (index 0), as in VQA questions
+    tokens[0] = 0                                # a fully padded question
+    assert blocks.lstm_supported(lstm, False)
+    lp_ih = LinearParams([(lstm.weight_ih_l0, lstm.bias_ih_l0)]).get(True)
+    lp_hh = LinearParams([(lstm.weight_hh_l0, lstm.bias_hh_l0)]).get(True)
+    rt = Runtime(True, 0.0)
+    q, mask, ctx = blocks.qenc_fwd(rt, emb.weight.detach(), lp_ih, lp_hh, tokens, True)
+    dq = torch.randn(B * T, H, device="cuda") * 0.1
+    dt, dwi, dbi, dwh, dbh = blocks.qenc_bwd(rt, ctx, dq, V)
+    torch.cuda.synchronize()
+    # fp64 reference
+    emb64 = torch.nn.Embedding(V, E).double()
+    lstm64 = torch.nn.LSTM(E, H, num_layers=1, batch_first=True).double()
+    emb64.load_state_dict({k: v.double().cpu() for k, v in emb.state_dict().items()})
+    lstm64.load_state_dict({k: v.double().cpu() for k, v in lstm.state_dict().items()})
+    ref, _ = lstm64(emb64(tokens.cpu()))
+    ref.backward(dq.double().cpu().view(B, T, H))
+    assert torch.equal(mask.view(B, T).bool().cpu(), tokens.cpu() == 0)
+    assert (q.view(B, T, H).double().cpu() - ref).abs().max().item() < 1.5e-2
+
+    def rel(a, b):
+        return ((a.double().cpu() - b).norm() / (b.norm() + 1e-30)).item()
+    assert rel(dwh, lstm64.weight_hh_l0.grad) < 3e-2
+    assert rel(dwi, lstm64.weight_ih_l0.grad) < 3e-2
+    assert rel(dbh, lstm64.bias_hh_l0.grad) < 3e-2 and rel(dbi, lstm64.bias_ih_l0.grad) < 3e-2
+    assert rel(dt, emb64.weight.grad) < 3e-2
+    # inference: no saved state, same outputs
+    q2, _, _ = blocks.qenc_fwd(Runtime(False, 0.0), emb.weight.detach(), lp_ih, lp_hh, tokens, False)
+    torch.cuda.synchronize()
+    assert torch.equal(q, q2)
