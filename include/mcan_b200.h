@@ -382,7 +382,8 @@ int mcan_gemm_plan(int64_t m, int64_t n, int64_t k, int32_t accumulate, int32_t 
  * 64-bit words {p, g, m, v, shadow, n, first_chunk, shadow2}: fp32 pointers p (in/out), g (in), m, v
  * (in/out); shadow / shadow2 = optional copies of the updated p (bf16, or fp32 when bit 62 / bit 61 of
  * first_chunk is set; 0 = none) -- two, because a weight can sit in two stacked operand buffers;
- * n elements; first_chunk (bits 0..60) = running index of the segment's first 4096-element chunk.
+ * n elements; first_chunk (bits 0..59) = running index of the segment's first 4096-element chunk; bit 60 set = g
+ * points to bf16 values (the all-reduced bf16 staging buffer of a compressed gradient exchange).
  * lr_dev / step_dev: device scalars (fp32) holding the learning rate and t >= 1, so a captured CUDA
  * graph replays with new values.  flags bit 0: one chunk per CTA (short-lived CTAs) instead of a persistent
  * grid, for an update that shares the GPU with latency-bound kernels of a higher-priority stream. */

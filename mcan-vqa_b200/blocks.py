@@ -654,10 +654,15 @@ def att_bwd(rt, mh, c, dout, norm=None, dkv=None, need_dx=True):
     else:
         ops.attn_bwd(c.q, c.k, c.v, c.mask, datt, dq, dk, dv, batch=B, heads=heads, sq=Sq, sk=Sk, head_dim=d,
                      scale=1.0 / math.sqrt(d), dropout_p=rt.p, seed=c.seed_att)
-        rt.wgrad(ops.colsum, dq, g.rows_b(0, 1))
-        if own_kv:
-            rt.wgrad(ops.colsum, dk, g.rows_b(1, 2))
-            rt.wgrad(ops.colsum, dv, g.rows_b(2, 3))
+        if c.mode == "self":
+            rt.wgrad(ops.colsum, dqkv, g.b)                     # one pass over the [rows, 3H] gradient buffer
+        else:
+            rt.wgrad(ops.colsum, dq, g.rows_b(0, 1))
+            if c.mode == "cross" and hasattr(c, "v_bf"):
+                rt.wgrad(ops.colsum, dk, g.rows_b(1, 2))
+                rt.wgrad(ops.colsum, dv, g.rows_b(2, 3))
+            elif c.mode == "cross":
+                rt.wgrad(ops.colsum, dkvb, g.rows_b(1, 3))
     dx = None
     if c.mode == "self":
         rt.wgrad_gemm(dqkv, c.x_bf, g.w)

@@ -32,7 +32,8 @@ struct AdamSeg {
 constexpr long long kAdamChunk = 4096;
 constexpr long long kAdamF32Flag = 1LL << 62;
 constexpr long long kAdamF32Flag2 = 1LL << 61;
-constexpr long long kAdamChunkMask = ~(kAdamF32Flag | kAdamF32Flag2);
+constexpr long long kAdamBf16Grad = 1LL << 60;    // g points to bf16 (the all-reduced bf16 staging buffer of dp.py)
+constexpr long long kAdamChunkMask = ~(kAdamF32Flag | kAdamF32Flag2 | kAdamBf16Grad);
 
 struct AdamCoef {
     float lr_wd;   // 1 - lr * wd
@@ -76,10 +77,12 @@ adamw_multi_kernel(const AdamSeg* __restrict__ segs, int nseg, long long total_c
         const AdamSeg sg = segs[lo];
         const bool shadow_f32 = (sg.first_chunk & kAdamF32Flag) != 0;
         const bool shadow2_f32 = (sg.first_chunk & kAdamF32Flag2) != 0;
+        const bool g_bf16 = (sg.first_chunk & kAdamBf16Grad) != 0;
         const long long off = (chunk - (sg.first_chunk & kAdamChunkMask)) * kAdamChunk;
         const long long n = min(kAdamChunk, sg.n - off);
         float* p = sg.p + off;
-        const float* g = sg.g + off;
+        const float* g = g_bf16 ? nullptr : sg.g + off;
+        const bf16* g16 = g_bf16 ? reinterpret_cast<const bf16*>(sg.g) + off : nullptr;
         float* m = sg.m + off;
         float* v = sg.v + off;
         float* sh32 = (sg.shadow != nullptr && shadow_f32) ? reinterpret_cast<float*>(sg.shadow) + off : nullptr;
@@ -87,13 +90,19 @@ adamw_multi_kernel(const AdamSeg* __restrict__ segs, int nseg, long long total_c
         float* sh32b = (sg.shadow2 != nullptr && shadow2_f32) ? reinterpret_cast<float*>(sg.shadow2) + off : nullptr;
         bf16* sh16b = (sg.shadow2 != nullptr && !shadow2_f32) ? reinterpret_cast<bf16*>(sg.shadow2) + off : nullptr;
         const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v | (uintptr_t)sh32 | (uintptr_t)sh32b) & 15) == 0) &&
-                         ((((uintptr_t)sh16 | (uintptr_t)sh16b) & 7) == 0);
+                         ((((uintptr_t)sh16 | (uintptr_t)sh16b | (uintptr_t)g16) & 7) == 0);
         long long done = 0;
         if (vec) {
             const long long nv = n >> 2;
             for (long long i = threadIdx.x; i < nv; i += blockDim.x) {
                 float4 pv = reinterpret_cast<float4*>(p)[i];
-                const float4 gv = reinterpret_cast<const float4*>(g)[i];
+                float4 gv;
+                if (g_bf16) {
+                    const uint2 gw = reinterpret_cast<const uint2*>(g16)[i];
+                    gv = make_float4(bf16_lo_to_f(gw.x), bf16_hi_to_f(gw.x), bf16_lo_to_f(gw.y), bf16_hi_to_f(gw.y));
+                } else {
+                    gv = reinterpret_cast<const float4*>(g)[i];
+                }
                 float4 mv = reinterpret_cast<float4*>(m)[i];
                 float4 vv = reinterpret_cast<float4*>(v)[i];
                 pv.x = adam_one(pv.x, gv.x, mv.x, vv.x, c);
@@ -117,7 +126,7 @@ adamw_multi_kernel(const AdamSeg* __restrict__ segs, int nseg, long long total_c
         }
         for (long long i = done + threadIdx.x; i < n; i += blockDim.x) {
             float mm = m[i], vv = v[i];
-            const float pn = adam_one(p[i], g[i], mm, vv, c);
+            const float pn = adam_one(p[i], g_bf16 ? __bfloat162float(g16[i]) : g[i], mm, vv, c);
             p[i] = pn;
             m[i] = mm;
             v[i] = vv;

@@ -20,6 +20,7 @@ _F32 = torch.float32
 _CHUNK = 4096
 _F32_FLAG = 1 << 62
 _F32_FLAG2 = 1 << 61
+_BF16_GRAD = 1 << 60
 _WORDS = 8
 
 
@@ -105,7 +106,8 @@ class FusedAdamW(object):
             n, o = p.numel(), self._off[i]
             sh = self._shadow.get(id(p), [])
             flag = (_F32_FLAG if (len(sh) > 0 and sh[0].dtype == _F32) else 0) | \
-                   (_F32_FLAG2 if (len(sh) > 1 and sh[1].dtype == _F32) else 0)
+                   (_F32_FLAG2 if (len(sh) > 1 and sh[1].dtype == _F32) else 0) | \
+                   (_BF16_GRAD if g.dtype == torch.bfloat16 else 0)
             rows.append([p.data_ptr(), g.data_ptr(), self._m.data_ptr() + 4 * o, self._v.data_ptr() + 4 * o,
                          sh[0].data_ptr() if len(sh) > 0 else 0, n, chunk | flag,
                          sh[1].data_ptr() if len(sh) > 1 else 0])
@@ -191,9 +193,13 @@ class FusedAdamW(object):
             work.wait()       # the current stream waits for this all-reduce; no host sync
             spans = [(t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()) for t in tensors]
             mine, rest = [], []
+            view = getattr(work, "grad_view", None)      # bf16 exchange: the reduced values live in the staging buffer
             for i, g in remaining:
                 a = g.data_ptr()
-                (mine if any(lo <= a < hi for lo, hi in spans) else rest).append((i, g))
+                if any(lo <= a < hi for lo, hi in spans):
+                    mine.append((i, view(g) if view is not None else g))
+                else:
+                    rest.append((i, g))
             remaining = rest
             self._launch(mine)
         if remaining:
@@ -316,12 +322,17 @@ class EarlyStep(object):
             for k in todo:
                 work, tensors, pairs = sync.pending[k]
                 active = []
+                view = getattr(work, "grad_view", None)  # bf16 exchange: read the reduced values from the staging buffer
                 for prm, g in pairs:
                     i = self.opt._index.get(id(prm))
                     if i is None or g is None or g.dtype != _F32 or not g.is_contiguous():
                         active = None
                         break
-                    active.append((i, g))
+                    gv = view(g) if view is not None else g
+                    if gv is None:
+                        active = None
+                        break
+                    active.append((i, gv))
                 if active is None:
                     continue          # left to step_buckets
                 work.wait()           # the side stream waits for this all-reduce

