@@ -559,8 +559,10 @@ def main():
                               "(training mode; the split-precision 'fp32' mode that reaches >= 99.9 % top-1 agreement is inference-only)",
             "details": {"launch": graph_note, "sms_reserved_for_nccl": reserve if world > 1 else 0,
                         "gemm_tile_schedule": "dynamic" if dynamic else "static",
-                        "grad_exchange": ("all-reduce(SUM), %s, buckets >= %s MB" % (os.environ.get("MCAN_DP_COMPRESS", "") or "fp32",
-                                                                                  os.environ.get("MCAN_DP_BUCKET_MB", "192"))) if world > 1 else "none",
+                        "grad_exchange": ("all-reduce(SUM), %s, buckets >= %s MB" % (
+                            (trainer.sync.compress or "fp32") + (" (fp32 gradients cast by the library, AdamW reads the bf16 sums in place)"
+                                                                if trainer.sync.compress == "bf16" else ""),
+                            os.environ.get("MCAN_DP_BUCKET_MB", "192"))) if world > 1 else "none",
                         "optimizer": "fused multi-tensor AdamW (library kernel, emits the bf16 operand copies)",
                         "decoder_wgrads": "second stream, next to the encoder backward" if blocks.OVERLAP_WGRAD else "inline"},
             "clocks": clocks,
