@@ -941,7 +941,7 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
             dx, g = sa_bwd(rt, m.enc_list[i], ctx.enc[i], dx)
             grads.update(g)
             if after_layer is not None:
-                after_layer(rt.drain(), g, "enc")
+                after_layer(rt.drain(), g, "enc" if i > 0 else "enc_last")
     if side is not None:
         torch.cuda.current_stream().wait_stream(side)    # join; `pending` kept every operand alive until here
         del pending

@@ -160,7 +160,10 @@ class GradSync(object):
         self.acc_pairs += self.ready_pairs + ([(p, g.detach()) for p, g in grads.items() if g is not None] if grads else [])
         self.ready, self.ready_pairs = [], []
         self.acc_bytes = sum(t.numel() * t.element_size() for t in self.acc)
-        if self.acc_bytes >= (self.bucket_bytes if kind in (None, "dec") else min(self.bucket_bytes, self.enc_bucket_bytes)):
+        # "enc_last": the backbone is done -- whatever has accumulated goes out now, next to the LSTM / image-projection
+        # backward that follows, so that only those few gradients are left for the exposed exchange after the backward pass
+        if (kind == "enc_last" and not os.environ.get("MCAN_DP_NO_LAST_FLUSH")) or self.acc_bytes >= (self.bucket_bytes if kind in (None, "dec")
+                                                    else min(self.bucket_bytes, self.enc_bucket_bytes)):
             self._flush_acc()
         self._ensure_final_callback()
         if self.early is not None:
