@@ -135,7 +135,7 @@ typedef struct mcan_gemm_group {
     const void* a;
     const void* b;
     int64_t m, n, lda, ldb;
-    float* out;
+    void* out;            /* fp32 [M, N], or bf16 when mcan_gemm_grouped_args.out_bf16 != 0 */
     int64_t ldo;
 } mcan_gemm_group;
 
@@ -144,6 +144,8 @@ typedef struct mcan_gemm_grouped_args {
     int32_t num_groups;
     int32_t split_k;
     int32_t accumulate;
+    int32_t out_bf16;     /* != 0: the outputs are bf16 (accumulate must be 0): gradients produced directly in the
+                           * buffer a bf16 gradient all-reduce works on */
     int64_t k;
     void* stream;
 } mcan_gemm_grouped_args;

@@ -67,7 +67,9 @@ class _Chain(torch.autograd.Function):
     def backward(ctx, *gouts):
         runner = ctx.runner
         act_grads, grads = runner.backward(gouts, ctx.act_needs)
-        pg = tuple(grads.get(p) for p in runner.params)
+        # a gradient in another dtype than its parameter (bf16 weight gradients produced directly in the all-reduce
+        # buffer, blocks.WGRAD_BF16) is not handed to autograd: the data-parallel optimiser gets it from dp.GradSync
+        pg = tuple(g if (g is None or g.dtype == p.dtype) else None for p, g in ((p, grads.get(p)) for p in runner.params))
         return (None, None) + tuple(act_grads) + pg
 
 

@@ -77,6 +77,7 @@ class GemmGroupedArgs(ctypes.Structure):
         ("num_groups", c_int32),
         ("split_k", c_int32),
         ("accumulate", c_int32),
+        ("out_bf16", c_int32),
         ("k", c_int64),
         ("stream", c_void_p),
     ]

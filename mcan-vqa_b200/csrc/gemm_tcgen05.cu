@@ -61,7 +61,7 @@ constexpr int kMaxGroups = 8;
 constexpr int kMaxTmaps = kMaxGroups > MCAN_MAX_GEMM_SEGMENTS ? kMaxGroups : MCAN_MAX_GEMM_SEGMENTS;
 struct GroupDesc {
     int m, n, n_tiles, tile_start;     // tile_start: index of the group's first tile in the launch
-    float* out;
+    void* out;                         // fp32, or bf16 when GemmParams::group_bf16 is set
     long long ldo;
 };
 
@@ -70,6 +70,7 @@ struct alignas(64) GemmParams {
     CUtensorMap tma_b[kMaxTmaps];
     CUtensorMap tma_b_half[MCAN_MAX_GEMM_SEGMENTS];   // K-major B, box of half as many rows (tail splitting)
     int num_groups;                    // 0: one problem
+    int group_bf16;                    // grouped launch writes bf16 outputs (EPI = 1 instantiation)
     GroupDesc grp[kMaxGroups];
     int num_seg;
     int m, n, k;
@@ -152,6 +153,8 @@ struct EpiDims {
     int m, n;
     float* out_f32;
     long long ldo_f32;
+    bf16* out_bf16;
+    long long ldo_bf16;
 };
 
 // generic (slow) path for chunks that cross the N boundary or odd N: per element, rolled loops, on the
@@ -177,10 +180,10 @@ __device__ __noinline__ void epilogue_frag_ragged(const GemmParams& p, const Epi
             if (p.accumulate) atomicAdd(d.out_f32 + row * d.ldo_f32 + col, x);
             else d.out_f32[row * d.ldo_f32 + col] = x;
         }
-        if (p.out_bf16 != nullptr) {
+        if (d.out_bf16 != nullptr) {
             const bf16 hi = __float2bfloat16_rn(x);
-            p.out_bf16[row * p.ldo_bf16 + col] = hi;
-            if (p.out_lo != nullptr) p.out_lo[row * p.ldo_bf16 + col] = __float2bfloat16_rn(x - __bfloat162float(hi));
+            d.out_bf16[row * d.ldo_bf16 + col] = hi;
+            if (p.out_lo != nullptr) p.out_lo[row * d.ldo_bf16 + col] = __float2bfloat16_rn(x - __bfloat162float(hi));
         }
     }
 }
@@ -327,7 +330,7 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const EpiDims
             }
         }
     }
-    if (p.out_bf16 != nullptr) {
+    if (d.out_bf16 != nullptr) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (ok[h]) {
@@ -336,14 +339,14 @@ __device__ __forceinline__ void epilogue_frag(const GemmParams& p, const EpiDims
                     uint32_t pk[4];
 #pragma unroll
                     for (int e = 0; e < 8; e += 2) pk[e >> 1] = pack_bf16x2(T8(v, q, h, e), T8(v, q, h, e + 1));
-                    *reinterpret_cast<uint4*>(p.out_bf16 + rows[h] * p.ldo_bf16 + col + 32 * q) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    *reinterpret_cast<uint4*>(d.out_bf16 + rows[h] * d.ldo_bf16 + col + 32 * q) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                     if (p.out_lo != nullptr) {
                         uint32_t lo[4];
 #pragma unroll
                         for (int e = 0; e < 8; e += 2)
                             lo[e >> 1] = pack_bf16x2(T8(v, q, h, e) - bf16_lo_to_f(pk[e >> 1]),
                                                      T8(v, q, h, e + 1) - bf16_hi_to_f(pk[e >> 1]));
-                        *reinterpret_cast<uint4*>(p.out_lo + rows[h] * p.ldo_bf16 + col + 32 * q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        *reinterpret_cast<uint4*>(p.out_lo + rows[h] * d.ldo_bf16 + col + 32 * q) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
             }
@@ -487,11 +490,11 @@ __device__ __forceinline__ void epilogue_frag_direct(const GemmParams& p, const 
             }
         }
     }
-    if (p.out_bf16 != nullptr) {
+    if (d.out_bf16 != nullptr) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             if (ok[h]) {
-                uint32_t* o = reinterpret_cast<uint32_t*>(p.out_bf16 + rows[h] * p.ldo_bf16 + col);
+                uint32_t* o = reinterpret_cast<uint32_t*>(d.out_bf16 + rows[h] * d.ldo_bf16 + col);
                 uint32_t pk[8];
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
@@ -499,7 +502,7 @@ __device__ __forceinline__ void epilogue_frag_direct(const GemmParams& p, const 
                     o[4 * k] = pk[k];
                 }
                 if (p.out_lo != nullptr) {
-                    uint32_t* ol = reinterpret_cast<uint32_t*>(p.out_lo + rows[h] * p.ldo_bf16 + col);
+                    uint32_t* ol = reinterpret_cast<uint32_t*>(p.out_lo + rows[h] * d.ldo_bf16 + col);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
                         ol[4 * k] = pack_bf16x2(v[4 * k + 2 * h] - bf16_lo_to_f(pk[k]),
@@ -897,9 +900,12 @@ gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
             EpiDims d;
             if (p.num_groups > 0) {
                 d.m = p.grp[ui.group].m; d.n = p.grp[ui.group].n;
-                d.out_f32 = p.grp[ui.group].out; d.ldo_f32 = p.grp[ui.group].ldo;
+                d.out_f32 = p.group_bf16 ? nullptr : reinterpret_cast<float*>(p.grp[ui.group].out);
+                d.out_bf16 = p.group_bf16 ? reinterpret_cast<bf16*>(p.grp[ui.group].out) : nullptr;
+                d.ldo_f32 = d.ldo_bf16 = p.grp[ui.group].ldo;
             } else {
                 d.m = p.m; d.n = p.n; d.out_f32 = p.out_f32; d.ldo_f32 = p.ldo_f32;
+                d.out_bf16 = p.out_bf16; d.ldo_bf16 = p.ldo_bf16;
             }
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N);
 #define MCAN_EPI_TILE(PF, T8L) epilogue_tile<CG, PF, T8L>(p, d, lane, chunk_par, row0, n0, ui.width, taddr, &tmem_full_bar[acc], \
@@ -1358,7 +1364,7 @@ extern "C" int mcan_gemm_grouped(const mcan_gemm_grouped_args* a) {
         MCAN_REQUIRE(q.a && q.b && q.out && q.m > 0 && q.n > 0 && q.m < (1LL << 31) && q.n < (1LL << 31) &&
                          q.m * q.n < (1LL << 32),
                      "mcan_gemm_grouped: bad group %d", g);
-        MCAN_REQUIRE(q.ldo % 4 == 0 && ((uintptr_t)q.out & 15) == 0, "mcan_gemm_grouped: out alignment (group %d)", g);
+        MCAN_REQUIRE(q.ldo % (a->out_bf16 ? 8 : 4) == 0 && ((uintptr_t)q.out & 15) == 0, "mcan_gemm_grouped: out alignment (group %d)", g);
         if (int rc = make_tmap_bf16(&p.tma_a[g], q.a, (uint64_t)q.m, (uint64_t)a->k, (uint64_t)q.lda, 64)) return rc;
         if (int rc = make_tmap_bf16(&p.tma_b[g], q.b, (uint64_t)q.n, (uint64_t)a->k, (uint64_t)q.ldb, 64)) return rc;
         p.grp[g].m = (int)q.m;
@@ -1369,10 +1375,17 @@ extern "C" int mcan_gemm_grouped(const mcan_gemm_grouped_args* a) {
         p.grp[g].ldo = q.ldo;
         tiles += (int)((q.m + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * p.grp[g].n_tiles;
     }
+    MCAN_REQUIRE(!a->out_bf16 || a->accumulate == 0, "mcan_gemm_grouped: bf16 outputs are written, not accumulated");
+    p.group_bf16 = a->out_bf16 ? 1 : 0;
     p.m = p.grp[0].m;
     p.n = p.grp[0].n;
-    p.out_f32 = p.grp[0].out;
-    p.ldo_f32 = p.grp[0].ldo;
+    if (a->out_bf16) {
+        p.out_bf16 = reinterpret_cast<bf16*>(p.grp[0].out);
+        p.ldo_bf16 = p.grp[0].ldo;
+    } else {
+        p.out_f32 = reinterpret_cast<float*>(p.grp[0].out);
+        p.ldo_f32 = p.grp[0].ldo;
+    }
     p.m_tiles = tiles;
     p.n_tiles = 1;
     const int slots = sms / 2;
@@ -1392,6 +1405,7 @@ extern "C" int mcan_gemm_grouped(const mcan_gemm_grouped_args* a) {
         if (int rc = next_tile_counter(&p.tile_counter)) return rc;
     }
     { const char* d = getenv("MCAN_GEMM_DEBUG"); p.debug = d ? atoi(d) : 0; }
+    if (a->out_bf16) return launch_gemm<256, 1, 1, 2, 1, 1>(p, p.units, sms, reinterpret_cast<cudaStream_t>(a->stream));
     return launch_gemm<256, 1, 1, 2, 1, 0>(p, p.units, sms, reinterpret_cast<cudaStream_t>(a->stream));
 }
 

@@ -80,23 +80,33 @@ class _Bf16Bucket(object):
         from . import ops
         self.spans = []
         o = 0
+        direct = []       # bf16 buffers (weight gradients written by the grouped launches): reduced in place
         for t in tensors:
+            if t.dtype == torch.bfloat16:
+                direct.append(t)
+                continue
             n = t.numel()
             ops.cast_bf16(t.view(-1), stage[o:o + n])
             self.spans.append((t.data_ptr(), t.data_ptr() + 4 * n, o))
             o += (n + 7) // 8 * 8
         self.stage = stage[:o]
-        self.work = dist.all_reduce(self.stage, op=dist.ReduceOp.SUM, group=group, async_op=True)
+        bufs = ([self.stage] if o > 0 else []) + direct
+        self.works = _all_reduce_sum_async(bufs, group) if len(bufs) > 1 else \
+            [dist.all_reduce(bufs[0], op=dist.ReduceOp.SUM, group=group, async_op=True)]
 
     @staticmethod
     def needed(tensors):
-        return sum((t.numel() + 7) // 8 * 8 for t in tensors)
+        return max(8, sum((t.numel() + 7) // 8 * 8 for t in tensors if t.dtype != torch.bfloat16))
 
     def wait(self):
-        self.work.wait()
+        for w in self.works:
+            w.wait()
 
     def grad_view(self, g):
-        """The all-reduced bf16 values of the fp32 gradient view `g` (which lies inside one of the bucket's buffers)."""
+        """The all-reduced bf16 values of the gradient view `g`: itself when it already is bf16 (reduced in place), else
+        its image in the staging buffer (g lies inside one of the bucket's fp32 buffers)."""
+        if g.dtype == torch.bfloat16:
+            return g
         a = g.data_ptr()
         for lo, hi, o in self.spans:
             if lo <= a < hi:
@@ -159,7 +169,7 @@ class GradSync(object):
         #  autograd's AccumulateGrad CLONE them into .grad instead of adopting the arena views being reduced in place)
         self.acc_pairs += self.ready_pairs + ([(p, g.detach()) for p, g in grads.items() if g is not None] if grads else [])
         self.ready, self.ready_pairs = [], []
-        self.acc_bytes = sum(t.numel() * t.element_size() for t in self.acc)
+        self.acc_bytes = sum(t.numel() * 4 for t in self.acc)      # fp32-equivalent bytes: same buckets whatever the dtype
         # "enc_last": the backbone is done -- whatever has accumulated goes out now, next to the LSTM / image-projection
         # backward that follows, so that only those few gradients are left for the exposed exchange after the backward pass
         if (kind == "enc_last" and not os.environ.get("MCAN_DP_NO_LAST_FLUSH")) or self.acc_bytes >= (self.bucket_bytes if kind in (None, "dec")
@@ -185,7 +195,8 @@ class GradSync(object):
         if self.world == 1 or not tensors:
             return
         pairs = list(pairs) if pairs else []
-        if self.compress == "bf16" and all(t.dtype == torch.float32 and t.is_contiguous() for t in tensors):
+        if self.compress == "bf16" and all(t.is_contiguous() for t in tensors) and \
+                (self.defer_wait or all(t.dtype == torch.float32 for t in tensors)):
             if self.defer_wait and tensors[0].is_cuda:
                 # the bucket-wise fused optimiser reads the reduced bf16 values in place: no unpack
                 k, need = self._bucket_no, _Bf16Bucket.needed(tensors)

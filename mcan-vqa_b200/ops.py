@@ -207,7 +207,7 @@ def gemm_grouped(problems, split_k=0, accumulate=True):
     for i, (a, b, out) in enumerate(problems):
         _req2d(a, _BF16, "gemm_grouped a")
         _req2d(b, _BF16, "gemm_grouped b")
-        _req2d(out, _F32, "gemm_grouped out")
+        _req2d(out, problems[0][2].dtype if problems[0][2].dtype in (_F32, _BF16) else _F32, "gemm_grouped out")
         if a.shape[0] != k or b.shape[0] != k or out.shape != (a.shape[1], b.shape[1]):
             raise capi.McanError("gemm_grouped: problem %d: shapes %s %s %s" % (i, tuple(a.shape), tuple(b.shape), tuple(out.shape)))
         g = args.g[i]
@@ -217,6 +217,7 @@ def gemm_grouped(problems, split_k=0, accumulate=True):
     args.num_groups = len(problems)
     args.split_k = int(split_k)
     args.accumulate = 1 if accumulate else 0
+    args.out_bf16 = 1 if problems[0][2].dtype == _BF16 else 0
     args.k = k
     args.stream = _stream()
     capi.check(lib.mcan_gemm_grouped(ctypes.byref(args)), "mcan_gemm_grouped")

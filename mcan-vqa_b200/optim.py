@@ -191,17 +191,37 @@ class FusedAdamW(object):
             if len(entry) > 3 and entry[3]:
                 continue      # already waited for and applied next to the encoder backward (EarlyStep.on_dp_layer)
             work.wait()       # the current stream waits for this all-reduce; no host sync
-            spans = [(t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()) for t in tensors]
-            mine, rest = [], []
-            view = getattr(work, "grad_view", None)      # bf16 exchange: the reduced values live in the staging buffer
-            for i, g in remaining:
-                a = g.data_ptr()
-                if any(lo <= a < hi for lo, hi in spans):
-                    mine.append((i, view(g) if view is not None else g))
-                else:
-                    rest.append((i, g))
-            remaining = rest
-            self._launch(mine)
+            view = getattr(work, "grad_view", None)      # bf16 exchange: the reduced values live in the exchange buffers
+            pairs = entry[2] if len(entry) > 2 else None
+            mine = []
+            if pairs:
+                # the bucket knows its (parameter, gradient) pairs -- including the bf16 weight gradients that never
+                # become a .grad (blocks.WGRAD_BF16)
+                taken = set()
+                open_idx = set(i for i, _ in remaining)
+                for prm, g in pairs:
+                    i = self._index.get(id(prm))
+                    if i is None or g is None or (self._early_done is not None and id(prm) in self._early_done):
+                        continue
+                    if g.dtype == _F32 and i not in open_idx:
+                        continue      # no .grad (any more): already applied through another handle of this bucket
+                    gv = view(g) if view is not None else g
+                    if gv is None:
+                        raise capi.McanError("FusedAdamW.step_buckets: a gradient of the bucket is not in its exchange buffers")
+                    mine.append((i, gv))
+                    taken.add(i)
+                remaining = [(i, g) for i, g in remaining if i not in taken]
+            else:
+                spans = [(t.data_ptr(), t.data_ptr() + t.numel() * t.element_size()) for t in tensors]
+                rest = []
+                for i, g in remaining:
+                    a = g.data_ptr()
+                    if any(lo <= a < hi for lo, hi in spans):
+                        mine.append((i, view(g) if view is not None else g))
+                    else:
+                        rest.append((i, g))
+                remaining = rest
+            self._launch(sorted(mine, key=lambda t: t[0]))
         if remaining:
             raise capi.McanError("FusedAdamW.step_buckets: %d gradients were not part of any all-reduce bucket"
                                  % len(remaining))
@@ -325,7 +345,8 @@ class EarlyStep(object):
                 view = getattr(work, "grad_view", None)  # bf16 exchange: read the reduced values from the staging buffer
                 for prm, g in pairs:
                     i = self.opt._index.get(id(prm))
-                    if i is None or g is None or g.dtype != _F32 or not g.is_contiguous():
+                    if i is None or g is None or g.dtype not in (_F32, torch.bfloat16) or not g.is_contiguous() or \
+                            (g.dtype != _F32 and view is None):
                         active = None
                         break
                     gv = view(g) if view is not None else g

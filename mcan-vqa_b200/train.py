@@ -68,6 +68,8 @@ class Trainer(object):
                 self.sync.compress = "bf16"
             elif os.environ["MCAN_DP_COMPRESS"] == "fp32":
                 self.sync.compress = ""
+            # ... and the layers' weight gradients are produced as bf16 directly in the exchange buffers
+            blocks.WGRAD_BF16 = self.sync.compress == "bf16" and os.environ.get("MCAN_DP_WGRAD_BF16", "1") != "0"
         # single GPU: the optimiser update of finished layers overlaps the encoder half of the backward pass
         self.early = None
         if (isinstance(self.opt, FusedAdamW) and not self.bucketed and (self.sync is None or self.sync.world == 1)
@@ -166,5 +168,6 @@ class Trainer(object):
             ops.set_seed_tensor(None)
         if self.sync is not None:
             dp.detach()
+            blocks.WGRAD_BF16 = False
         if self.early is not None:
             _optim.set_early(None)

@@ -451,3 +451,19 @@ def test_layer_backward_with_grouped_wgrads_matches_individual_launches():
     for n, g in res[False][0].items():
         err = (res[True][0][n] - g).norm().item()
         assert err <= 2e-2 * g.norm().item() + 1e-5 * total, (n, err, g.norm().item())
+
+
+def test_gemm_grouped_bf16_outputs():
+    """Grouped wgrad launch writing bf16 (the data-parallel bf16 exchange buffers): == bf16(fp32 result)."""
+    ops = _ops()
+    rows = 6400
+    probs, refs = [], []
+    for i, (n, k) in enumerate([(1024, 1024), (512, 2048), (264, 520)]):
+        dy, x = _rand((rows, n), 300 + i, 0.1), _rand((rows, k), 400 + i)
+        out = torch.full((n, k), float("nan"), device="cuda", dtype=torch.bfloat16)
+        probs.append((dy, x, out))
+        refs.append(dy.float().t() @ x.float())
+    ops.gemm_grouped(probs, accumulate=False)
+    torch.cuda.synchronize()
+    for (dy, x, out), ref in zip(probs, refs):
+        assert (out.float() - ref).abs().max().item() <= 2 ** -7 * ref.abs().max().item()
