@@ -26,7 +26,8 @@ class WarmupOptimizer(object):
         self._step += 1
         sync = dp.active()
         if sync is None or not sync.overlap:
-            dp.sync_all_grads([p for g in self.optimizer.param_groups for p in g['params']])
+            if not dp.consume_presync():      # (the loop may have reduced before clip_grad_norm_: dp.sync_all_grads(..., before_clip=True))
+                dp.sync_all_grads([p for g in self.optimizer.param_groups for p in g['params']])
         else:
             sync.step_done()
         self._rate = self.rate()

@@ -1191,8 +1191,11 @@ def qenc_bwd(rt, c, dq, vocab):
     ops.gemm_grouped([(da, c.hbuf, g_hh.w), (da, c.x[:, :E], g_ih.w)])     # dW_hh = dA^T h_prev, dW_ih = dA^T x
     ops.colsum(da, g_hh.b)
     ops.colsum(da, g_ih.b)
-    dx = torch.empty((R, (E + 3) // 4 * 4), dtype=_F32, device=dev)[:, :E]
-    ops.gemm(da, c.lp_ih.w, b_layout=1, out_f32=dx)
+    if E % 4 == 0:
+        dx = _resid_gemm(da, c.lp_ih.w, R, E, 4 * H, dev, b_layout=1)      # short M, K = 4H: split-K on all SMs
+    else:
+        dx = torch.empty((R, (E + 3) // 4 * 4), dtype=_F32, device=dev)[:, :E]
+        ops.gemm(da, c.lp_ih.w, b_layout=1, out_f32=dx)
     dtable = rt.zeros(vocab * E, dev).view(vocab, E)
     ops.embed_scatter_add(c.tokens, dx, dtable)
     return dtable, g_ih.w, g_ih.b, g_hh.w, g_hh.b

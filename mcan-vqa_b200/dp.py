@@ -294,8 +294,15 @@ def broadcast_params(model, group=None, src=0):
             dist.broadcast(b.data, src=src, group=group)
 
 
-def sync_all_grads(params, group=None):
-    """At-step mode: all-reduce(SUM) every existing .grad once (coalesced) and wait."""
+_presynced = [False]
+
+
+def sync_all_grads(params, group=None, before_clip=False):
+    """At-step mode: all-reduce(SUM) every existing .grad once (coalesced) and wait.
+
+    before_clip=True: the training loop calls this itself BEFORE clip_grad_norm_ (core/exec.py:186-191 clips before
+    optim.step()), so that the clip and the logged norms see the summed gradient; the overlay WarmupOptimizer.step()
+    then skips its own reduction for this step."""
     if world_size(group) == 1:
         return 0
     grads = [p.grad for p in params if p.grad is not None]
@@ -303,4 +310,12 @@ def sync_all_grads(params, group=None):
         return 0
     for w in _all_reduce_sum_async(grads, group):
         w.wait()
+    if before_clip:
+        _presynced[0] = True
     return len(grads)
+
+
+def consume_presync():
+    """True (once) when the gradients of this step were already reduced by sync_all_grads(..., before_clip=True)."""
+    done, _presynced[0] = _presynced[0], False
+    return done

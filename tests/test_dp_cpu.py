@@ -121,6 +121,17 @@ def _worker(rank, world, port, mode, out):
         model.zero_grad(set_to_none=True)
         sync.pending = []
         loss_fn(model(xs), ys).backward()      # after the refusal the counter restarts: a normal step works again
+    elif mode == "presync":
+        # the training loop reduces BEFORE clip_grad_norm_ (exec.py clips before optim.step()): step() must not reduce again
+        dp.attach(model, overlap=False)
+        sys.path.insert(0, ROOT)
+        from core.model.optim import WarmupOptimizer
+        opt = WarmupOptimizer(0.0, torch.optim.SGD(model.parameters(), lr=0.0), 64, 8)
+        loss_fn(model(xs), ys).backward()
+        assert dp.sync_all_grads(model.parameters(), before_clip=True) > 0
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1e9)       # sees the summed gradient
+        opt.step()
+        assert not dp.consume_presync()                              # consumed by step()
     else:
         dp.attach(model, overlap=False)
         sys.path.insert(0, ROOT)
@@ -144,9 +155,9 @@ def _worker(rank, world, port, mode, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode", ["overlap", "merged", "bf16", "buckets", "at_step", "plain_backbone", "second_backward"])
+@pytest.mark.parametrize("mode", ["overlap", "merged", "bf16", "buckets", "at_step", "plain_backbone", "second_backward", "presync"])
 def test_two_rank_sum_allreduce_equals_global_batch_gradient(mode, tmp_path):
     out = str(tmp_path / "ok.txt")
-    port = 29500 + (os.getpid() % 2000) + {"overlap": 0, "at_step": 1, "buckets": 2, "merged": 3, "bf16": 4, "plain_backbone": 5, "second_backward": 6}[mode]
+    port = 29500 + (os.getpid() % 2000) + {"overlap": 0, "at_step": 1, "buckets": 2, "merged": 3, "bf16": 4, "plain_backbone": 5, "second_backward": 6, "presync": 7}[mode]
     mp.spawn(_worker, args=(2, port, mode, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
