@@ -83,8 +83,12 @@ class Runtime(object):
         self.split = (PRECISION == "fp32") and not self.grad
         self.arena = None   # one zero-initialised flat buffer all gradients of a backward are carved from
         self.arena_w = None  # uninitialised flat buffer for the weight gradients that grouped launches write
+        self.scratch = None  # zero-initialised pool for the split-K outputs of the backward chain
+        self.scratch_off = 0
         self.arena_w_off = 0
         self.arena_w_mark = 0
+        self.scratch = torch.zeros(scratch_numel, dtype=_F32, device=device) if scratch_numel > 0 else None
+        self.scratch_off = 0
         self.arena_off = 0
         self.arena_mark = 0
         self.deferred = None   # list of (fn, args, kwargs) while weight-gradient work is being deferred
@@ -147,7 +151,17 @@ class Runtime(object):
         self.arena_w_off += n4
         return v
 
-    def use_arena(self, numel, device, store_numel=0):
+    def scratch_zeros(self, m, n, device):
+        """Zero-initialised fp32 [m, n] for a split-K output (an activation gradient, not a parameter gradient)."""
+        need = (m * n + 3) // 4 * 4
+        p = self.scratch
+        if p is None or p.device != device or self.scratch_off + need > p.numel():
+            return torch.zeros((m, n), dtype=_F32, device=device)
+        v = p[self.scratch_off:self.scratch_off + m * n].view(m, n)
+        self.scratch_off += need
+        return v
+
+    def use_arena(self, numel, device, store_numel=0, scratch_numel=0):
         """One memset instead of one per gradient tensor; contiguous per-layer slices for dp.py.  store_numel > 0:
         that many elements are an UNINITIALISED second arena for the weight gradients grouped launches write."""
         self.arena = torch.zeros(numel, dtype=_F32, device=device)
@@ -254,11 +268,12 @@ SPLITK_MIN_K = 2048
 SPLITK_FWD = os.environ.get("MCAN_SPLITK_FWD", "0") != "0"
 
 
-def _resid_gemm(a, w, M, N, K, dev, **kw):
+def _resid_gemm(a, w, M, N, K, dev, rt=None, **kw):
     """out_f32[M,N] = epilogue(a w^T) for an epilogue without ReLU / bf16 output; split-K when short and deep.
-    Used by the backward chain only (the forward's FFN2 applies the same rule when grad is enabled)."""
+    Used by the backward chain only (the forward's FFN2 applies the same rule when grad is enabled).  With `rt` the
+    zero-initialised output comes out of the Runtime's scratch pool (one memset per backward pass instead of one each)."""
     if SPLITK_MIN_K > 0 and M <= SPLITK_MAX_ROWS and K >= SPLITK_MIN_K:
-        out = torch.zeros((M, N), dtype=_F32, device=dev)
+        out = rt.scratch_zeros(M, N, dev) if rt is not None else torch.zeros((M, N), dtype=_F32, device=dev)
         ops.gemm(a, w, out_f32=out, accumulate=True, **kw)
     else:
         out = _empty(M, N, _F32, dev)
@@ -678,7 +693,7 @@ def att_bwd(rt, mh, c, dout, norm=None, dkv=None, need_dx=True):
     if c.mode == "self":
         rt.wgrad_gemm(dqkv, c.x_bf, g.w)
         if need_dx:
-            dx = _resid_gemm(dqkv, lp.w, M, H, 3 * H, dev, b_layout=1, resid=ds_f32)
+            dx = _resid_gemm(dqkv, lp.w, M, H, 3 * H, dev, rt=rt, b_layout=1, resid=ds_f32)
     else:
         rt.wgrad_gemm(dq, c.x_bf, g.rows_w(0, 1))
         if need_dx:
@@ -773,7 +788,7 @@ def mlp_bwd(rt, mlp, c, dout, norm=None, need_dx=True):
     rt.wgrad_gemm(dh, c.x_bf, g1.w)
     dx = None
     if need_dx:
-        dx = _resid_gemm(dh, c.lp1.w, M, c.lp1.k, c.lp1.n, dev, b_layout=1, resid=ds_f32)
+        dx = _resid_gemm(dh, c.lp1.w, M, c.lp1.k, c.lp1.n, dev, rt=rt, b_layout=1, resid=ds_f32)
     (w1, b1), = g1.per_param()
     (w2, b2), = g2.per_param()
     grads[mlp.fc.linear.weight], grads[mlp.fc.linear.bias] = w1, b1
@@ -899,7 +914,10 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
     # decoder layers) are written by grouped launches into an uninitialised arena; everything else starts from zero
     batched = set(id(w) for w, _ in ctx.lpkv.pairs) if L > 0 else set()
     store = sum(p.numel() + 8 for p in m.parameters() if p.dim() == 2 and id(p) not in batched) if GROUP_WGRADS else 0
-    rt.use_arena(total - store if store and STORE_WGRADS else total, dev, store_numel=store)
+    # split-K outputs of the question-side chain (2 per encoder layer + the batched K/V back-projection): one zero pool
+    rows_x = B * Sx
+    scratch = (2 * len(m.enc_list) + 1) * ((rows_x * H + 3) // 4 * 4) if (SPLITK_MIN_K > 0 and rows_x <= SPLITK_MAX_ROWS) else 0
+    rt.use_arena(total - store if store and STORE_WGRADS else total, dev, store_numel=store, scratch_numel=scratch)
     dkv_all = _empty(B * Sx, 2 * H * L, _BF16, dev)
     dy = dy_out
     overlap = OVERLAP_WGRAD and L > 0 and len(m.enc_list) > 0
@@ -923,7 +941,7 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
             rt.deferred = []
         rt.wgrad(ops.colsum, dkv_all, gkv.b)
         rt.wgrad_gemm(dkv_all, ctx.xenc_bf, gkv.w)
-        dx = _resid_gemm(dkv_all, ctx.lpkv.w, B * Sx, H, 2 * H * L, dev, b_layout=1, resid=dx_out)
+        dx = _resid_gemm(dkv_all, ctx.lpkv.w, B * Sx, H, 2 * H * L, dev, rt=rt, b_layout=1, resid=dx_out)
         gk = {}
         for (w, b), (gw, gb) in zip(ctx.lpkv.pairs, gkv.per_param()):
             gk[w], gk[b] = gw, gb
