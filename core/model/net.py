@@ -87,7 +87,7 @@ class _VQABase(nn.Module):
 
     def _features_impl(self, v, ques_ix):
         split = _blocks.PRECISION == "fp32" and not torch.is_grad_enabled()
-        if ques_ix.is_cuda and _blocks.lstm_supported(self.lstm, split):
+        if (ques_ix.is_cuda or _blocks.DRY_RUN) and _blocks.lstm_supported(self.lstm, split):
             # embedding + LSTM + make_mask(ques_ix) on the library's persistent LSTM kernels
             q, q_mask = _ag.question_encoder(self, ques_ix)
         else:

@@ -23,7 +23,7 @@ def cfg_get(opt, name, default=None):
 
 
 def _as_f32_2d(x, feat):
-    if not x.is_cuda:
+    if not x.is_cuda and not blocks.DRY_RUN:
         raise ops.capi.McanError("MCAN hot-path modules need CUDA tensors (no CPU fallback); got %s" % x.device)
     x2 = x.detach()
     if x2.dtype != torch.float32:

@@ -40,6 +40,11 @@ _F32 = torch.float32
 # happened since the last refresh.  Cost: one multi-tensor cast per step (refresh_params).
 ALWAYS_RECAST = True
 
+# Host-logic dry run (tests/test_hostlogic_cpu.py only): the C ABI is replaced by a stub that launches nothing, so the
+# whole launch chain -- buffer shapes, arenas, grouping, autograd plumbing -- runs on CPU tensors without a GPU.  The
+# product never sets this; with it unset every entry point still refuses CPU tensors (no fallback).
+DRY_RUN = False
+
 
 # "bf16": bf16 GEMM/attention operands, fp32 accumulation (training and default inference).
 # "fp32": split-precision INFERENCE -- every operand is carried as bf16 hi + lo and every product is
@@ -87,8 +92,6 @@ class Runtime(object):
         self.scratch_off = 0
         self.arena_w_off = 0
         self.arena_w_mark = 0
-        self.scratch = torch.zeros(scratch_numel, dtype=_F32, device=device) if scratch_numel > 0 else None
-        self.scratch_off = 0
         self.arena_off = 0
         self.arena_mark = 0
         self.deferred = None   # list of (fn, args, kwargs) while weight-gradient work is being deferred
@@ -172,6 +175,8 @@ class Runtime(object):
             self.arena_w = torch.empty(store_numel, dtype=_BF16 if WGRAD_BF16 else _F32, device=device)
         self.arena_w_off = 0
         self.arena_w_mark = 0
+        self.scratch = torch.zeros(scratch_numel, dtype=_F32, device=device) if scratch_numel > 0 else None
+        self.scratch_off = 0
 
     def zeros(self, n, device):
         n4 = (n + 3) // 4 * 4          # keep every carve-out 16-byte aligned
