@@ -318,10 +318,11 @@ int mcan_sigmoid_bce_bwd(const float* probs, const float* target, const float* g
  * weight gradients dW_hh = dA^T hbuf, dW_ih = dA^T x are plain GEMMs over R rows.
  *
  * mcan_embed_gather: x[row(b, t), :embed] = bf16(table[tokens[b, t]]) (pad columns and slot `steps` zero);
+ *   x_bf16_lo (optional, same layout) = bf16(value - x), for a split-precision input projection;
  *   mask[b * steps + t] = (tokens[b, t] == 0)  -- make_mask(ques_ix), net.py:99,135-137.  mask may be NULL.
  * mcan_embed_scatter_add: dtable[tokens[b, t], :] += dx[row(b, t), :embed] (fp32 atomics, dtable zero-initialised). */
 int mcan_embed_gather(const int64_t* tokens, const float* table, int32_t vocab, int32_t embed, int32_t batch,
-                      int32_t steps, void* x_bf16, int32_t ldx, uint8_t* mask, void* stream);
+                      int32_t steps, void* x_bf16, void* x_bf16_lo, int32_t ldx, uint8_t* mask, void* stream);
 int mcan_embed_scatter_add(const int64_t* tokens, const float* dx, int32_t lddx, int32_t vocab, int32_t embed,
                            int32_t batch, int32_t steps, float* dtable, void* stream);
 

@@ -462,7 +462,7 @@ class _QuestionEncoderRunner(_Runner):
         (tokens,) = acts
         net = self.module
         force = blocks._force(self.rt.grad)
-        lp_ih, lp_hh = net.lp_lstm_ih().get(force), net.lp_lstm_hh().get(force)
+        lp_ih, lp_hh = net.lp_lstm_ih().get(force, blocks.LSTM_SPLIT_INPUT), net.lp_lstm_hh().get(force)
         tok = tokens.detach().to(torch.int64).contiguous()
         q, mask, self.c = blocks.qenc_fwd(self.rt, net.embedding.weight.detach(), lp_ih, lp_hh, tok, self.rt.grad)
         self.non_differentiable = (mask,)

@@ -1162,6 +1162,7 @@ def head_bwd(rt, norm, c, g_a, g_probs, g_loss):
 LSTM_KERNEL = os.environ.get("MCAN_LSTM", "1") != "0"
 LSTM_HIDDEN = (128, 256, 512, 1024)
 LSTM_CHUNK = 64       # samples per persistent launch
+LSTM_SPLIT_INPUT = os.environ.get("MCAN_LSTM_SPLIT_INPUT", "1") != "0"
 
 
 def lstm_supported(lstm, split):
@@ -1181,9 +1182,17 @@ def qenc_fwd(rt, table, lp_ih, lp_hh, tokens, training):
     ldx = (E + 7) // 8 * 8
     x = torch.empty((R, ldx), dtype=_BF16, device=dev)
     mask = torch.empty(B * T, dtype=torch.uint8, device=dev)
-    ops.embed_gather(tokens, table, x, mask)
     xw = _empty(R, 4 * H, _F32, dev)
-    ops.gemm(x[:, :E], lp_ih.w, bias=lp_ih.b, out_f32=xw)
+    if LSTM_SPLIT_INPUT and lp_ih.w_lo is not None:
+        # The input projection feeds all T steps of the recurrence: it runs at split precision (x and W_ih as bf16
+        # hi + lo, three tensor-core products) -- K = 300, a few microseconds -- so that the only bf16 rounding inside
+        # the question encoder is that of W_hh and h in the recurrent product.
+        xlo = torch.empty((R, ldx), dtype=_BF16, device=dev)
+        ops.embed_gather(tokens, table, x, mask, xlo)
+        ops.gemm([x[:, :E], x[:, :E], xlo[:, :E]], [lp_ih.w, lp_ih.w_lo, lp_ih.w], bias=lp_ih.b, out_f32=xw)
+    else:
+        ops.embed_gather(tokens, table, x, mask)
+        ops.gemm(x[:, :E], lp_ih.w, bias=lp_ih.b, out_f32=xw)
     hbuf = _empty(R, H, _BF16, dev)
     q = _empty(B * T, H, _F32, dev)
     cbuf = _empty(R, H, _F32, dev) if training else None

@@ -187,8 +187,8 @@ SYMBOLS = {
     "mcan_gemm_grouped": (ctypes.c_int, [ctypes.POINTER(GemmGroupedArgs)]),
     "mcan_attn_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs)]),
     "mcan_attn_bwd": (ctypes.c_int, [ctypes.POINTER(AttnBwdArgs)]),
-    "mcan_embed_gather": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p,
-                                         c_void_p]),
+    "mcan_embed_gather": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int32,
+                                         c_void_p, c_void_p]),
     "mcan_embed_scatter_add": (ctypes.c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                               c_void_p]),
     "mcan_lstm_fwd": (ctypes.c_int, [ctypes.POINTER(LstmArgs)]),

@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(kLstmThreads, 1) lstm_bwd_kernel(const LstmPar
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 embed_gather_kernel(const long long* __restrict__ tokens, const float* __restrict__ table, int vocab, int E,
-                    int batch, int steps, bf16* __restrict__ x, int ldx, uint8_t* __restrict__ mask) {
+                    int batch, int steps, bf16* __restrict__ x, bf16* __restrict__ xlo, int ldx, uint8_t* __restrict__ mask) {
     pdl_launch_dependents();
     pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -397,15 +397,24 @@ embed_gather_kernel(const long long* __restrict__ tokens, const float* __restric
     if (row >= batch * S1) return;
     const int b = row / S1, s = row % S1;
     bf16* xr = x + (long long)row * ldx;
+    bf16* lr = xlo != nullptr ? xlo + (long long)row * ldx : nullptr;      // low-order halves: x = hi + lo to ~16 bits
     if (s == steps) {
-        for (int c = lane; c < ldx; c += 32) xr[c] = __float2bfloat16_rn(0.f);
+        for (int c = lane; c < ldx; c += 32) {
+            xr[c] = __float2bfloat16_rn(0.f);
+            if (lr) lr[c] = __float2bfloat16_rn(0.f);
+        }
         return;
     }
     long long tok = tokens[(long long)b * steps + s];
     if (lane == 0 && mask != nullptr) mask[b * steps + s] = tok == 0 ? 1 : 0;
     if (tok < 0 || tok >= vocab) tok = 0;       // (torch raises for an out-of-range index; never reached with valid data)
     const float* tr = table + tok * E;
-    for (int c = lane; c < ldx; c += 32) xr[c] = __float2bfloat16_rn(c < E ? tr[c] : 0.f);
+    for (int c = lane; c < ldx; c += 32) {
+        const float v = c < E ? tr[c] : 0.f;
+        const bf16 h = __float2bfloat16_rn(v);
+        xr[c] = h;
+        if (lr) lr[c] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
 }
 
 // dTable[token[b, t], :] += dx[row(b, t), :E]   (fp32 atomics on a zero-initialised gradient; slot T is skipped)
@@ -506,13 +515,14 @@ extern "C" int mcan_lstm_bwd(const mcan_lstm_args* a) {
 }
 
 extern "C" int mcan_embed_gather(const int64_t* tokens, const float* table, int32_t vocab, int32_t embed, int32_t batch,
-                                 int32_t steps, void* x_bf16, int32_t ldx, uint8_t* mask, void* stream) {
+                                 int32_t steps, void* x_bf16, void* x_bf16_lo, int32_t ldx, uint8_t* mask, void* stream) {
     MCAN_REQUIRE(tokens && table && x_bf16 && vocab > 0 && embed > 0 && batch > 0 && steps > 0 && ldx >= embed,
                  "mcan_embed_gather: bad args");
     const int rows = batch * (steps + 1);
     MCAN_CHECK_CUDA(launch_kernel(embed_gather_kernel, dim3((rows + 7) / 8), dim3(256), 0,
                                   reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<const long long*>(tokens), table,
-                                  (int)vocab, (int)embed, (int)batch, (int)steps, reinterpret_cast<bf16*>(x_bf16), (int)ldx, mask));
+                                  (int)vocab, (int)embed, (int)batch, (int)steps, reinterpret_cast<bf16*>(x_bf16),
+                                  reinterpret_cast<bf16*>(x_bf16_lo), (int)ldx, mask));
     return 0;
 }
 

@@ -370,7 +370,7 @@ def _lstm_barrier(device):
     return t
 
 
-def embed_gather(tokens, table, x, mask=None):
+def embed_gather(tokens, table, x, mask=None, x_lo=None):
     """x[b * (T + 1) + t, :E] = bf16(table[tokens[b, t]]) (slot T and the pad columns zero); mask[b * T + t] = tokens == 0."""
     lib = capi.load()
     _req(tokens, torch.int64, "embed tokens")
@@ -381,8 +381,12 @@ def embed_gather(tokens, table, x, mask=None):
         raise capi.McanError("embed_gather: tokens / table contiguous, x = full [B * (T + 1), ld] buffer")
     if mask is not None:
         _req(mask, torch.uint8, "embed mask")
+    if x_lo is not None:
+        _req2d(x_lo, _BF16, "embed x_lo")
+        if x_lo.shape != x.shape or x_lo.stride(0) != x.stride(0):
+            raise capi.McanError("embed_gather: x_lo must have the layout of x")
     capi.check(lib.mcan_embed_gather(tokens.data_ptr(), table.data_ptr(), table.shape[0], table.shape[1], B, T, x.data_ptr(),
-                                     x.stride(0), _ptr(mask), _stream()), "mcan_embed_gather")
+                                     _ptr(x_lo), x.stride(0), _ptr(mask), _stream()), "mcan_embed_gather")
 
 
 def embed_scatter_add(tokens, dx, dtable):
