@@ -13,8 +13,11 @@
 //   dQ = scale dS K,  dK = scale dS^T Q.
 #include "../../include/mcan_b200.h"
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace mcan {
+
+int device_num_sms();
 
 constexpr int kAttnMaxSeq = 128;
 constexpr int kAttnMaxNT = kAttnMaxSeq / 8;  // n-tiles of 8 keys
@@ -48,6 +51,8 @@ struct AttnParams {
     float* dbq;     // optional: += column sums of dq / dk / dv (the bias gradients of linear_q / _k / _v), fp32 [heads * D]
     float* dbk;
     float* dbv;
+    int prefetch;   // backward: persistent grid, the operand tiles of the CTA's NEXT (batch, head) are staged into a
+                    // second shared-memory set while the current one is being processed
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
@@ -457,33 +462,36 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
     pdl_wait();
     constexpr int LDS = D + 8;
     extern __shared__ __align__(16) uint8_t smem_attn[];
-    const int b = blockIdx.x / p.heads, h = blockIdx.x % p.heads;
     const int sqp = (p.sq + 15) & ~15, skp = (p.sk + 15) & ~15;
     const int ldp = skp + 8;
-    bf16* sQ = reinterpret_cast<bf16*>(smem_attn);
-    bf16* sdO = sQ + sqp * LDS;
-    bf16* sK = sdO + sqp * LDS;
-    bf16* sV = sK + skp * LDS;
-    bf16* sP = sV + skp * LDS;      // dropped probabilities Pd   [sqp][ldp]
-    bf16* sdS = sP + sqp * ldp;     // scale * dS                 [sqp][ldp]
-    uint8_t* sMask = reinterpret_cast<uint8_t*>(sdS + sqp * ldp);
-    // column sums of this (batch, head)'s dQ / dK / dV: the bias gradients of the three projections come out of this
-    // kernel (one shared-memory reduction per CTA, then one global atomic per column) instead of a column-sum pass
-    // over the [rows, 3H] gradient buffer per attention block
-    // [warp][dq | dk | dv][column], behind the mask bytes (16-byte aligned)
-    float (*s_cs)[3][D] = reinterpret_cast<float (*)[3][D]>(sMask + ((skp + 15) & ~15));
+    // operand tiles of one (batch, head): Q, dO [sqp][LDS], K, V [skp][LDS]; two such sets when prefetching
+    const int set_elems = (2 * sqp + 2 * skp) * LDS;
+    const int nsets = p.prefetch ? 2 : 1;
+    bf16* sets = reinterpret_cast<bf16*>(smem_attn);
+    bf16* sP = sets + (size_t)nsets * set_elems;   // dropped probabilities Pd   [sqp][ldp]
+    bf16* sdS = sP + sqp * ldp;                    // scale * dS                 [sqp][ldp]
+    uint8_t* sMaskAll = reinterpret_cast<uint8_t*>(sdS + sqp * ldp);      // [nsets][round16(skp)]
+    const int mask_stride = (skp + 15) & ~15;
+    // [warp][dq | dk | dv][column], behind the mask bytes (16-byte aligned): column sums of this (batch, head)'s
+    // dQ / dK / dV (optional: the bias gradients of the three projections)
+    float (*s_cs)[3][D] = reinterpret_cast<float (*)[3][D]>(sMaskAll + nsets * mask_stride);
     const bool want_cs = p.dbq != nullptr || p.dbk != nullptr || p.dbv != nullptr;
-    if (want_cs)
-        for (int i = threadIdx.x; i < 8 * 3 * D; i += blockDim.x) (&s_cs[0][0][0])[i] = 0.f;
 
-    stage_rows<D>(sQ, p.q + (long long)b * p.sq * p.ldq + h * D, p.ldq, p.sq, sqp);
-    stage_rows<D>(sdO, p.dout + (long long)b * p.sq * p.lddo + h * D, p.lddo, p.sq, sqp);
-    stage_rows<D>(sK, p.k + (long long)b * p.sk * p.ldk + h * D, p.ldk, p.sk, skp);
-    stage_rows<D>(sV, p.v + (long long)b * p.sk * p.ldv + h * D, p.ldv, p.sk, skp);
-    for (int i = threadIdx.x; i < skp; i += blockDim.x)
-        sMask[i] = (p.mask != nullptr && i < p.sk) ? p.mask[(long long)b * p.sk + i] : 0;
-    cp_async_wait_all();
-    __syncthreads();
+    const int items = p.batch * p.heads;
+    auto stage_item = [&](int item, int set) {
+        const int b = item / p.heads, h = item % p.heads;
+        bf16* sQ = sets + (size_t)set * set_elems;
+        bf16* sdO = sQ + sqp * LDS;
+        bf16* sK = sdO + sqp * LDS;
+        bf16* sV = sK + skp * LDS;
+        stage_rows<D>(sQ, p.q + (long long)b * p.sq * p.ldq + h * D, p.ldq, p.sq, sqp);
+        stage_rows<D>(sdO, p.dout + (long long)b * p.sq * p.lddo + h * D, p.lddo, p.sq, sqp);
+        stage_rows<D>(sK, p.k + (long long)b * p.sk * p.ldk + h * D, p.ldk, p.sk, skp);
+        stage_rows<D>(sV, p.v + (long long)b * p.sk * p.ldv + h * D, p.ldv, p.sk, skp);
+        uint8_t* sm = sMaskAll + set * mask_stride;
+        for (int i = threadIdx.x; i < skp; i += blockDim.x)
+            sm[i] = (p.mask != nullptr && i < p.sk) ? p.mask[(long long)b * p.sk + i] : 0;
+    };
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nwarps = blockDim.x >> 5;
@@ -492,6 +500,28 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
     const int nkt = EXACT ? NT : skp / 8;
     const uint32_t drop_seed =
         p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
+
+    if ((int)blockIdx.x < items) stage_item(blockIdx.x, 0);
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
+    const int set = p.prefetch ? (it & 1) : 0;
+    const int b = item / p.heads, h = item % p.heads;
+    bf16* sQ = sets + (size_t)set * set_elems;
+    bf16* sdO = sQ + sqp * LDS;
+    bf16* sK = sdO + sqp * LDS;
+    bf16* sV = sK + skp * LDS;
+    const uint8_t* sMask = sMaskAll + set * mask_stride;
+    if (!p.prefetch && it > 0) {      // single tile set and more items than CTAs: stage synchronously
+        __syncthreads();
+        stage_item(item, 0);
+    }
+    cp_async_wait_all();
+    __syncthreads();          // this item's tiles are in place; every warp is done with the previous item
+    if (p.prefetch && item + (int)gridDim.x < items) stage_item(item + gridDim.x, set ^ 1);   // in flight during this item
+    if (want_cs) {
+        for (int i = threadIdx.x; i < 8 * 3 * D; i += blockDim.x) (&s_cs[0][0][0])[i] = 0.f;
+        __syncthreads();
+    }
     uint32_t kmasked, kvalid;
     key_bits(sMask, nkt, p.sk, lane, kmasked, kvalid);
 
@@ -506,8 +536,8 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
         qk_tile<D, NT>(sdO, sV, mt, nkt, lane, dp);
 
         const int row0 = mt * 16 + g, row1 = row0 + 8;
-        const uint32_t base0 = (uint32_t)(((long long)blockIdx.x * p.sq + row0) * p.sk);
-        const uint32_t base1 = (uint32_t)(((long long)blockIdx.x * p.sq + row1) * p.sk);
+        const uint32_t base0 = (uint32_t)(((long long)item * p.sq + row0) * p.sk);
+        const uint32_t base1 = (uint32_t)(((long long)item * p.sq + row1) * p.sk);
         const bool v0 = row0 < p.sq, v1 = row1 < p.sq;
         float d0 = 0.f, d1 = 0.f;
         // acc = P (undropped); Pd = keep*P goes to smem; dp <- dP = keep * dPd;
@@ -644,15 +674,17 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
             }
         }
     }
+    }   // items of this CTA
 }
 
 static size_t attn_fwd_smem(int sq, int sk, int d) {
     const int sqp = (sq + 15) & ~15, skp = (sk + 15) & ~15;
     return (size_t)(sqp + 2 * skp) * (d + 8) * 2 + skp + 16;
 }
-static size_t attn_bwd_smem(int sq, int sk, int d) {
+static size_t attn_bwd_smem(int sq, int sk, int d, int nsets) {
     const int sqp = (sq + 15) & ~15, skp = (sk + 15) & ~15;
-    return (size_t)(2 * sqp + 2 * skp) * (d + 8) * 2 + (size_t)2 * sqp * (skp + 8) * 2 + skp + 16 + (size_t)8 * 3 * d * 4;
+    return (size_t)nsets * (2 * sqp + 2 * skp) * (d + 8) * 2 + (size_t)2 * sqp * (skp + 8) * 2 + (size_t)nsets * skp + 16 +
+           (size_t)8 * 3 * d * 4;
 }
 
 static int check_attn(const mcan_attn_args* a, const char* who) {
@@ -776,11 +808,21 @@ extern "C" int mcan_attn_bwd(const mcan_attn_bwd_args* a) {
     p.dv = reinterpret_cast<bf16*>(a->dv);
     p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
     p.dbq = a->dbq; p.dbk = a->dbk; p.dbv = a->dbv;
-    const size_t smem = attn_bwd_smem(a->fwd.sq, a->fwd.sk, a->fwd.head_dim);
+    // Large tiles (one CTA per SM anyway: the image self-attention, 124 KB): persistent grid, the operand tiles of the
+    // CTA's next (batch, head) are prefetched into a second shared-memory set while the current one is processed --
+    // the load phase (cp.async of Q, K, V, dO from HBM) no longer sits exposed in front of every CTA's compute.
+    // MCAN_ATTN_PREFETCH=0: one (batch, head) per CTA as before.
+    static const bool allow_prefetch = [] { const char* e = getenv("MCAN_ATTN_PREFETCH"); return !(e && e[0] == '0'); }();
+    const size_t single = attn_bwd_smem(a->fwd.sq, a->fwd.sk, a->fwd.head_dim, 1);
+    const size_t dbl = attn_bwd_smem(a->fwd.sq, a->fwd.sk, a->fwd.head_dim, 2);
+    const int items = a->fwd.batch * a->fwd.heads;
+    const int sms = device_num_sms();
+    p.prefetch = (allow_prefetch && single > 64 * 1024 && dbl <= 220 * 1024 && sms > 0 && items > sms) ? 1 : 0;
+    const size_t smem = p.prefetch ? dbl : single;
     const int mtiles = (a->fwd.sq + 15) / 16, ktiles = (a->fwd.sk + 15) / 16;
     const int mx = mtiles > ktiles ? mtiles : ktiles;
     const int threads = 32 * (mx < 8 ? mx : 8);
-    const int grid = a->fwd.batch * a->fwd.heads;
+    const int grid = p.prefetch ? sms : items;
     const int sk = a->fwd.sk;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(a->fwd.stream);
     if (a->fwd.head_dim == 64) MCAN_ATTN_DISPATCH(launch_attn_bwd, 64);
