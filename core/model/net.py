@@ -73,7 +73,7 @@ class _VQABase(nn.Module):
 
     def lp_lstm_ih(self):
         if getattr(self, "_lp_ih", None) is None:
-            self._lp_ih = LinearParams([(self.lstm.weight_ih_l0, self.lstm.bias_ih_l0)])
+            self._lp_ih = LinearParams([(self.lstm.weight_ih_l0, self.lstm.bias_ih_l0)], pad=64)
         return self._lp_ih
 
     def lp_lstm_hh(self):

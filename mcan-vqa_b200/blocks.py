@@ -271,6 +271,9 @@ SPLITK_MIN_K = 2048
 # box gave 7.98 ms/step without vs 8.01 ms with (the zero-fill of the output eats the gain), and an unsplit forward is
 # bit-reproducible run to run.  MCAN_SPLITK_FWD=1 switches them to split-K when gradients are being recorded.
 SPLITK_FWD = os.environ.get("MCAN_SPLITK_FWD", "0") != "0"
+# MCAN_SPLITK_HEAD=1: only the 64-row answer projection (64 x 3129 x 2048: 34.8 us unsplit, 33.6 us as 125 split-K units --
+# no gain, so off: the forward stays free of fp32 atomics)
+SPLITK_HEAD = os.environ.get("MCAN_SPLITK_HEAD", "0") != "0"
 
 
 def _resid_gemm(a, w, M, N, K, dev, rt=None, **kw):
@@ -305,8 +308,10 @@ class LinearParams(object):
     when a master's version counter or storage changes (optimizer step, load_state_dict, .cuda()).
     """
 
-    def __init__(self, pairs):
+    def __init__(self, pairs, pad=8):
         self.pairs = list(pairs)
+        self.pad = pad          # the copy's leading dimension is k rounded up to a multiple of `pad` (zero-filled columns)
+        self.w_full = None      # the copy with its pad columns: [n, ld]
         self.sizes = [w.shape[0] for w, _ in self.pairs]
         self.n = sum(self.sizes)
         self.k = self.pairs[0][0].shape[1]
@@ -338,8 +343,9 @@ class LinearParams(object):
     def _ensure_storage(self):
         dev = self.pairs[0][0].device
         if self.w is None or self.w.device != dev:
-            ld = (self.k + 7) // 8 * 8
-            self.w = torch.zeros((self.n, ld), dtype=_BF16, device=dev)[:, :self.k]
+            ld = (self.k + self.pad - 1) // self.pad * self.pad
+            self.w_full = torch.zeros((self.n, ld), dtype=_BF16, device=dev)
+            self.w = self.w_full[:, :self.k]
             self.b = torch.empty((self.n,), dtype=_F32, device=dev) if len(self.pairs) > 1 else None
             self.w_lo = None
             self._stamp = None
@@ -1123,7 +1129,7 @@ def head_fwd(rt, norm, lp, x, x2, target):
     if rt.split:
         logits = torch.empty((B, ldo), dtype=_F32, device=dev)[:, :lp.n]
         ops.gemm([ybf, ybf, ylo], [lp.w, lp.w_lo, lp.w], bias=lp.b, out_f32=logits)
-    elif rt.grad and SPLITK_FWD and SPLITK_MIN_K > 0 and B <= SPLITK_MAX_ROWS and lp.k >= SPLITK_MIN_K:
+    elif rt.grad and (SPLITK_FWD or SPLITK_HEAD) and SPLITK_MIN_K > 0 and B <= SPLITK_MAX_ROWS and lp.k >= SPLITK_MIN_K:
         # 64 rows x 3129 answers x K 2048 is one wave of 49 tiles that stream the 12.8 MB weight through 49 SMs
         # (45 us); split-K puts every SM on it (training only, like every split-K GEMM: fp32 atomics)
         logits = torch.zeros((B, ldo), dtype=_F32, device=dev)[:, :lp.n]
@@ -1179,7 +1185,7 @@ def qenc_fwd(rt, table, lp_ih, lp_hh, tokens, training):
     H, E = lp_hh.k, lp_ih.k
     R = B * S1
     c = Bag()
-    ldx = (E + 7) // 8 * 8
+    ldx = lp_ih.w.stride(0)         # E rounded up to a multiple of 64: no ragged 64-column chunk in any GEMM of the encoder
     x = torch.empty((R, ldx), dtype=_BF16, device=dev)
     mask = torch.empty(B * T, dtype=torch.uint8, device=dev)
     xw = _empty(R, 4 * H, _F32, dev)
@@ -1220,14 +1226,16 @@ def qenc_bwd(rt, c, dq, vocab):
         ops.lstm_bwd(dq[b0 * T:(b0 + nb) * T], c.lp_hh.w, c.hbuf[r0:r1], c.cbuf[r0:r1], c.gates[r0:r1], da[r0:r1],
                      batch=nb, steps=T, hidden=H)
     g_ih, g_hh = GradBuf(rt, c.lp_ih), GradBuf(rt, c.lp_hh)
-    ops.gemm_grouped([(da, c.hbuf, g_hh.w), (da, c.x[:, :E], g_ih.w)])     # dW_hh = dA^T h_prev, dW_ih = dA^T x
+    # dW_hh = dA^T h_prev and dW_ih = dA^T x as one grouped launch.  E = 300 is not a multiple of the epilogue's 64-column
+    # chunk: the GEMMs run on the zero-padded width (x and the W_ih copy are E_pad = 320 wide), so no chunk takes the
+    # per-element path (it cost 25 us per launch); dW_ih lands in a padded temporary and is copied out.
+    ldx = c.x.shape[1]
+    dwi = torch.empty((4 * H, ldx), dtype=_F32, device=dev)
+    ops.gemm_grouped([(da, c.hbuf, g_hh.w), (da, c.x, dwi)], accumulate=False)
+    g_ih.w.copy_(dwi[:, :E])
     ops.colsum(da, g_hh.b)
     ops.colsum(da, g_ih.b)
-    if E % 4 == 0:
-        dx = _resid_gemm(da, c.lp_ih.w, R, E, 4 * H, dev, b_layout=1)      # short M, K = 4H: split-K on all SMs
-    else:
-        dx = torch.empty((R, (E + 3) // 4 * 4), dtype=_F32, device=dev)[:, :E]
-        ops.gemm(da, c.lp_ih.w, b_layout=1, out_f32=dx)
+    dx = _resid_gemm(da, c.lp_ih.w_full, R, ldx, 4 * H, dev, b_layout=1)[:, :E]      # short M, K = 4H: split-K on all SMs
     dtable = rt.zeros(vocab * E, dev).view(vocab, E)
     ops.embed_scatter_add(c.tokens, dx, dtable)
     return dtable, g_ih.w, g_ih.b, g_hh.w, g_hh.b

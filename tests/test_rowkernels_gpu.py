@@ -398,7 +398,7 @@ def test_question_encoder_embedding_lstm_fwd_bwd(B, T, E, H, V):
     tokens[:, T - T // 3:] = 0                   # padding tokens (index 0), as in VQA questions
     tokens[0] = 0                                # a fully padded question
     assert blocks.lstm_supported(lstm, False)
-    lp_ih = LinearParams([(lstm.weight_ih_l0, lstm.bias_ih_l0)]).get(True, True)      # hi + lo: split-precision input projection
+    lp_ih = LinearParams([(lstm.weight_ih_l0, lstm.bias_ih_l0)], pad=64).get(True, True)      # hi + lo: split-precision input projection
     lp_hh = LinearParams([(lstm.weight_hh_l0, lstm.bias_hh_l0)]).get(True)
     rt = Runtime(True, 0.0)
     q, mask, ctx = blocks.qenc_fwd(rt, emb.weight.detach(), lp_ih, lp_hh, tokens, True)

@@ -31,7 +31,7 @@ for H in (1024, 512):
     emb = torch.nn.Embedding(V, E).cuda()
     lstm = torch.nn.LSTM(E, H, num_layers=1, batch_first=True).cuda()
     tokens = torch.randint(1, V, (B, T), device="cuda")
-    lp_ih = LinearParams([(lstm.weight_ih_l0, lstm.bias_ih_l0)]).get(True)
+    lp_ih = LinearParams([(lstm.weight_ih_l0, lstm.bias_ih_l0)], pad=64).get(True, True)
     lp_hh = LinearParams([(lstm.weight_hh_l0, lstm.bias_hh_l0)]).get(True)
     dq = torch.randn(B * T, H, device="cuda") * 0.1
     state = {}
