@@ -1118,6 +1118,11 @@ static TileCfg pick_tile(int64_t m, int64_t n, int64_t k, bool accumulate, int s
     double best_cost = 1e30;
     // deep split-K GEMMs (wgrad over 6400 rows): K splits fill the machine whatever the tile, so take
     // the tile with the highest arithmetic intensity (1024x1024x6400: 23.5 us vs 27.7 us with 256x128)
+    // ... but only with many rows: for the 896-row split-K dgrads of the question side (K 3072 / 4096 / 12288) the
+    // single-CTA 128 x 128 tile is 17-24 % faster than the pair tile (profiles/r02_tile_sweep.txt: 25.6 -> 21.5 us,
+    // 25.5 -> 19.3 us): 7 x 8 tiles x the K splits fill the machine without padding 896 rows to 1024
+    static const bool short_m_rule = [] { const char* e = getenv("MCAN_GEMM_SHORT_M_RULE"); return !(e && e[0] == '0'); }();
+    if (short_m_rule && accumulate && k >= 2048 && m < 1024 && m > 128 && m % 256 != 0 && n >= 256) return cand[3];
     if (accumulate && k >= 2048 && m >= 256 && n >= 256) return cand[0];
     for (int i = 0; i < 5; ++i) {
         const int cg = cand[i].cg, bn = cand[i].bn;
@@ -1269,8 +1274,20 @@ extern "C" int mcan_gemm(const mcan_gemm_args* a) {
     p.n = (int)a->n;
     p.k = (int)a->k;
     p.kblocks = (int)((a->k + BLOCK_K - 1) / BLOCK_K);
+    // Tile override for the fp32 + residual epilogue on short contractions (merge / q-projection dgrad of MCAN-large:
+    // 6400 x 1024 x 1024).  That epilogue moves 256 KB per 128 x 256 CTA tile through 8-byte accesses and is as long as
+    // the K = 1024 main loop; 100 CTA-pair tiles on 74 pairs leave most of it exposed, 200 single-CTA tiles on 148 SMs
+    // overlap it better: 33.5 -> 29.4 us (fp32 + resid), 37.6 -> 32.8 us (+ bias + dropout); for K >= 3072 the pair
+    // tile stays ahead (profiles/r02_epilogue_tile_choice.txt).  MCAN_GEMM_RESID_1CTA=0 switches the rule off.
+    static const bool resid_1cta = [] { const char* e = getenv("MCAN_GEMM_RESID_1CTA"); return !(e && e[0] == '0'); }();
+    int block_n_req = a->block_n, cg_req = a->cta_group;
+    if (resid_1cta && block_n_req == 0 && cg_req == 0 && a->out_f32 && a->resid && !a->accumulate && a->num_seg == 1 &&
+        a->k <= 1024 && a->n == 1024 && a->m >= 4096) {
+        cg_req = 1;
+        block_n_req = 256;
+    }
     GemmPlan plan;
-    if (int rc = plan_gemm(a->m, a->n, a->k, a->accumulate != 0, a->split_k, a->block_n, a->cta_group, sms, &plan))
+    if (int rc = plan_gemm(a->m, a->n, a->k, a->accumulate != 0, a->split_k, block_n_req, cg_req, sms, &plan))
         return rc;
     const int block_n = plan.block_n, cl = plan.cl, cg = plan.cg, mc = plan.mc;
     p.m_tiles = plan.m_tiles;

@@ -50,9 +50,10 @@ def test_plan_of_the_mcan_large_shapes(ops):
     assert (merge["block_n"], merge["cluster"], merge["full_tiles"], merge["units"]) == (256, 2, 74, 126)
     enc = ops.gemm_plan(896, 1024, 1024, sms=SMS)            # short M, short K: 128 x 64 single-CTA tiles
     assert (enc["block_n"], enc["cluster"]) == (64, 1) and enc["units"] == 7 * 16
-    enc_sk = ops.gemm_plan(896, 1024, 4096, accumulate=True, sms=SMS)    # split-K with the linear fused epilogue
-    assert enc_sk["block_n"] == 256 and enc_sk["cluster"] == 2 and enc_sk["splits"] >= 4
-    assert _tiles(enc_sk) * enc_sk["splits"] <= SMS // 2
+    enc_sk = ops.gemm_plan(896, 1024, 4096, accumulate=True, sms=SMS)    # split-K with the linear fused epilogue:
+    # short M -> single-CTA 128 x 128 tiles (profiles/r02_tile_sweep.txt), K splits fill the SMs
+    assert enc_sk["block_n"] == 128 and enc_sk["cluster"] == 1 and enc_sk["splits"] >= 2
+    assert _tiles(enc_sk) == 7 * 8 and _tiles(enc_sk) * enc_sk["splits"] <= 2 * SMS
     wgrad = ops.gemm_plan(1024, 1024, 6400, accumulate=True, sms=SMS)    # deep split-K: the 256 x 256 pair tile
     assert (wgrad["block_n"], wgrad["cluster"], wgrad["splits"]) == (256, 2, 4)
     head = ops.gemm_plan(64, 3129, 2048, sms=SMS)
