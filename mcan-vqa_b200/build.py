@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libmcan_b200.so")
-SOURCES = ["c_api.cu", "gemm_tcgen05.cu", "gemm_ln.cu", "attention.cu", "layernorm.cu", "attflat.cu", "elementwise.cu", "adamw.cu", "head.cu", "lstm.cu"]
+SOURCES = ["c_api.cu", "gemm_tcgen05.cu", "gemm_ln.cu", "attention.cu", "attention_tc.cu", "layernorm.cu", "attflat.cu", "elementwise.cu", "adamw.cu", "head.cu", "lstm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

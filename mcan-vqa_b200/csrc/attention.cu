@@ -12,48 +12,12 @@
 //   dV = Pd^T dO,  dPd = dO V^T,  dS = P o (m/(1-p) dPd - rowsum(Pd o dPd)), 0 where masked,
 //   dQ = scale dS K,  dK = scale dS^T Q.
 #include "../../include/mcan_b200.h"
-#include "common.cuh"
+#include "attention.cuh"
 #include <stdlib.h>
 
 namespace mcan {
 
 int device_num_sms();
-
-constexpr int kAttnMaxSeq = 128;
-constexpr int kAttnMaxNT = kAttnMaxSeq / 8;  // n-tiles of 8 keys
-constexpr float kLog2e = 1.4426950408889634f;
-
-struct AttnParams {
-    const bf16* q;
-    const bf16* k;
-    const bf16* v;
-    const bf16* q_lo;   // split precision ("bf16x3"): low-order halves, same addressing as q/k/v/out
-    const bf16* k_lo;
-    const bf16* v_lo;
-    bf16* out_lo;
-    long long ldq, ldk, ldv;
-    const uint8_t* mask;
-    bf16* out;
-    long long ldo;
-    int batch, heads, sq, sk;
-    float scale;
-    uint32_t drop_thr;
-    float drop_scale;
-    uint32_t drop_seed;
-    const uint32_t* drop_seed_dev;
-    // backward only
-    const bf16* dout;
-    long long lddo;
-    bf16* dq;
-    bf16* dk;
-    bf16* dv;
-    long long lddq, lddk, lddv;
-    float* dbq;     // optional: += column sums of dq / dk / dv (the bias gradients of linear_q / _k / _v), fp32 [heads * D]
-    float* dbk;
-    float* dbv;
-    int prefetch;   // backward: persistent grid, the operand tiles of the CTA's NEXT (batch, head) are staged into a
-                    // second shared-memory set while the current one is being processed
-};
 
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2,
                                         uint32_t& r3) {
@@ -787,6 +751,7 @@ extern "C" int mcan_attn_fwd(const mcan_attn_args* a) {
         MCAN_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
+    if (attn_tc_fwd_eligible(p, a->head_dim)) return attn_tc_fwd_launch(p, st);     // image-side queries: tcgen05 path
     if (a->head_dim == 64) MCAN_ATTN_DISPATCH(launch_attn_fwd, 64);
     MCAN_ATTN_DISPATCH(launch_attn_fwd, 128);
 }
@@ -808,6 +773,7 @@ extern "C" int mcan_attn_bwd(const mcan_attn_bwd_args* a) {
     p.dv = reinterpret_cast<bf16*>(a->dv);
     p.lddq = a->lddq; p.lddk = a->lddk; p.lddv = a->lddv;
     p.dbq = a->dbq; p.dbk = a->dbk; p.dbv = a->dbv;
+    if (attn_tc_bwd_eligible(p, a->fwd.head_dim)) return attn_tc_bwd_launch(p, reinterpret_cast<cudaStream_t>(a->fwd.stream));
     // Large tiles (one CTA per SM anyway: the image self-attention, 124 KB): persistent grid, the operand tiles of the
     // CTA's next (batch, head) are prefetched into a second shared-memory set while the current one is processed --
     // the load phase (cp.async of Q, K, V, dO from HBM) no longer sits exposed in front of every CTA's compute.

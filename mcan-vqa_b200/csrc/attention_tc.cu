@@ -1,0 +1,532 @@
+// A1 on the 5th-generation tensor cores: fused masked-softmax attention for the IMAGE side of MCAN
+// (100 query rows x 100 / 14 keys, head dim 64: mca.py:33-78), forward and backward.
+//
+// One CTA of 128 threads per (batch, head).  The (batch, head) problem is exactly one M = 128 UMMA tile:
+//   forward :  S = Q K^T            (tcgen05.mma, A/B K-major from shared memory, S in TMEM)
+//              thread r owns query row r = TMEM lane r: scale, masked_fill(-1e9), softmax (log2 domain) and
+//              dropout straight off tcgen05.ld -- no shuffles, no score fragment shared between threads;
+//              the un-normalised, dropped probabilities go to shared memory as the K-major A operand of
+//              O = P V              (V read MN-major from the same tile it was staged into);
+//              1 / rowsum and the dropout scale are applied to the O row when it leaves TMEM.
+//   backward:  S = Q K^T, dPd = dO V^T (both in TMEM), P recomputed, D_i = sum_j P_ij dP_ij,
+//              Pd and scale*dS written ONCE to shared memory; that one [query][key] tile is the K-major A
+//              operand of dQ = dS K and, read MN-major (= transposed), the A operand of dV = Pd^T dO and
+//              dK = dS^T Q.  dV / dK / dQ accumulate in the TMEM columns S and dPd occupied.
+// Operand tiles are [rows x 64] bf16 with the 128-byte swizzle (what a TMA box {64, rows} would produce); they
+// are filled with 16-byte cp.async from the strided [rows, 3H] activations (a head is a 128-byte column slice),
+// so no tensor map per call is needed.  Results leave through a swizzled staging tile with coalesced 16-byte stores.
+//
+// Occupancy: forward 46 KB shared memory + 128 TMEM columns -> 4 CTAs / SM; backward 112 KB + 256 columns ->
+// 2 CTAs / SM: one CTA's load and MMA phases hide behind the other's softmax arithmetic.
+//
+// Same arithmetic contract as attention.cu (which keeps every other shape: question side, head dim 128, split
+// precision, fused bias gradients): identical dropout hash and element indices, bf16 probabilities, fp32 softmax.
+#include "../../include/mcan_b200.h"
+#include "attention.cuh"
+#include <stdlib.h>
+
+namespace mcan {
+
+namespace {
+
+constexpr int kTcThreads = 128;
+constexpr int kTileRows = 128;                      // UMMA M
+constexpr float kMaskedLog2 = -1e9f * kLog2e;
+
+__device__ __forceinline__ void cp_async16_tc(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_tc() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// byte offset of 16-byte chunk c (8 bf16) of row r inside a [rows x 64] bf16 tile with the 128-byte swizzle
+// (tile base 1024-byte aligned)
+__device__ __forceinline__ uint32_t sw_off(int r, int c) {
+    return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4));
+}
+
+// rows x 64 bf16 from global (row stride ld elements) into a swizzled tile; rows [rows, rows_pad) are zero
+__device__ __forceinline__ void stage_tile(uint8_t* tile, const bf16* g, long long ld, int rows, int rows_pad) {
+    for (int i = threadIdx.x; i < rows_pad * 8; i += kTcThreads) {
+        const int r = i >> 3, c = i & 7;
+        uint8_t* dst = tile + sw_off(r, c);
+        if (r < rows) cp_async16_tc(dst, g + (long long)r * ld + c * 8);
+        else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+}
+// swizzled staging tile -> global rows (coalesced: 8 threads write one 128-byte row)
+__device__ __forceinline__ void unstage_tile(const uint8_t* tile, bf16* g, long long ld, int rows) {
+    for (int i = threadIdx.x; i < rows * 8; i += kTcThreads) {
+        const int r = i >> 3, c = i & 7;
+        *reinterpret_cast<uint4*>(g + (long long)r * ld + c * 8) = *reinterpret_cast<const uint4*>(tile + sw_off(r, c));
+    }
+}
+
+// keep bits of the 32 consecutive dropout elements idx .. idx+31 (bit j <=> element idx + j is kept); same hash and
+// indices as attention.cu / the host mirror (one mix32 per aligned pair of elements)
+__device__ __forceinline__ uint32_t keep32(uint32_t idx, uint32_t seed, uint32_t thr) {
+    uint32_t m = 0;
+    if ((idx & 1U) == 0) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t hsh = dropout_bits_pair((idx >> 1) + j, seed);
+            m |= ((hsh & 0xFFFFU) >= thr ? 1U : 0U) << (2 * j);
+            m |= ((hsh >> 16) >= thr ? 1U : 0U) << (2 * j + 1);
+        }
+    } else {
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) m |= (dropout_u16(idx + j, seed) >= thr ? 1U : 0U) << j;
+    }
+    return m;
+}
+
+// bit j <=> key 32*ch + j exists
+__device__ __forceinline__ uint32_t valid32(int sk, int ch) {
+    const int n = sk - 32 * ch;
+    return n >= 32 ? 0xFFFFFFFFU : (n <= 0 ? 0U : ((1U << n) - 1U));
+}
+
+// 32 fp32 accumulator columns of this thread's TMEM lane -> 16 packed bf16 pairs * mul -> four 16-byte chunks
+// c0 .. c0+3 of staging row `row`
+__device__ __forceinline__ void stage_acc32(uint32_t taddr, float mul, uint8_t* tile, int row, int c0, bool store) {
+    uint32_t r[32];
+    tmem_ld_32x32(taddr, r);
+    tmem_ld_wait();
+    if (store) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(r[8 * q + 0]) * mul, __uint_as_float(r[8 * q + 1]) * mul);
+            w.y = pack_bf16x2(__uint_as_float(r[8 * q + 2]) * mul, __uint_as_float(r[8 * q + 3]) * mul);
+            w.z = pack_bf16x2(__uint_as_float(r[8 * q + 4]) * mul, __uint_as_float(r[8 * q + 5]) * mul);
+            w.w = pack_bf16x2(__uint_as_float(r[8 * q + 6]) * mul, __uint_as_float(r[8 * q + 7]) * mul);
+            *reinterpret_cast<uint4*>(tile + sw_off(row, c0 + q)) = w;
+        }
+    }
+}
+
+// scaled, masked score in the log2 domain: masked key -> -1e9 * log2(e) (mca.py:70), key beyond sk -> -inf
+__device__ __forceinline__ float score_log2(uint32_t raw, float c, uint32_t mw, uint32_t vw, int j) {
+    float x = __uint_as_float(raw) * c;
+    x = ((mw >> j) & 1U) ? kMaskedLog2 : x;
+    return ((vw >> j) & 1U) ? x : -INFINITY;
+}
+
+struct TcSmall {            // behind the tiles
+    uint64_t bar[3];
+    uint32_t tmem_slot;
+    uint32_t pad;
+    uint32_t mask[4];       // bit (key & 31) of word key / 32 <=> key is masked
+};
+
+__device__ __forceinline__ void load_mask_words(const AttnParams& p, int b, uint32_t* words) {
+    const int key = threadIdx.x;
+    const bool m = p.mask != nullptr && key < p.sk && p.mask[(long long)b * p.sk + key] != 0;
+    const uint32_t w = __ballot_sync(0xFFFFFFFFU, m);
+    if ((threadIdx.x & 31) == 0) words[threadIdx.x >> 5] = w;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+template <bool DROP>
+__device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], float c, uint32_t mw, uint32_t vw, float mx,
+                                          uint32_t km, float& sum, uint8_t* prow_chunk, int row, int c0) {
+    uint32_t w[16];
+#pragma unroll
+    for (int j2 = 0; j2 < 16; ++j2) {
+        float e0 = exp2f(score_log2(r[2 * j2], c, mw, vw, 2 * j2) - mx);
+        float e1 = exp2f(score_log2(r[2 * j2 + 1], c, mw, vw, 2 * j2 + 1) - mx);
+        sum += e0 + e1;
+        if (DROP) {
+            e0 = ((km >> (2 * j2)) & 1U) ? e0 : 0.f;
+            e1 = ((km >> (2 * j2 + 1)) & 1U) ? e1 : 0.f;
+        }
+        w[j2] = pack_bf16x2(e0, e1);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(prow_chunk + sw_off(row, c0 + q)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnParams p, const int tmem_cols) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int item = blockIdx.x, b = item / p.heads, h = item % p.heads;
+    const int skp = (p.sk + 15) & ~15;
+    const int nkc = (skp + 63) >> 6;                       // 64-key chunks of the probability tile
+    const uint32_t kv_bytes = (uint32_t)skp * 128U;
+    const uint32_t qk_bytes = 16384U + kv_bytes, p_bytes = (uint32_t)nkc * 16384U;
+    uint8_t* sV = smem;
+    uint8_t* sQ = smem + kv_bytes;
+    uint8_t* sK = sQ + 16384;
+    uint8_t* sP = sQ;                                      // overlays Q and K once S is complete; later the O staging tile
+    TcSmall* sm = reinterpret_cast<TcSmall*>(sQ + (qk_bytes > p_bytes ? qk_bytes : p_bytes));
+
+    if (warp == 0) {
+        tmem_alloc(&sm->tmem_slot, (uint32_t)tmem_cols);
+        tmem_relinquish();
+    } else if (tid == 32) {
+        mbar_init(&sm->bar[0], 1);
+        mbar_init(&sm->bar[1], 1);
+        fence_mbar_init();
+    }
+    pdl_wait();
+    stage_tile(sQ, p.q + (long long)b * p.sq * p.ldq + h * 64, p.ldq, p.sq, kTileRows);
+    stage_tile(sK, p.k + (long long)b * p.sk * p.ldk + h * 64, p.ldk, p.sk, skp);
+    stage_tile(sV, p.v + (long long)b * p.sk * p.ldv + h * 64, p.ldv, p.sk, skp);
+    load_mask_words(p, b, sm->mask);
+    const uint32_t drop_seed = p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
+    cp_async_wait_all_tc();
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm->tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(kTileRows, skp, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base, make_smem_desc_sw128(smem_u32(sQ) + k * 32, 0, 1024),
+                          make_smem_desc_sw128(smem_u32(sK) + k * 32, 0, 1024), idesc, k > 0 ? 1U : 0U);
+            umma_commit(&sm->bar[0]);
+        }
+        __syncwarp();
+    }
+    mbar_wait(&sm->bar[0], 0);
+    tc_fence_after();
+
+    const int row = tid;                                   // query row == TMEM lane
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float c = p.scale * kLog2e;
+    const int nch = (skp + 31) >> 5;
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int ch = 0; ch < nch; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + ch * 32, r);
+        tmem_ld_wait();
+        const uint32_t mw = sm->mask[ch], vw = valid32(p.sk, ch);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, score_log2(r[j], c, mw, vw, j));
+    }
+    float sum = 0.f;
+    const uint32_t base = (uint32_t)(((long long)item * p.sq + row) * p.sk);
+#pragma unroll 1
+    for (int ch = 0; ch < nch; ++ch) {
+        uint32_t r[32];
+        tmem_ld_32x32(trow + ch * 32, r);
+        tmem_ld_wait();
+        const uint32_t mw = sm->mask[ch], vw = valid32(p.sk, ch);
+        uint8_t* chunk = sP + (ch >> 1) * 16384;
+        if (p.drop_thr != 0) {
+            const uint32_t km = keep32(base + 32U * ch, drop_seed, p.drop_thr);
+            fwd_chunk<true>(r, c, mw, vw, mx, km, sum, chunk, row, (ch & 1) * 4);
+        } else {
+            fwd_chunk<false>(r, c, mw, vw, mx, 0U, sum, chunk, row, (ch & 1) * 4);
+        }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();                                       // P complete, every thread is done reading S
+    tc_fence_after();
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(kTileRows, 64, 0, 1);
+            const int ksteps = skp >> 4;
+            for (int j = 0; j < ksteps; ++j)
+                umma_bf16(tmem_base, make_smem_desc_sw128(smem_u32(sP) + (j >> 2) * 16384 + (j & 3) * 32, 0, 1024),
+                          make_smem_desc_sw128(smem_u32(sV) + j * 2048, 8192, 1024), idesc, j > 0 ? 1U : 0U);
+            umma_commit(&sm->bar[1]);
+        }
+        __syncwarp();
+    }
+    mbar_wait(&sm->bar[1], 0);
+    tc_fence_after();
+    const float mul = p.drop_scale / sum;
+    stage_acc32(trow, mul, sP, row, 0, true);
+    stage_acc32(trow + 32, mul, sP, row, 4, true);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+    }
+    unstage_tile(sP, p.out + (long long)b * p.sq * p.ldo + h * 64, p.ldo, p.sq);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward.  NCH = compile-time number of 32-key chunks held in registers (1: <= 32 keys, 4: <= 128 keys)
+// ------------------------------------------------------------------------------------------------------------
+template <int NCH>
+__global__ void __launch_bounds__(kTcThreads, 2) attn_bwd_tc_kernel(const AttnParams p) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int item = blockIdx.x, b = item / p.heads, h = item % p.heads;
+    const int sqp = (p.sq + 15) & ~15, skp = (p.sk + 15) & ~15;
+    const int nkc = (skp + 63) >> 6;
+    const uint32_t q_bytes = (uint32_t)sqp * 128U, kv_bytes = (uint32_t)skp * 128U;
+    const uint32_t chunk_stride = q_bytes;                 // one 64-key chunk of the [query][key] tiles
+    uint8_t* sP = smem;                                    // dropped probabilities Pd   [nkc][sqp][64 keys]
+    uint8_t* sdS = sP + nkc * chunk_stride;                // scale * dS                 same layout
+    uint8_t* sQ = sdS + nkc * chunk_stride;
+    uint8_t* sdO = sQ + q_bytes;
+    uint8_t* sK = sdO + q_bytes;
+    uint8_t* sV = sK + kv_bytes;
+    // A operands are read as 128 rows: the bytes behind a shorter tile must exist (their products are never used)
+    const uint32_t tiles_end = (uint32_t)(sV - smem) + kv_bytes, a_end = (uint32_t)(sdO - smem) + 16384U;
+    TcSmall* sm = reinterpret_cast<TcSmall*>(smem + (tiles_end > a_end ? tiles_end : a_end));
+
+    if (warp == 0) {
+        tmem_alloc(&sm->tmem_slot, 256);
+        tmem_relinquish();
+    } else if (tid == 32) {
+        mbar_init(&sm->bar[0], 1);
+        mbar_init(&sm->bar[1], 1);
+        mbar_init(&sm->bar[2], 1);
+        fence_mbar_init();
+    }
+    pdl_wait();
+    stage_tile(sQ, p.q + (long long)b * p.sq * p.ldq + h * 64, p.ldq, p.sq, sqp);
+    stage_tile(sK, p.k + (long long)b * p.sk * p.ldk + h * 64, p.ldk, p.sk, skp);
+    stage_tile(sdO, p.dout + (long long)b * p.sq * p.lddo + h * 64, p.lddo, p.sq, sqp);
+    stage_tile(sV, p.v + (long long)b * p.sk * p.ldv + h * 64, p.ldv, p.sk, skp);
+    load_mask_words(p, b, sm->mask);
+    const uint32_t drop_seed = p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
+    cp_async_wait_all_tc();
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm->tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(kTileRows, skp, 0, 0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)      // S = Q K^T -> columns [0, skp)
+                umma_bf16(tmem_base, make_smem_desc_sw128(smem_u32(sQ) + k * 32, 0, 1024),
+                          make_smem_desc_sw128(smem_u32(sK) + k * 32, 0, 1024), idesc, k > 0 ? 1U : 0U);
+            umma_commit(&sm->bar[0]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)      // dPd = dO V^T -> columns [128, 128 + skp)
+                umma_bf16(tmem_base + 128, make_smem_desc_sw128(smem_u32(sdO) + k * 32, 0, 1024),
+                          make_smem_desc_sw128(smem_u32(sV) + k * 32, 0, 1024), idesc, k > 0 ? 1U : 0U);
+            umma_commit(&sm->bar[1]);
+        }
+        __syncwarp();
+    }
+
+    const int row = tid;
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const float c = p.scale * kLog2e;
+    uint32_t mw[NCH], vw[NCH], km[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        mw[ch] = sm->mask[ch];
+        vw[ch] = valid32(p.sk, ch);
+        km[ch] = 0xFFFFFFFFU;
+    }
+    if (p.drop_thr != 0) {                                 // (hash work overlaps the first MMAs)
+        const uint32_t base = (uint32_t)(((long long)item * p.sq + row) * p.sk);
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+            if (ch * 32 < skp) km[ch] = keep32(base + 32U * ch, drop_seed, p.drop_thr);
+    }
+
+    mbar_wait(&sm->bar[0], 0);
+    tc_fence_after();
+    float e[NCH * 32];                                     // the whole score row stays in registers
+    float mx = -INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+        if (ch * 32 < skp) {
+            uint32_t r[32];
+            tmem_ld_32x32(trow + ch * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                e[ch * 32 + j] = score_log2(r[j], c, mw[ch], vw[ch], j);
+                mx = fmaxf(mx, e[ch * 32 + j]);
+            }
+        }
+    float sum = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+        if (ch * 32 < skp) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                e[ch * 32 + j] = exp2f(e[ch * 32 + j] - mx);
+                sum += e[ch * 32 + j];
+            }
+        }
+    const float inv = 1.f / sum;
+
+    mbar_wait(&sm->bar[1], 0);
+    tc_fence_after();
+    // D_i = sum_j P_ij dP_ij with dP = keep / (1 - p) * dPd
+    float dsum = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+        if (ch * 32 < skp) {
+            uint32_t r[32];
+            tmem_ld_32x32(trow + 128 + ch * 32, r);
+            tmem_ld_wait();
+            const uint32_t live = km[ch] & vw[ch];          // (columns beyond skp hold whatever TMEM held before)
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dsum += ((live >> j) & 1U) ? e[ch * 32 + j] * __uint_as_float(r[j]) : 0.f;
+        }
+    const float di = dsum * inv * p.drop_scale;
+    const bool live_row = row < p.sq;
+    const float pk = live_row ? inv * p.drop_scale : 0.f;  // e -> dropped probability (kept elements)
+    const float ps = live_row ? inv * p.scale : 0.f;       // e -> P * scale
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+        if (ch * 32 < skp) {
+            uint32_t r[32];
+            tmem_ld_32x32(trow + 128 + ch * 32, r);
+            tmem_ld_wait();
+            uint32_t wp[16], wd[16];
+            const uint32_t dead = mw[ch] | ~vw[ch];
+#pragma unroll
+            for (int j2 = 0; j2 < 16; ++j2) {
+                float pd[2], ds[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int j = 2 * j2 + u;
+                    const bool keep = (km[ch] >> j) & 1U;
+                    const float ev = e[ch * 32 + j];
+                    pd[u] = keep ? ev * pk : 0.f;
+                    const float dp = keep ? __uint_as_float(r[j]) * p.drop_scale : 0.f;
+                    ds[u] = ((dead >> j) & 1U) ? 0.f : ev * ps * (dp - di);
+                }
+                wp[j2] = pack_bf16x2(pd[0], pd[1]);
+                wd[j2] = pack_bf16x2(ds[0], ds[1]);
+            }
+            if (row < sqp) {
+                uint8_t* cp = sP + (ch >> 1) * chunk_stride;
+                uint8_t* cd = sdS + (ch >> 1) * chunk_stride;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t off = sw_off(row, (ch & 1) * 4 + q);
+                    *reinterpret_cast<uint4*>(cp + off) = make_uint4(wp[4 * q], wp[4 * q + 1], wp[4 * q + 2], wp[4 * q + 3]);
+                    *reinterpret_cast<uint4*>(cd + off) = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
+                }
+            }
+        }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();                                       // Pd, dS complete; S and dPd have been read by everybody
+    tc_fence_after();
+    if (warp == 0) {
+        if (elect_one()) {
+            const uint32_t idesc_t = make_idesc_bf16(kTileRows, 64, 1, 1);
+            const uint32_t idesc_q = make_idesc_bf16(kTileRows, 64, 0, 1);
+            const int qsteps = sqp >> 4, ksteps = skp >> 4;
+            for (int j = 0; j < qsteps; ++j)     // dV[key] = Pd^T dO -> columns [0, 64)
+                umma_bf16(tmem_base, make_smem_desc_sw128(smem_u32(sP) + j * 2048, chunk_stride, 1024),
+                          make_smem_desc_sw128(smem_u32(sdO) + j * 2048, 8192, 1024), idesc_t, j > 0 ? 1U : 0U);
+            for (int j = 0; j < qsteps; ++j)     // dK[key] = (scale dS)^T Q -> columns [64, 128)
+                umma_bf16(tmem_base + 64, make_smem_desc_sw128(smem_u32(sdS) + j * 2048, chunk_stride, 1024),
+                          make_smem_desc_sw128(smem_u32(sQ) + j * 2048, 8192, 1024), idesc_t, j > 0 ? 1U : 0U);
+            for (int j = 0; j < ksteps; ++j)     // dQ[query] = (scale dS) K -> columns [128, 192)
+                umma_bf16(tmem_base + 128, make_smem_desc_sw128(smem_u32(sdS) + (j >> 2) * chunk_stride + (j & 3) * 32, 0, 1024),
+                          make_smem_desc_sw128(smem_u32(sK) + j * 2048, 8192, 1024), idesc_q, j > 0 ? 1U : 0U);
+            umma_commit(&sm->bar[2]);
+        }
+        __syncwarp();
+    }
+    mbar_wait(&sm->bar[2], 0);
+    tc_fence_after();
+    // every operand tile is free now: dV -> V tile, dK -> K tile, dQ -> Q tile (swizzled staging), then coalesced stores
+    stage_acc32(trow, 1.f, sV, row, 0, row < skp);
+    stage_acc32(trow + 32, 1.f, sV, row, 4, row < skp);
+    stage_acc32(trow + 64, 1.f, sK, row, 0, row < skp);
+    stage_acc32(trow + 96, 1.f, sK, row, 4, row < skp);
+    stage_acc32(trow + 128, 1.f, sQ, row, 0, row < sqp);
+    stage_acc32(trow + 160, 1.f, sQ, row, 4, row < sqp);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+    unstage_tile(sV, p.dv + (long long)b * p.sk * p.lddv + h * 64, p.lddv, p.sk);
+    unstage_tile(sK, p.dk + (long long)b * p.sk * p.lddk + h * 64, p.lddk, p.sk);
+    unstage_tile(sQ, p.dq + (long long)b * p.sq * p.lddq + h * 64, p.lddq, p.sq);
+}
+
+size_t fwd_tc_smem(int sk) {
+    const int skp = (sk + 15) & ~15, nkc = (skp + 63) >> 6;
+    const size_t kv = (size_t)skp * 128, qk = 16384 + kv, pb = (size_t)nkc * 16384;
+    return kv + (qk > pb ? qk : pb) + sizeof(TcSmall);
+}
+size_t bwd_tc_smem(int sq, int sk) {
+    const int sqp = (sq + 15) & ~15, skp = (sk + 15) & ~15, nkc = (skp + 63) >> 6;
+    const size_t qb = (size_t)sqp * 128, kv = (size_t)skp * 128;
+    const size_t tiles_end = 2 * nkc * qb + 2 * qb + 2 * kv, a_end = 2 * nkc * qb + qb + 16384;
+    return (tiles_end > a_end ? tiles_end : a_end) + sizeof(TcSmall);
+}
+
+bool tc_enabled() {
+    static const bool on = [] { const char* e = getenv("MCAN_ATTN_TC"); return !(e && e[0] == '0'); }();
+    return on;
+}
+bool tc_shape_ok(const AttnParams& p, int head_dim) {
+    return tc_enabled() && head_dim == 64 && p.sq >= 49 && p.sq <= 128 && p.sk >= 1 && p.sk <= 128 &&
+           p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0;
+}
+
+template <typename K>
+int prepare_kernel(K kernel, size_t smem, size_t* configured) {
+    if (smem > *configured) {
+        MCAN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MCAN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        *configured = smem;
+    }
+    return 0;
+}
+
+}  // namespace
+
+bool attn_tc_fwd_eligible(const AttnParams& p, int head_dim) {
+    return tc_shape_ok(p, head_dim) && p.q_lo == nullptr && p.out_lo == nullptr && p.ldo % 8 == 0 &&
+           ((uintptr_t)p.out & 15) == 0;
+}
+bool attn_tc_bwd_eligible(const AttnParams& p, int head_dim) {
+    return tc_shape_ok(p, head_dim) && p.dbq == nullptr && p.dbk == nullptr && p.dbv == nullptr && p.lddo % 8 == 0 &&
+           p.lddq % 8 == 0 && p.lddk % 8 == 0 && p.lddv % 8 == 0 &&
+           (((uintptr_t)p.dout | (uintptr_t)p.dq | (uintptr_t)p.dk | (uintptr_t)p.dv) & 15) == 0;
+}
+
+int attn_tc_fwd_launch(const AttnParams& p, cudaStream_t st) {
+    static size_t configured = 0;
+    const size_t smem = fwd_tc_smem(p.sk);
+    if (int rc = prepare_kernel(attn_fwd_tc_kernel, smem, &configured)) return rc;
+    const int skp = (p.sk + 15) & ~15;
+    const int tmem_cols = skp <= 64 ? 64 : 128;            // S (skp columns), then O (64 columns) in the same place
+    MCAN_CHECK_CUDA(launch_kernel(attn_fwd_tc_kernel, dim3(p.batch * p.heads), dim3(kTcThreads), smem, st, p, tmem_cols));
+    return 0;
+}
+
+int attn_tc_bwd_launch(const AttnParams& p, cudaStream_t st) {
+    const size_t smem = bwd_tc_smem(p.sq, p.sk);
+    const int skp = (p.sk + 15) & ~15;
+    if (skp <= 32) {
+        static size_t configured = 0;
+        if (int rc = prepare_kernel(attn_bwd_tc_kernel<1>, smem, &configured)) return rc;
+        MCAN_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel<1>, dim3(p.batch * p.heads), dim3(kTcThreads), smem, st, p));
+    } else {
+        static size_t configured = 0;
+        if (int rc = prepare_kernel(attn_bwd_tc_kernel<4>, smem, &configured)) return rc;
+        MCAN_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel<4>, dim3(p.batch * p.heads), dim3(kTcThreads), smem, st, p));
+    }
+    return 0;
+}
+
+}  // namespace mcan
