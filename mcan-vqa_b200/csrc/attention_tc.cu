@@ -29,15 +29,22 @@ namespace mcan {
 
 namespace {
 
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 128;                     // forward: thread = query row
+constexpr int kBwdThreads = 256;                    // backward: two threads per query row
 constexpr int kTileRows = 128;                      // UMMA M
 constexpr float kMaskedLog2 = -1e9f * kLog2e;
 
 __device__ __forceinline__ void cp_async16_tc(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all_tc() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// inputs are <= 0 here (score - row maximum): no range fix-up needed, tiny results flush to zero
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 // byte offset of 16-byte chunk c (8 bf16) of row r inside a [rows x 64] bf16 tile with the 128-byte swizzle
@@ -47,8 +54,9 @@ __device__ __forceinline__ uint32_t sw_off(int r, int c) {
 }
 
 // rows x 64 bf16 from global (row stride ld elements) into a swizzled tile; rows [rows, rows_pad) are zero
+template <int NTHREADS>
 __device__ __forceinline__ void stage_tile(uint8_t* tile, const bf16* g, long long ld, int rows, int rows_pad) {
-    for (int i = threadIdx.x; i < rows_pad * 8; i += kTcThreads) {
+    for (int i = threadIdx.x; i < rows_pad * 8; i += NTHREADS) {
         const int r = i >> 3, c = i & 7;
         uint8_t* dst = tile + sw_off(r, c);
         if (r < rows) cp_async16_tc(dst, g + (long long)r * ld + c * 8);
@@ -56,8 +64,9 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const bf16* g, long lo
     }
 }
 // swizzled staging tile -> global rows (coalesced: 8 threads write one 128-byte row)
+template <int NTHREADS>
 __device__ __forceinline__ void unstage_tile(const uint8_t* tile, bf16* g, long long ld, int rows) {
-    for (int i = threadIdx.x; i < rows * 8; i += kTcThreads) {
+    for (int i = threadIdx.x; i < rows * 8; i += NTHREADS) {
         const int r = i >> 3, c = i & 7;
         *reinterpret_cast<uint4*>(g + (long long)r * ld + c * 8) = *reinterpret_cast<const uint4*>(tile + sw_off(r, c));
     }
@@ -130,18 +139,37 @@ __device__ __forceinline__ void load_mask_words(const AttnParams& p, int b, uint
 // ------------------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------------------
-template <bool DROP>
+// One 32-key chunk of this thread's score row: e = exp2(score - max), row sum, dropout, bf16 pack, four 16-byte stores
+// into the K-major probability tile.
+//   FAST: no key of the chunk is masked or beyond sk (CTA-uniform: the key mask is per sample) -> no selects, one FFMA
+//         + one MUFU per score.  The general path keeps the reference's masked_fill(-1e9) exact: a fully masked row
+//         has every score EQUAL to the row maximum, i.e. uniform probabilities (mca.py:70-75).
+//   DM:   0 no dropout; 1 one hash per aligned pair of elements, compared in place (no bitmask); 2 keep bitmask `km`
+//         (odd element offsets: odd sk)
+template <bool FAST, int DM>
 __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], float c, uint32_t mw, uint32_t vw, float mx,
-                                          uint32_t km, float& sum, uint8_t* prow_chunk, int row, int c0) {
+                                          uint32_t km_or_pair, uint32_t seed, uint32_t thr16, float& sum0, float& sum1,
+                                          uint8_t* prow_chunk, int row, int c0) {
     uint32_t w[16];
 #pragma unroll
     for (int j2 = 0; j2 < 16; ++j2) {
-        float e0 = exp2f(score_log2(r[2 * j2], c, mw, vw, 2 * j2) - mx);
-        float e1 = exp2f(score_log2(r[2 * j2 + 1], c, mw, vw, 2 * j2 + 1) - mx);
-        sum += e0 + e1;
-        if (DROP) {
-            e0 = ((km >> (2 * j2)) & 1U) ? e0 : 0.f;
-            e1 = ((km >> (2 * j2 + 1)) & 1U) ? e1 : 0.f;
+        float e0, e1;
+        if (FAST) {
+            e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j2]), c, -mx));
+            e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j2 + 1]), c, -mx));
+        } else {
+            e0 = ex2_approx(score_log2(r[2 * j2], c, mw, vw, 2 * j2) - mx);
+            e1 = ex2_approx(score_log2(r[2 * j2 + 1], c, mw, vw, 2 * j2 + 1) - mx);
+        }
+        sum0 += e0;
+        sum1 += e1;
+        if (DM == 1) {
+            const uint32_t hsh = dropout_bits_pair(km_or_pair + j2, seed);
+            e0 = ((hsh << 16) >= thr16) ? e0 : 0.f;      // low 16 bits >= thr
+            e1 = (hsh >= thr16) ? e1 : 0.f;              // high 16 bits >= thr
+        } else if (DM == 2) {
+            e0 = ((km_or_pair >> (2 * j2)) & 1U) ? e0 : 0.f;
+            e1 = ((km_or_pair >> (2 * j2 + 1)) & 1U) ? e1 : 0.f;
         }
         w[j2] = pack_bf16x2(e0, e1);
     }
@@ -174,12 +202,14 @@ __global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnPa
         fence_mbar_init();
     }
     pdl_wait();
-    stage_tile(sQ, p.q + (long long)b * p.sq * p.ldq + h * 64, p.ldq, p.sq, kTileRows);
-    stage_tile(sK, p.k + (long long)b * p.sk * p.ldk + h * 64, p.ldk, p.sk, skp);
-    stage_tile(sV, p.v + (long long)b * p.sk * p.ldv + h * 64, p.ldv, p.sk, skp);
+    stage_tile<kTcThreads>(sQ, p.q + (long long)b * p.sq * p.ldq + h * 64, p.ldq, p.sq, kTileRows);
+    stage_tile<kTcThreads>(sK, p.k + (long long)b * p.sk * p.ldk + h * 64, p.ldk, p.sk, skp);
+    cp_async_commit();
+    stage_tile<kTcThreads>(sV, p.v + (long long)b * p.sk * p.ldv + h * 64, p.ldv, p.sk, skp);   // needed only by the second MMA
+    cp_async_commit();
     load_mask_words(p, b, sm->mask);
     const uint32_t drop_seed = p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
-    cp_async_wait_all_tc();
+    cp_async_wait_group<1>();                              // Q and K have landed
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -197,13 +227,16 @@ __global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnPa
         }
         __syncwarp();
     }
-    mbar_wait(&sm->bar[0], 0);
-    tc_fence_after();
-
     const int row = tid;                                   // query row == TMEM lane
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
     const float c = p.scale * kLog2e;
     const int nch = (skp + 31) >> 5;
+    const uint32_t base = (uint32_t)(((long long)item * p.sq + row) * p.sk);
+    const uint32_t thr16 = p.drop_thr << 16;
+    const int dm = p.drop_thr == 0 ? 0 : ((base & 1U) ? 2 : 1);
+    mbar_wait(&sm->bar[0], 0);
+    tc_fence_after();
+
     float mx = -INFINITY;
 #pragma unroll 1
     for (int ch = 0; ch < nch; ++ch) {
@@ -211,11 +244,17 @@ __global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnPa
         tmem_ld_32x32(trow + ch * 32, r);
         tmem_ld_wait();
         const uint32_t mw = sm->mask[ch], vw = valid32(p.sk, ch);
+        if ((mw | ~vw) == 0U) {
+            float m = __uint_as_float(r[0]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, score_log2(r[j], c, mw, vw, j));
+            for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+            mx = fmaxf(mx, m * c);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, score_log2(r[j], c, mw, vw, j));
+        }
     }
-    float sum = 0.f;
-    const uint32_t base = (uint32_t)(((long long)item * p.sq + row) * p.sk);
+    float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll 1
     for (int ch = 0; ch < nch; ++ch) {
         uint32_t r[32];
@@ -223,16 +262,24 @@ __global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnPa
         tmem_ld_wait();
         const uint32_t mw = sm->mask[ch], vw = valid32(p.sk, ch);
         uint8_t* chunk = sP + (ch >> 1) * 16384;
-        if (p.drop_thr != 0) {
-            const uint32_t km = keep32(base + 32U * ch, drop_seed, p.drop_thr);
-            fwd_chunk<true>(r, c, mw, vw, mx, km, sum, chunk, row, (ch & 1) * 4);
+        const int c0 = (ch & 1) * 4;
+        const bool fast = (mw | ~vw) == 0U;
+        const uint32_t idx = base + 32U * ch;
+#define MCAN_FWD_CHUNK(F, D, KM) fwd_chunk<F, D>(r, c, mw, vw, mx, KM, drop_seed, thr16, sum0, sum1, chunk, row, c0)
+        if (dm == 1) {
+            if (fast) MCAN_FWD_CHUNK(true, 1, idx >> 1); else MCAN_FWD_CHUNK(false, 1, idx >> 1);
+        } else if (dm == 0) {
+            if (fast) MCAN_FWD_CHUNK(true, 0, 0U); else MCAN_FWD_CHUNK(false, 0, 0U);
         } else {
-            fwd_chunk<false>(r, c, mw, vw, mx, 0U, sum, chunk, row, (ch & 1) * 4);
+            const uint32_t km = keep32(idx, drop_seed, p.drop_thr);
+            MCAN_FWD_CHUNK(false, 2, km);
         }
+#undef MCAN_FWD_CHUNK
     }
+    cp_async_wait_group<0>();                              // this thread's part of V
     fence_proxy_async_smem();
     tc_fence_before();
-    __syncthreads();                                       // P complete, every thread is done reading S
+    __syncthreads();                                       // P and V complete, every thread is done reading S
     tc_fence_after();
     if (warp == 0) {
         if (elect_one()) {
@@ -247,7 +294,7 @@ __global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnPa
     }
     mbar_wait(&sm->bar[1], 0);
     tc_fence_after();
-    const float mul = p.drop_scale / sum;
+    const float mul = p.drop_scale / (sum0 + sum1);
     stage_acc32(trow, mul, sP, row, 0, true);
     stage_acc32(trow + 32, mul, sP, row, 4, true);
     tc_fence_before();
@@ -256,17 +303,71 @@ __global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnPa
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
     }
-    unstage_tile(sP, p.out + (long long)b * p.sq * p.ldo + h * 64, p.ldo, p.sq);
+    unstage_tile<kTcThreads>(sP, p.out + (long long)b * p.sq * p.ldo + h * 64, p.ldo, p.sq);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// backward.  NCH = compile-time number of 32-key chunks held in registers (1: <= 32 keys, 4: <= 128 keys)
+// backward: 256 threads, TWO threads per query row (warps 0-3: keys 0..63, warps 4-7: keys 64..127 of the same TMEM
+// lanes); row maximum, row sum and D_i are combined through a scratch area in shared memory (the V tile, which is
+// free once dPd is complete).  64 scores per thread stay in registers.
 // ------------------------------------------------------------------------------------------------------------
-template <int NCH>
-__global__ void __launch_bounds__(kTcThreads, 2) attn_bwd_tc_kernel(const AttnParams p) {
+// scores of one chunk: FAST -> raw accumulator values (scaled later by one FFMA), else scaled / masked log2 scores
+template <bool FAST>
+__device__ __forceinline__ float bwd_scores(const uint32_t (&r)[32], float (&e)[32], float c, uint32_t mw, uint32_t vw) {
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        e[j] = FAST ? __uint_as_float(r[j]) : score_log2(r[j], c, mw, vw, j);
+        m = fmaxf(m, e[j]);
+    }
+    return FAST ? m * c : m;
+}
+template <bool FAST>
+__device__ __forceinline__ void bwd_exp(float (&e)[32], float c, float mx, float& s0, float& s1) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        e[j] = FAST ? ex2_approx(fmaf(e[j], c, -mx)) : ex2_approx(e[j] - mx);
+        e[j + 1] = FAST ? ex2_approx(fmaf(e[j + 1], c, -mx)) : ex2_approx(e[j + 1] - mx);
+        s0 += e[j];
+        s1 += e[j + 1];
+    }
+}
+// Pd = keep * P / (1 - p) and scale * dS = scale * P o (dP - D_i) for one chunk -> the two [query][key] tiles
+template <bool FAST>
+__device__ __forceinline__ void bwd_chunk_out(const uint32_t (&r)[32], const float (&e)[32], uint32_t km, uint32_t dead,
+                                              float pk, float ps, float drop_scale, float di, uint8_t* cp, uint8_t* cd,
+                                              int row, int c0, bool store) {
+    uint32_t wp[16], wd[16];
+#pragma unroll
+    for (int j2 = 0; j2 < 16; ++j2) {
+        float pd[2], ds[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int j = 2 * j2 + u;
+            const bool keep = (km >> j) & 1U;
+            pd[u] = keep ? e[j] * pk : 0.f;
+            const float t = keep ? fmaf(__uint_as_float(r[j]), drop_scale, -di) : -di;
+            ds[u] = e[j] * ps * t;
+            if (!FAST) ds[u] = ((dead >> j) & 1U) ? 0.f : ds[u];
+        }
+        wp[j2] = pack_bf16x2(pd[0], pd[1]);
+        wd[j2] = pack_bf16x2(ds[0], ds[1]);
+    }
+    if (store) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t off = sw_off(row, c0 + q);
+            *reinterpret_cast<uint4*>(cp + off) = make_uint4(wp[4 * q], wp[4 * q + 1], wp[4 * q + 2], wp[4 * q + 3]);
+            *reinterpret_cast<uint4*>(cd + off) = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_tc_kernel(const AttnParams p) {
     pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int qw = warp & 3, half = warp >> 2;             // TMEM lane quarter, key half
     const int item = blockIdx.x, b = item / p.heads, h = item % p.heads;
     const int sqp = (p.sq + 15) & ~15, skp = (p.sk + 15) & ~15;
     const int nkc = (skp + 63) >> 6;
@@ -292,13 +393,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) attn_bwd_tc_kernel(const AttnPa
         fence_mbar_init();
     }
     pdl_wait();
-    stage_tile(sQ, p.q + (long long)b * p.sq * p.ldq + h * 64, p.ldq, p.sq, sqp);
-    stage_tile(sK, p.k + (long long)b * p.sk * p.ldk + h * 64, p.ldk, p.sk, skp);
-    stage_tile(sdO, p.dout + (long long)b * p.sq * p.lddo + h * 64, p.lddo, p.sq, sqp);
-    stage_tile(sV, p.v + (long long)b * p.sk * p.ldv + h * 64, p.ldv, p.sk, skp);
-    load_mask_words(p, b, sm->mask);
+    stage_tile<kBwdThreads>(sQ, p.q + (long long)b * p.sq * p.ldq + h * 64, p.ldq, p.sq, sqp);
+    stage_tile<kBwdThreads>(sK, p.k + (long long)b * p.sk * p.ldk + h * 64, p.ldk, p.sk, skp);
+    stage_tile<kBwdThreads>(sdO, p.dout + (long long)b * p.sq * p.lddo + h * 64, p.lddo, p.sq, sqp);
+    stage_tile<kBwdThreads>(sV, p.v + (long long)b * p.sk * p.ldv + h * 64, p.ldv, p.sk, skp);
+    cp_async_commit();
+    if (warp < 4) load_mask_words(p, b, sm->mask);
     const uint32_t drop_seed = p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
-    cp_async_wait_all_tc();
+    cp_async_wait_group<0>();
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -312,112 +414,87 @@ __global__ void __launch_bounds__(kTcThreads, 2) attn_bwd_tc_kernel(const AttnPa
             for (int k = 0; k < 4; ++k)      // S = Q K^T -> columns [0, skp)
                 umma_bf16(tmem_base, make_smem_desc_sw128(smem_u32(sQ) + k * 32, 0, 1024),
                           make_smem_desc_sw128(smem_u32(sK) + k * 32, 0, 1024), idesc, k > 0 ? 1U : 0U);
-            umma_commit(&sm->bar[0]);
 #pragma unroll
             for (int k = 0; k < 4; ++k)      // dPd = dO V^T -> columns [128, 128 + skp)
                 umma_bf16(tmem_base + 128, make_smem_desc_sw128(smem_u32(sdO) + k * 32, 0, 1024),
                           make_smem_desc_sw128(smem_u32(sV) + k * 32, 0, 1024), idesc, k > 0 ? 1U : 0U);
-            umma_commit(&sm->bar[1]);
+            umma_commit(&sm->bar[0]);
         }
         __syncwarp();
     }
 
-    const int row = tid;
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int row = qw * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(qw * 32) << 16);
     const float c = p.scale * kLog2e;
-    uint32_t mw[NCH], vw[NCH], km[NCH];
+    // this thread's two 32-key chunks: 2 * half, 2 * half + 1
+    uint32_t mw[2], vw[2], km[2];
+    bool act[2], fast[2];
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch) {
-        mw[ch] = sm->mask[ch];
-        vw[ch] = valid32(p.sk, ch);
-        km[ch] = 0xFFFFFFFFU;
+    for (int i = 0; i < 2; ++i) {
+        const int ch = 2 * half + i;
+        act[i] = ch * 32 < skp;
+        mw[i] = sm->mask[ch];
+        vw[i] = valid32(p.sk, ch);
+        fast[i] = (mw[i] | ~vw[i]) == 0U;
+        km[i] = 0xFFFFFFFFU;
     }
-    if (p.drop_thr != 0) {                                 // (hash work overlaps the first MMAs)
+    if (p.drop_thr != 0) {                                 // (the hash work overlaps the first MMAs)
         const uint32_t base = (uint32_t)(((long long)item * p.sq + row) * p.sk);
 #pragma unroll
-        for (int ch = 0; ch < NCH; ++ch)
-            if (ch * 32 < skp) km[ch] = keep32(base + 32U * ch, drop_seed, p.drop_thr);
+        for (int i = 0; i < 2; ++i)
+            if (act[i]) km[i] = keep32(base + 32U * (2 * half + i), drop_seed, p.drop_thr);
     }
 
-    mbar_wait(&sm->bar[0], 0);
+    mbar_wait(&sm->bar[0], 0);                             // S and dPd complete (V is free from here on)
     tc_fence_after();
-    float e[NCH * 32];                                     // the whole score row stays in registers
-    float mx = -INFINITY;
+    float* xch = reinterpret_cast<float*>(sV);             // [3][2 halves][128 rows]: max | sum | D partials
+    float e[2][32];
+    float mloc = -INFINITY;
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-        if (ch * 32 < skp) {
+    for (int i = 0; i < 2; ++i)
+        if (act[i]) {
             uint32_t r[32];
-            tmem_ld_32x32(trow + ch * 32, r);
+            tmem_ld_32x32(trow + (2 * half + i) * 32, r);
             tmem_ld_wait();
+            mloc = fmaxf(mloc, fast[i] ? bwd_scores<true>(r, e[i], c, mw[i], vw[i]) : bwd_scores<false>(r, e[i], c, mw[i], vw[i]));
+        }
+    xch[half * 128 + row] = mloc;
+    __syncthreads();
+    const float mx = fmaxf(xch[row], xch[128 + row]);
+    float s0 = 0.f, s1 = 0.f, d0 = 0.f, d1 = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                e[ch * 32 + j] = score_log2(r[j], c, mw[ch], vw[ch], j);
-                mx = fmaxf(mx, e[ch * 32 + j]);
+    for (int i = 0; i < 2; ++i)
+        if (act[i]) {
+            if (fast[i]) bwd_exp<true>(e[i], c, mx, s0, s1); else bwd_exp<false>(e[i], c, mx, s0, s1);
+            uint32_t r[32];
+            tmem_ld_32x32(trow + 128 + (2 * half + i) * 32, r);
+            tmem_ld_wait();
+            const uint32_t live = km[i] & vw[i];           // (columns beyond skp hold whatever TMEM held before)
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+                d0 += ((live >> j) & 1U) ? e[i][j] * __uint_as_float(r[j]) : 0.f;
+                d1 += ((live >> (j + 1)) & 1U) ? e[i][j + 1] * __uint_as_float(r[j + 1]) : 0.f;
             }
         }
-    float sum = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-        if (ch * 32 < skp) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                e[ch * 32 + j] = exp2f(e[ch * 32 + j] - mx);
-                sum += e[ch * 32 + j];
-            }
-        }
-    const float inv = 1.f / sum;
-
-    mbar_wait(&sm->bar[1], 0);
-    tc_fence_after();
-    // D_i = sum_j P_ij dP_ij with dP = keep / (1 - p) * dPd
-    float dsum = 0.f;
-#pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-        if (ch * 32 < skp) {
-            uint32_t r[32];
-            tmem_ld_32x32(trow + 128 + ch * 32, r);
-            tmem_ld_wait();
-            const uint32_t live = km[ch] & vw[ch];          // (columns beyond skp hold whatever TMEM held before)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) dsum += ((live >> j) & 1U) ? e[ch * 32 + j] * __uint_as_float(r[j]) : 0.f;
-        }
-    const float di = dsum * inv * p.drop_scale;
+    xch[256 + half * 128 + row] = s0 + s1;
+    xch[512 + half * 128 + row] = d0 + d1;
+    __syncthreads();
+    const float inv = 1.f / (xch[256 + row] + xch[384 + row]);
+    const float di = (xch[512 + row] + xch[640 + row]) * inv * p.drop_scale;     // D_i = sum_j P_ij dP_ij
     const bool live_row = row < p.sq;
     const float pk = live_row ? inv * p.drop_scale : 0.f;  // e -> dropped probability (kept elements)
     const float ps = live_row ? inv * p.scale : 0.f;       // e -> P * scale
 #pragma unroll
-    for (int ch = 0; ch < NCH; ++ch)
-        if (ch * 32 < skp) {
+    for (int i = 0; i < 2; ++i)
+        if (act[i]) {
             uint32_t r[32];
-            tmem_ld_32x32(trow + 128 + ch * 32, r);
+            tmem_ld_32x32(trow + 128 + (2 * half + i) * 32, r);
             tmem_ld_wait();
-            uint32_t wp[16], wd[16];
-            const uint32_t dead = mw[ch] | ~vw[ch];
-#pragma unroll
-            for (int j2 = 0; j2 < 16; ++j2) {
-                float pd[2], ds[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int j = 2 * j2 + u;
-                    const bool keep = (km[ch] >> j) & 1U;
-                    const float ev = e[ch * 32 + j];
-                    pd[u] = keep ? ev * pk : 0.f;
-                    const float dp = keep ? __uint_as_float(r[j]) * p.drop_scale : 0.f;
-                    ds[u] = ((dead >> j) & 1U) ? 0.f : ev * ps * (dp - di);
-                }
-                wp[j2] = pack_bf16x2(pd[0], pd[1]);
-                wd[j2] = pack_bf16x2(ds[0], ds[1]);
-            }
-            if (row < sqp) {
-                uint8_t* cp = sP + (ch >> 1) * chunk_stride;
-                uint8_t* cd = sdS + (ch >> 1) * chunk_stride;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t off = sw_off(row, (ch & 1) * 4 + q);
-                    *reinterpret_cast<uint4*>(cp + off) = make_uint4(wp[4 * q], wp[4 * q + 1], wp[4 * q + 2], wp[4 * q + 3]);
-                    *reinterpret_cast<uint4*>(cd + off) = make_uint4(wd[4 * q], wd[4 * q + 1], wd[4 * q + 2], wd[4 * q + 3]);
-                }
-            }
+            uint8_t* cp = sP + half * chunk_stride;
+            uint8_t* cd = sdS + half * chunk_stride;
+            const uint32_t dead = mw[i] | ~vw[i];
+            if (fast[i]) bwd_chunk_out<true>(r, e[i], km[i], dead, pk, ps, p.drop_scale, di, cp, cd, row, i * 4, row < sqp);
+            else bwd_chunk_out<false>(r, e[i], km[i], dead, pk, ps, p.drop_scale, di, cp, cd, row, i * 4, row < sqp);
         }
     fence_proxy_async_smem();
     tc_fence_before();
@@ -437,28 +514,26 @@ __global__ void __launch_bounds__(kTcThreads, 2) attn_bwd_tc_kernel(const AttnPa
             for (int j = 0; j < ksteps; ++j)     // dQ[query] = (scale dS) K -> columns [128, 192)
                 umma_bf16(tmem_base + 128, make_smem_desc_sw128(smem_u32(sdS) + (j >> 2) * chunk_stride + (j & 3) * 32, 0, 1024),
                           make_smem_desc_sw128(smem_u32(sK) + j * 2048, 8192, 1024), idesc_q, j > 0 ? 1U : 0U);
-            umma_commit(&sm->bar[2]);
+            umma_commit(&sm->bar[1]);
         }
         __syncwarp();
     }
-    mbar_wait(&sm->bar[2], 0);
+    mbar_wait(&sm->bar[1], 0);
     tc_fence_after();
-    // every operand tile is free now: dV -> V tile, dK -> K tile, dQ -> Q tile (swizzled staging), then coalesced stores
-    stage_acc32(trow, 1.f, sV, row, 0, row < skp);
-    stage_acc32(trow + 32, 1.f, sV, row, 4, row < skp);
-    stage_acc32(trow + 64, 1.f, sK, row, 0, row < skp);
-    stage_acc32(trow + 96, 1.f, sK, row, 4, row < skp);
-    stage_acc32(trow + 128, 1.f, sQ, row, 0, row < sqp);
-    stage_acc32(trow + 160, 1.f, sQ, row, 4, row < sqp);
+    // every operand tile is free now: dV -> V tile, dK -> K tile, dQ -> Q tile (swizzled staging), then coalesced
+    // stores; each thread moves its key half's 32 columns of the three accumulators
+    stage_acc32(trow + half * 32, 1.f, sV, row, half * 4, row < skp);
+    stage_acc32(trow + 64 + half * 32, 1.f, sK, row, half * 4, row < skp);
+    stage_acc32(trow + 128 + half * 32, 1.f, sQ, row, half * 4, row < sqp);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 256);
     }
-    unstage_tile(sV, p.dv + (long long)b * p.sk * p.lddv + h * 64, p.lddv, p.sk);
-    unstage_tile(sK, p.dk + (long long)b * p.sk * p.lddk + h * 64, p.lddk, p.sk);
-    unstage_tile(sQ, p.dq + (long long)b * p.sq * p.lddq + h * 64, p.lddq, p.sq);
+    unstage_tile<kBwdThreads>(sV, p.dv + (long long)b * p.sk * p.lddv + h * 64, p.lddv, p.sk);
+    unstage_tile<kBwdThreads>(sK, p.dk + (long long)b * p.sk * p.lddk + h * 64, p.lddk, p.sk);
+    unstage_tile<kBwdThreads>(sQ, p.dq + (long long)b * p.sq * p.lddq + h * 64, p.lddq, p.sq);
 }
 
 size_t fwd_tc_smem(int sk) {
@@ -478,7 +553,9 @@ bool tc_enabled() {
     return on;
 }
 bool tc_shape_ok(const AttnParams& p, int head_dim) {
-    return tc_enabled() && head_dim == 64 && p.sq >= 49 && p.sq <= 128 && p.sk >= 1 && p.sk <= 128 &&
+    // 33 .. 128 keys: with <= 32 keys (the question-guided attention, 100 x 14) the mma.sync kernel is faster
+    // (measured: profiles/r02_attention_tc_v1_bandwidth.txt) -- nothing but loads and stores is left of that problem
+    return tc_enabled() && head_dim == 64 && p.sq >= 49 && p.sq <= 128 && p.sk >= 33 && p.sk <= 128 && p.scale > 0.f &&
            p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0;
 }
 
@@ -515,17 +592,10 @@ int attn_tc_fwd_launch(const AttnParams& p, cudaStream_t st) {
 }
 
 int attn_tc_bwd_launch(const AttnParams& p, cudaStream_t st) {
+    static size_t configured = 0;
     const size_t smem = bwd_tc_smem(p.sq, p.sk);
-    const int skp = (p.sk + 15) & ~15;
-    if (skp <= 32) {
-        static size_t configured = 0;
-        if (int rc = prepare_kernel(attn_bwd_tc_kernel<1>, smem, &configured)) return rc;
-        MCAN_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel<1>, dim3(p.batch * p.heads), dim3(kTcThreads), smem, st, p));
-    } else {
-        static size_t configured = 0;
-        if (int rc = prepare_kernel(attn_bwd_tc_kernel<4>, smem, &configured)) return rc;
-        MCAN_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel<4>, dim3(p.batch * p.heads), dim3(kTcThreads), smem, st, p));
-    }
+    if (int rc = prepare_kernel(attn_bwd_tc_kernel, smem, &configured)) return rc;
+    MCAN_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel, dim3(p.batch * p.heads), dim3(kBwdThreads), smem, st, p));
     return 0;
 }
 
