@@ -55,6 +55,11 @@ int mcan_set_gemm_schedule(int dynamic);
  * kernel's launch latency and prologue overlap the previous kernel's tail; every kernel waits for
  * its predecessors' completion (griddepcontrol.wait) before touching global memory. */
 int mcan_set_pdl(int enabled);
+/* Attention implementation for the image-side problems (head_dim 64, 49..128 query rows, 33..128 keys; everything
+ * else always runs on the mma.sync kernels).  1 (default): tcgen05 / TMEM kernels (csrc/attention_tc.cu);
+ * 0: mma.sync kernels (csrc/attention.cu).  Same results contract (dropout mask, masking semantics); the
+ * environment variable MCAN_ATTN_TC=0 selects 0 at load time. */
+int mcan_set_attn_impl(int tcgen05);
 
 /* -- G1/G2/G3: tcgen05 GEMM with fused epilogue --------------------------------------
  * D[M,N] = epilogue( sum_{s<num_seg} A_s[M,K] * B_s[N,K]^T )         (fp32 accumulate in TMEM)

@@ -182,6 +182,7 @@ SYMBOLS = {
     "mcan_set_sm_limit": (ctypes.c_int, [ctypes.c_int]),
     "mcan_set_gemm_schedule": (ctypes.c_int, [ctypes.c_int]),
     "mcan_set_pdl": (ctypes.c_int, [ctypes.c_int]),
+    "mcan_set_attn_impl": (ctypes.c_int, [ctypes.c_int]),
     "mcan_gemm": (ctypes.c_int, [ctypes.POINTER(GemmArgs)]),
     "mcan_gemm_ln": (ctypes.c_int, [ctypes.POINTER(GemmLnArgs)]),
     "mcan_gemm_grouped": (ctypes.c_int, [ctypes.POINTER(GemmGroupedArgs)]),

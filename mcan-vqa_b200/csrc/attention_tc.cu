@@ -14,7 +14,7 @@
 //              dK = dS^T Q.  dV / dK / dQ accumulate in the TMEM columns S and dPd occupied.
 // Operand tiles are [rows x 64] bf16 with the 128-byte swizzle (what a TMA box {64, rows} would produce); they
 // are filled with 16-byte cp.async from the strided [rows, 3H] activations (a head is a 128-byte column slice),
-// so no tensor map per call is needed.  Results leave through a swizzled staging tile with coalesced 16-byte stores.
+// so no tensor map per call is needed.  Results leave straight from registers (64-byte runs per thread).
 //
 // Occupancy: forward 46 KB shared memory + 128 TMEM columns -> 4 CTAs / SM; backward 112 KB + 256 columns ->
 // 2 CTAs / SM: one CTA's load and MMA phases hide behind the other's softmax arithmetic.
@@ -23,6 +23,7 @@
 // precision, fused bias gradients): identical dropout hash and element indices, bf16 probabilities, fp32 softmax.
 #include "../../include/mcan_b200.h"
 #include "attention.cuh"
+#include <atomic>
 #include <stdlib.h>
 
 namespace mcan {
@@ -63,25 +64,21 @@ __device__ __forceinline__ void stage_tile(uint8_t* tile, const bf16* g, long lo
         else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
     }
 }
-// swizzled staging tile -> global rows (coalesced: 8 threads write one 128-byte row)
-template <int NTHREADS>
-__device__ __forceinline__ void unstage_tile(const uint8_t* tile, bf16* g, long long ld, int rows) {
-    for (int i = threadIdx.x; i < rows * 8; i += NTHREADS) {
-        const int r = i >> 3, c = i & 7;
-        *reinterpret_cast<uint4*>(g + (long long)r * ld + c * 8) = *reinterpret_cast<const uint4*>(tile + sw_off(r, c));
-    }
-}
-
 // keep bits of the 32 consecutive dropout elements idx .. idx+31 (bit j <=> element idx + j is kept); same hash and
 // indices as attention.cu / the host mirror (one mix32 per aligned pair of elements)
-__device__ __forceinline__ uint32_t keep32(uint32_t idx, uint32_t seed, uint32_t thr) {
+__device__ __forceinline__ uint32_t keep32(uint32_t idx, uint32_t seed, uint32_t thr, uint32_t vw) {
     uint32_t m = 0;
     if ((idx & 1U) == 0) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const uint32_t hsh = dropout_bits_pair((idx >> 1) + j, seed);
-            m |= ((hsh & 0xFFFFU) >= thr ? 1U : 0U) << (2 * j);
-            m |= ((hsh >> 16) >= thr ? 1U : 0U) << (2 * j + 1);
+        for (int q = 0; q < 4; ++q) {
+            if ((vw >> (8 * q)) & 0xFFU) {             // (uniform) quarters of 8 keys beyond sk are never used
+#pragma unroll
+                for (int j = 4 * q; j < 4 * q + 4; ++j) {
+                    const uint32_t hsh = dropout_bits_pair((idx >> 1) + j, seed);
+                    m |= ((hsh & 0xFFFFU) >= thr ? 1U : 0U) << (2 * j);
+                    m |= ((hsh >> 16) >= thr ? 1U : 0U) << (2 * j + 1);
+                }
+            }
         }
     } else {
 #pragma unroll 4
@@ -96,9 +93,9 @@ __device__ __forceinline__ uint32_t valid32(int sk, int ch) {
     return n >= 32 ? 0xFFFFFFFFU : (n <= 0 ? 0U : ((1U << n) - 1U));
 }
 
-// 32 fp32 accumulator columns of this thread's TMEM lane -> 16 packed bf16 pairs * mul -> four 16-byte chunks
-// c0 .. c0+3 of staging row `row`
-__device__ __forceinline__ void stage_acc32(uint32_t taddr, float mul, uint8_t* tile, int row, int c0, bool store) {
+// 32 fp32 accumulator columns of this thread's TMEM lane * mul -> bf16 -> 64 contiguous bytes of a global row
+// (whole 32-byte sectors; no staging pass, no barrier)
+__device__ __forceinline__ void store_acc32(uint32_t taddr, float mul, bf16* grow, bool store) {
     uint32_t r[32];
     tmem_ld_32x32(taddr, r);
     tmem_ld_wait();
@@ -110,7 +107,7 @@ __device__ __forceinline__ void stage_acc32(uint32_t taddr, float mul, uint8_t* 
             w.y = pack_bf16x2(__uint_as_float(r[8 * q + 2]) * mul, __uint_as_float(r[8 * q + 3]) * mul);
             w.z = pack_bf16x2(__uint_as_float(r[8 * q + 4]) * mul, __uint_as_float(r[8 * q + 5]) * mul);
             w.w = pack_bf16x2(__uint_as_float(r[8 * q + 6]) * mul, __uint_as_float(r[8 * q + 7]) * mul);
-            *reinterpret_cast<uint4*>(tile + sw_off(row, c0 + q)) = w;
+            *reinterpret_cast<uint4*>(grow + q * 8) = w;
         }
     }
 }
@@ -152,26 +149,34 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], float c, uint
                                           uint8_t* prow_chunk, int row, int c0) {
     uint32_t w[16];
 #pragma unroll
-    for (int j2 = 0; j2 < 16; ++j2) {
-        float e0, e1;
-        if (FAST) {
-            e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j2]), c, -mx));
-            e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j2 + 1]), c, -mx));
+    for (int q = 0; q < 4; ++q) {
+        if (FAST || ((vw >> (8 * q)) & 0xFFU)) {           // (uniform) a quarter of 8 keys beyond sk: zeros, no arithmetic
+#pragma unroll
+            for (int j2 = 4 * q; j2 < 4 * q + 4; ++j2) {
+                float e0, e1;
+                if (FAST) {
+                    e0 = ex2_approx(fmaf(__uint_as_float(r[2 * j2]), c, -mx));
+                    e1 = ex2_approx(fmaf(__uint_as_float(r[2 * j2 + 1]), c, -mx));
+                } else {
+                    e0 = ex2_approx(score_log2(r[2 * j2], c, mw, vw, 2 * j2) - mx);
+                    e1 = ex2_approx(score_log2(r[2 * j2 + 1], c, mw, vw, 2 * j2 + 1) - mx);
+                }
+                sum0 += e0;
+                sum1 += e1;
+                if (DM == 1) {
+                    const uint32_t hsh = dropout_bits_pair(km_or_pair + j2, seed);
+                    e0 = ((hsh << 16) >= thr16) ? e0 : 0.f;      // low 16 bits >= thr
+                    e1 = (hsh >= thr16) ? e1 : 0.f;              // high 16 bits >= thr
+                } else if (DM == 2) {
+                    e0 = ((km_or_pair >> (2 * j2)) & 1U) ? e0 : 0.f;
+                    e1 = ((km_or_pair >> (2 * j2 + 1)) & 1U) ? e1 : 0.f;
+                }
+                w[j2] = pack_bf16x2(e0, e1);
+            }
         } else {
-            e0 = ex2_approx(score_log2(r[2 * j2], c, mw, vw, 2 * j2) - mx);
-            e1 = ex2_approx(score_log2(r[2 * j2 + 1], c, mw, vw, 2 * j2 + 1) - mx);
+#pragma unroll
+            for (int j2 = 4 * q; j2 < 4 * q + 4; ++j2) w[j2] = 0U;
         }
-        sum0 += e0;
-        sum1 += e1;
-        if (DM == 1) {
-            const uint32_t hsh = dropout_bits_pair(km_or_pair + j2, seed);
-            e0 = ((hsh << 16) >= thr16) ? e0 : 0.f;      // low 16 bits >= thr
-            e1 = (hsh >= thr16) ? e1 : 0.f;              // high 16 bits >= thr
-        } else if (DM == 2) {
-            e0 = ((km_or_pair >> (2 * j2)) & 1U) ? e0 : 0.f;
-            e1 = ((km_or_pair >> (2 * j2 + 1)) & 1U) ? e1 : 0.f;
-        }
-        w[j2] = pack_bf16x2(e0, e1);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnPa
     uint8_t* sV = smem;
     uint8_t* sQ = smem + kv_bytes;
     uint8_t* sK = sQ + 16384;
-    uint8_t* sP = sQ;                                      // overlays Q and K once S is complete; later the O staging tile
+    uint8_t* sP = sQ;                                      // overlays Q and K once S is complete
     TcSmall* sm = reinterpret_cast<TcSmall*>(sQ + (qk_bytes > p_bytes ? qk_bytes : p_bytes));
 
     if (warp == 0) {
@@ -251,7 +256,11 @@ __global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnPa
             mx = fmaxf(mx, m * c);
         } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, score_log2(r[j], c, mw, vw, j));
+            for (int q = 0; q < 4; ++q)
+                if ((vw >> (8 * q)) & 0xFFU) {
+#pragma unroll
+                    for (int j = 8 * q; j < 8 * q + 8; ++j) mx = fmaxf(mx, score_log2(r[j], c, mw, vw, j));
+                }
         }
     }
     float sum0 = 0.f, sum1 = 0.f;
@@ -271,7 +280,7 @@ __global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnPa
         } else if (dm == 0) {
             if (fast) MCAN_FWD_CHUNK(true, 0, 0U); else MCAN_FWD_CHUNK(false, 0, 0U);
         } else {
-            const uint32_t km = keep32(idx, drop_seed, p.drop_thr);
+            const uint32_t km = keep32(idx, drop_seed, p.drop_thr, vw);
             MCAN_FWD_CHUNK(false, 2, km);
         }
 #undef MCAN_FWD_CHUNK
@@ -295,15 +304,17 @@ __global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnPa
     mbar_wait(&sm->bar[1], 0);
     tc_fence_after();
     const float mul = p.drop_scale / (sum0 + sum1);
-    stage_acc32(trow, mul, sP, row, 0, true);
-    stage_acc32(trow + 32, mul, sP, row, 4, true);
+    // results leave straight from registers (64-byte runs = whole sectors per thread; a swizzled staging tile with a
+    // coalesced copy measured the same)
+    bf16* orow = p.out + ((long long)b * p.sq + row) * p.ldo + h * 64;
+    store_acc32(trow, mul, orow, row < p.sq);
+    store_acc32(trow + 32, mul, orow + 32, row < p.sq);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
     }
-    unstage_tile<kTcThreads>(sP, p.out + (long long)b * p.sq * p.ldo + h * 64, p.ldo, p.sq);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -400,6 +411,16 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_tc_kernel(const AttnP
     cp_async_commit();
     if (warp < 4) load_mask_words(p, b, sm->mask);
     const uint32_t drop_seed = p.drop_seed ^ ((p.drop_thr != 0 && p.drop_seed_dev != nullptr) ? __ldg(p.drop_seed_dev) : 0U);
+    // the dropout keep bits of this thread's 64 scores depend on nothing that is being loaded: hashed while the
+    // operand tiles are in flight
+    const int row = qw * 32 + lane;
+    uint32_t km[2] = {0xFFFFFFFFU, 0xFFFFFFFFU};
+    if (p.drop_thr != 0) {
+        const uint32_t base = (uint32_t)(((long long)item * p.sq + row) * p.sk);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            if ((2 * half + i) * 32 < skp) km[i] = keep32(base + 32U * (2 * half + i), drop_seed, p.drop_thr, valid32(p.sk, 2 * half + i));
+    }
     cp_async_wait_group<0>();
     fence_proxy_async_smem();
     tc_fence_before();
@@ -423,11 +444,10 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_tc_kernel(const AttnP
         __syncwarp();
     }
 
-    const int row = qw * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(qw * 32) << 16);
     const float c = p.scale * kLog2e;
     // this thread's two 32-key chunks: 2 * half, 2 * half + 1
-    uint32_t mw[2], vw[2], km[2];
+    uint32_t mw[2], vw[2];
     bool act[2], fast[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
@@ -436,13 +456,6 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_tc_kernel(const AttnP
         mw[i] = sm->mask[ch];
         vw[i] = valid32(p.sk, ch);
         fast[i] = (mw[i] | ~vw[i]) == 0U;
-        km[i] = 0xFFFFFFFFU;
-    }
-    if (p.drop_thr != 0) {                                 // (the hash work overlaps the first MMAs)
-        const uint32_t base = (uint32_t)(((long long)item * p.sq + row) * p.sk);
-#pragma unroll
-        for (int i = 0; i < 2; ++i)
-            if (act[i]) km[i] = keep32(base + 32U * (2 * half + i), drop_seed, p.drop_thr);
     }
 
     mbar_wait(&sm->bar[0], 0);                             // S and dPd complete (V is free from here on)
@@ -520,20 +533,16 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_tc_kernel(const AttnP
     }
     mbar_wait(&sm->bar[1], 0);
     tc_fence_after();
-    // every operand tile is free now: dV -> V tile, dK -> K tile, dQ -> Q tile (swizzled staging), then coalesced
-    // stores; each thread moves its key half's 32 columns of the three accumulators
-    stage_acc32(trow + half * 32, 1.f, sV, row, half * 4, row < skp);
-    stage_acc32(trow + 64 + half * 32, 1.f, sK, row, half * 4, row < skp);
-    stage_acc32(trow + 128 + half * 32, 1.f, sQ, row, half * 4, row < sqp);
+    // each thread stores its key half's 32 columns (64 contiguous bytes) of its row of the three accumulators
+    store_acc32(trow + half * 32, 1.f, p.dv + ((long long)b * p.sk + row) * p.lddv + h * 64 + half * 32, row < p.sk);
+    store_acc32(trow + 64 + half * 32, 1.f, p.dk + ((long long)b * p.sk + row) * p.lddk + h * 64 + half * 32, row < p.sk);
+    store_acc32(trow + 128 + half * 32, 1.f, p.dq + ((long long)b * p.sq + row) * p.lddq + h * 64 + half * 32, row < p.sq);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 256);
     }
-    unstage_tile<kBwdThreads>(sV, p.dv + (long long)b * p.sk * p.lddv + h * 64, p.lddv, p.sk);
-    unstage_tile<kBwdThreads>(sK, p.dk + (long long)b * p.sk * p.lddk + h * 64, p.lddk, p.sk);
-    unstage_tile<kBwdThreads>(sQ, p.dq + (long long)b * p.sq * p.lddq + h * 64, p.lddq, p.sq);
 }
 
 size_t fwd_tc_smem(int sk) {
@@ -548,9 +557,15 @@ size_t bwd_tc_smem(int sq, int sk) {
     return (tiles_end > a_end ? tiles_end : a_end) + sizeof(TcSmall);
 }
 
+std::atomic<int> g_tc_enabled{-1};      // -1: not decided yet (environment at first use)
 bool tc_enabled() {
-    static const bool on = [] { const char* e = getenv("MCAN_ATTN_TC"); return !(e && e[0] == '0'); }();
-    return on;
+    int v = g_tc_enabled.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = getenv("MCAN_ATTN_TC");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_tc_enabled.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
 }
 bool tc_shape_ok(const AttnParams& p, int head_dim) {
     // 33 .. 128 keys: with <= 32 keys (the question-guided attention, 100 x 14) the mma.sync kernel is faster
@@ -600,3 +615,8 @@ int attn_tc_bwd_launch(const AttnParams& p, cudaStream_t st) {
 }
 
 }  // namespace mcan
+
+extern "C" int mcan_set_attn_impl(int tcgen05) {
+    mcan::g_tc_enabled.store(tcgen05 ? 1 : 0, std::memory_order_relaxed);
+    return 0;
+}

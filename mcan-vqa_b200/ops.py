@@ -115,6 +115,11 @@ def set_pdl(enabled):
     capi.check(capi.load().mcan_set_pdl(1 if enabled else 0), "mcan_set_pdl", launch=False)
 
 
+def set_attn_impl(tcgen05):
+    """Image-side attention on the tcgen05 / TMEM kernels (default) or on the mma.sync kernels."""
+    capi.check(capi.load().mcan_set_attn_impl(1 if tcgen05 else 0), "mcan_set_attn_impl", launch=False)
+
+
 def gemm_plan(m, n, k, *, accumulate=False, split_k=0, block_n=0, cta_group=0, sms=0):
     """The launch plan mcan_gemm uses for this shape (host logic only, no GPU needed when `sms` is given)."""
     out = (ctypes.c_int32 * 7)()

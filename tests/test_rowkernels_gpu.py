@@ -192,6 +192,63 @@ def test_attention_dropout_matches_host_hash():
         assert err < 3e-2 * max(1.0, rf.abs().max().item())
 
 
+TC_ATTN_CASES = [
+    # batch, heads, sq, sk, mask kind, dropout: shapes the tcgen05 path takes (head dim 64, >= 49 queries, >= 33 keys)
+    (3, 8, 100, 100, "none", 0.0),
+    (3, 8, 100, 100, "allmasked", 0.1),     # one fully masked sample -> uniform probabilities (mca.py:70-75)
+    (2, 16, 60, 60, "prefix", 0.1),
+    (2, 4, 128, 128, "random", 0.1),
+    (2, 4, 64, 77, "random", 0.1),          # odd key count: dropout element pairs straddle rows
+    (2, 4, 99, 51, "random", 0.1),
+    (2, 4, 50, 33, "prefix", 0.0),
+    (64, 16, 100, 100, "none", 0.1),        # the MCAN-large launch (1024 CTAs, several waves)
+]
+
+
+@pytest.mark.parametrize("batch,heads,sq,sk,kind,p", TC_ATTN_CASES)
+def test_attention_tcgen05_path(batch, heads, sq, sk, kind, p):
+    """tcgen05 / TMEM attention (csrc/attention_tc.cu) vs fp32 torch math with the host mirror of the dropout mask, and
+    vs the mma.sync kernels on the same inputs (same mask, same masking semantics)."""
+    ops = _ops()
+    d, seed = 64, 977
+    q, k, v, mask = _make_attn(batch, heads, sq, sk, d, kind)
+    H = heads * d
+    scale = 1.0 / math.sqrt(d)
+    mask_u8 = None if mask is None else mask.to(torch.uint8).contiguous()
+    dout = (torch.randn(batch * sq, H, device="cuda") * 0.5).to(torch.bfloat16)
+    kw = dict(batch=batch, heads=heads, sq=sq, sk=sk, head_dim=d, scale=scale, dropout_p=p, seed=seed)
+    res = {}
+    try:
+        for impl in (1, 0):
+            ops.set_attn_impl(impl)
+            out = torch.full((batch * sq, H), float("nan"), device="cuda", dtype=torch.bfloat16)
+            dqkv = torch.full((batch * max(sq, sk), 3 * H), float("nan"), device="cuda", dtype=torch.bfloat16)
+            dq, dk, dv = dqkv[: batch * sq, :H], dqkv[: batch * sk, H:2 * H], dqkv[: batch * sk, 2 * H:]
+            ops.attn_fwd(q, k, v, mask_u8, out, **kw)
+            ops.attn_bwd(q, k, v, mask_u8, dout, dq, dk, dv, **kw)
+            torch.cuda.synchronize()
+            res[impl] = (out, dq, dk, dv)
+    finally:
+        ops.set_attn_impl(1)
+    keep = None
+    if p > 0:
+        keep = ops.dropout_keep_mask(batch * heads * sq * sk, p, seed).view(batch, heads, sq, sk).cuda().float()
+    qh = _heads(q, batch, sq, heads, d).requires_grad_(True)
+    kh = _heads(k, batch, sk, heads, d).requires_grad_(True)
+    vh = _heads(v, batch, sk, heads, d).requires_grad_(True)
+    ref = _attn_ref(qh, kh, vh, mask, scale, keep, p) if p > 0 else _attn_ref(qh, kh, vh, mask, scale)
+    ref.backward(_heads(dout, batch, sq, heads, d))
+    refs = (ref.detach(), qh.grad, kh.grad, vh.grad)
+    for i, (name, s) in enumerate((("out", sq), ("dq", sq), ("dk", sk), ("dv", sk))):
+        rf = refs[i]
+        tc = _heads(res[1][i], batch, s, heads, d)
+        mma = _heads(res[0][i], batch, s, heads, d)
+        tol = 3e-2 * max(1.0, rf.abs().max().item())
+        assert not torch.isnan(tc).any(), name
+        assert (tc - rf).abs().max().item() < tol, (name, (tc - rf).abs().max().item())
+        assert (tc - mma).abs().max().item() < tol, (name, (tc - mma).abs().max().item())
+
+
 @pytest.mark.parametrize("batch,s,h,mlp,glimpses", [(8, 100, 512, 512, 1), (4, 14, 1024, 512, 1), (3, 60, 512, 512, 2), (2, 100, 512, 256, 3),
                                                     (64, 100, 1024, 512, 1), (64, 14, 1024, 512, 1), (1, 100, 2048, 512, 2),
                                                     (5, 3, 40, 16, 5), (300, 100, 512, 512, 1), (2, 1, 8, 8, 1)])
