@@ -564,6 +564,9 @@ def main():
                                                                 if trainer.sync.compress == "bf16" else ""),
                             os.environ.get("MCAN_DP_BUCKET_MB", "192"))) if world > 1 else "none",
                         "optimizer": "fused multi-tensor AdamW (library kernel, emits the bf16 operand copies)",
+                        "attention": ("image self-attention (100 x 100): tcgen05 / TMEM kernels; question side and guided "
+                                      "attention (<= 32 keys): mma.sync kernels") if os.environ.get("MCAN_ATTN_TC", "1") != "0"
+                        else "mma.sync kernels (MCAN_ATTN_TC=0)",
                         "decoder_wgrads": "second stream, next to the encoder backward" if blocks.OVERLAP_WGRAD else "inline"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -95,6 +95,11 @@ def test_trainer_fused_optimizer_keeps_operand_copies_current_and_matches_torch_
         losses[fused] = [tr.step(*batch).item() for _ in range(12)]
         if fused:
             for lp in tr.net.all_lps():
+                if lp.shadow_items() is None:
+                    # padded leading dimension (the LSTM input projection, E -> multiple of 64 columns): a flat kernel
+                    # cannot write this copy, it is re-cast by the refresh kernel of every training forward instead
+                    assert lp.managed is None and lp.w.stride(0) != lp.k
+                    continue
                 assert lp.managed is tr.opt
                 r = 0
                 for (w, b), n in zip(lp.pairs, lp.sizes):
@@ -108,7 +113,7 @@ def test_trainer_fused_optimizer_keeps_operand_copies_current_and_matches_torch_
                 with torch.no_grad():
                     tr.net.eval()
                     p1 = tr.net(batch[0], batch[1])[0]
-                    assert all(lp.pending(need_lo=True) == [] for lp in tr.net.all_lps())
+                    assert all(lp.pending(need_lo=True) == [] for lp in tr.net.all_lps() if lp.managed is not None)
                     p2 = tr.net(batch[0], batch[1])[0]
                 assert torch.equal(p1, p2)
             finally:
