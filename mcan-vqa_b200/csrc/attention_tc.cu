@@ -34,6 +34,7 @@ constexpr int kTcThreads = 128;                     // forward: thread = query r
 constexpr int kBwdThreads = 256;                    // backward: two threads per query row
 constexpr int kTileRows = 128;                      // UMMA M
 constexpr float kMaskedLog2 = -1e9f * kLog2e;
+constexpr int kDefaultStageMode = 3;   // measured: profiles/r02b_attention_tc_store_ab.txt (staged 52-53 vs 55.3 us backward)
 
 __device__ __forceinline__ void cp_async16_tc(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
@@ -93,9 +94,11 @@ __device__ __forceinline__ uint32_t valid32(int sk, int ch) {
     return n >= 32 ? 0xFFFFFFFFU : (n <= 0 ? 0U : ((1U << n) - 1U));
 }
 
-// 32 fp32 accumulator columns of this thread's TMEM lane * mul -> bf16 -> 64 contiguous bytes of a global row
-// (whole 32-byte sectors; no staging pass, no barrier)
-__device__ __forceinline__ void store_acc32(uint32_t taddr, float mul, bf16* grow, bool store) {
+// 32 fp32 accumulator columns of this thread's TMEM lane * mul -> bf16 -> either 64 contiguous bytes of a global row
+// (straight from registers) or four 16-byte chunks c0 .. c0+3 of row `row` of a swizzled staging tile (copied out
+// with coalesced stores by unstage_tile afterwards)
+__device__ __forceinline__ void emit_acc32(uint32_t taddr, float mul, bool staged, uint8_t* tile, int row, int c0,
+                                           bf16* grow, bool store) {
     uint32_t r[32];
     tmem_ld_32x32(taddr, r);
     tmem_ld_wait();
@@ -107,8 +110,17 @@ __device__ __forceinline__ void store_acc32(uint32_t taddr, float mul, bf16* gro
             w.y = pack_bf16x2(__uint_as_float(r[8 * q + 2]) * mul, __uint_as_float(r[8 * q + 3]) * mul);
             w.z = pack_bf16x2(__uint_as_float(r[8 * q + 4]) * mul, __uint_as_float(r[8 * q + 5]) * mul);
             w.w = pack_bf16x2(__uint_as_float(r[8 * q + 6]) * mul, __uint_as_float(r[8 * q + 7]) * mul);
-            *reinterpret_cast<uint4*>(grow + q * 8) = w;
+            if (staged) *reinterpret_cast<uint4*>(tile + sw_off(row, c0 + q)) = w;
+            else *reinterpret_cast<uint4*>(grow + q * 8) = w;
         }
+    }
+}
+// swizzled staging tile -> global rows (8 threads write one 128-byte row)
+template <int NTHREADS>
+__device__ __forceinline__ void unstage_tile(const uint8_t* tile, bf16* g, long long ld, int rows) {
+    for (int i = threadIdx.x; i < rows * 8; i += NTHREADS) {
+        const int r = i >> 3, c = i & 7;
+        *reinterpret_cast<uint4*>(g + (long long)r * ld + c * 8) = *reinterpret_cast<const uint4*>(tile + sw_off(r, c));
     }
 }
 
@@ -183,7 +195,8 @@ __device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], float c, uint
         *reinterpret_cast<uint4*>(prow_chunk + sw_off(row, c0 + q)) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 }
 
-__global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnParams p, const int tmem_cols) {
+__global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnParams p, const int tmem_cols, const int staged_i) {
+    const bool staged = staged_i != 0;
     pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -304,17 +317,18 @@ __global__ void __launch_bounds__(kTcThreads, 4) attn_fwd_tc_kernel(const AttnPa
     mbar_wait(&sm->bar[1], 0);
     tc_fence_after();
     const float mul = p.drop_scale / (sum0 + sum1);
-    // results leave straight from registers (64-byte runs = whole sectors per thread; a swizzled staging tile with a
-    // coalesced copy measured the same)
+    // results leave straight from registers (64-byte runs per thread) or through a swizzled staging tile (the P tile
+    // is free once the second MMA has retired)
     bf16* orow = p.out + ((long long)b * p.sq + row) * p.ldo + h * 64;
-    store_acc32(trow, mul, orow, row < p.sq);
-    store_acc32(trow + 32, mul, orow + 32, row < p.sq);
+    emit_acc32(trow, mul, staged, sP, row, 0, orow, row < p.sq);
+    emit_acc32(trow + 32, mul, staged, sP, row, 4, orow + 32, row < p.sq);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
     }
+    if (staged) unstage_tile<kTcThreads>(sP, p.out + (long long)b * p.sq * p.ldo + h * 64, p.ldo, p.sq);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -374,7 +388,8 @@ __device__ __forceinline__ void bwd_chunk_out(const uint32_t (&r)[32], const flo
     }
 }
 
-__global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_tc_kernel(const AttnParams p) {
+__global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_tc_kernel(const AttnParams p, const int staged_i) {
+    const bool staged = staged_i != 0;
     pdl_launch_dependents();
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -534,14 +549,20 @@ __global__ void __launch_bounds__(kBwdThreads, 2) attn_bwd_tc_kernel(const AttnP
     mbar_wait(&sm->bar[1], 0);
     tc_fence_after();
     // each thread stores its key half's 32 columns (64 contiguous bytes) of its row of the three accumulators
-    store_acc32(trow + half * 32, 1.f, p.dv + ((long long)b * p.sk + row) * p.lddv + h * 64 + half * 32, row < p.sk);
-    store_acc32(trow + 64 + half * 32, 1.f, p.dk + ((long long)b * p.sk + row) * p.lddk + h * 64 + half * 32, row < p.sk);
-    store_acc32(trow + 128 + half * 32, 1.f, p.dq + ((long long)b * p.sq + row) * p.lddq + h * 64 + half * 32, row < p.sq);
+    // (staged: every operand tile is free now -- dV -> V tile, dK -> K tile, dQ -> Q tile)
+    emit_acc32(trow + half * 32, 1.f, staged, sV, row, half * 4, p.dv + ((long long)b * p.sk + row) * p.lddv + h * 64 + half * 32, row < p.sk);
+    emit_acc32(trow + 64 + half * 32, 1.f, staged, sK, row, half * 4, p.dk + ((long long)b * p.sk + row) * p.lddk + h * 64 + half * 32, row < p.sk);
+    emit_acc32(trow + 128 + half * 32, 1.f, staged, sQ, row, half * 4, p.dq + ((long long)b * p.sq + row) * p.lddq + h * 64 + half * 32, row < p.sq);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 256);
+    }
+    if (staged) {
+        unstage_tile<kBwdThreads>(sV, p.dv + (long long)b * p.sk * p.lddv + h * 64, p.lddv, p.sk);
+        unstage_tile<kBwdThreads>(sK, p.dk + (long long)b * p.sk * p.lddk + h * 64, p.lddk, p.sk);
+        unstage_tile<kBwdThreads>(sQ, p.dq + (long long)b * p.sq * p.lddq + h * 64, p.lddq, p.sq);
     }
 }
 
@@ -566,6 +587,11 @@ bool tc_enabled() {
         g_tc_enabled.store(v, std::memory_order_relaxed);
     }
     return v != 0;
+}
+// MCAN_ATTN_TC_STAGE: bit 0 forward, bit 1 backward -- results through a staging tile instead of straight from registers
+int stage_mode() {
+    static const int mode = [] { const char* e = getenv("MCAN_ATTN_TC_STAGE"); return e ? atoi(e) : kDefaultStageMode; }();
+    return mode;
 }
 bool tc_shape_ok(const AttnParams& p, int head_dim) {
     // 33 .. 128 keys: with <= 32 keys (the question-guided attention, 100 x 14) the mma.sync kernel is faster
@@ -602,7 +628,7 @@ int attn_tc_fwd_launch(const AttnParams& p, cudaStream_t st) {
     if (int rc = prepare_kernel(attn_fwd_tc_kernel, smem, &configured)) return rc;
     const int skp = (p.sk + 15) & ~15;
     const int tmem_cols = skp <= 64 ? 64 : 128;            // S (skp columns), then O (64 columns) in the same place
-    MCAN_CHECK_CUDA(launch_kernel(attn_fwd_tc_kernel, dim3(p.batch * p.heads), dim3(kTcThreads), smem, st, p, tmem_cols));
+    MCAN_CHECK_CUDA(launch_kernel(attn_fwd_tc_kernel, dim3(p.batch * p.heads), dim3(kTcThreads), smem, st, p, tmem_cols, stage_mode() & 1));
     return 0;
 }
 
@@ -610,7 +636,7 @@ int attn_tc_bwd_launch(const AttnParams& p, cudaStream_t st) {
     static size_t configured = 0;
     const size_t smem = bwd_tc_smem(p.sq, p.sk);
     if (int rc = prepare_kernel(attn_bwd_tc_kernel, smem, &configured)) return rc;
-    MCAN_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel, dim3(p.batch * p.heads), dim3(kBwdThreads), smem, st, p));
+    MCAN_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel, dim3(p.batch * p.heads), dim3(kBwdThreads), smem, st, p, (stage_mode() >> 1) & 1));
     return 0;
 }
 
