@@ -600,12 +600,16 @@ bool tc_shape_ok(const AttnParams& p, int head_dim) {
            p.ldq % 8 == 0 && p.ldk % 8 == 0 && p.ldv % 8 == 0;
 }
 
+// function attributes are per device: remember the largest configured size for each one
 template <typename K>
-int prepare_kernel(K kernel, size_t smem, size_t* configured) {
-    if (smem > *configured) {
+int prepare_kernel(K kernel, size_t smem, size_t (&configured)[64]) {
+    int dev = 0;
+    MCAN_CHECK_CUDA(cudaGetDevice(&dev));
+    MCAN_REQUIRE(dev >= 0 && dev < 64, "attention: device ordinal %d", dev);
+    if (smem > configured[dev]) {
         MCAN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MCAN_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        *configured = smem;
+        configured[dev] = smem;
     }
     return 0;
 }
@@ -623,9 +627,9 @@ bool attn_tc_bwd_eligible(const AttnParams& p, int head_dim) {
 }
 
 int attn_tc_fwd_launch(const AttnParams& p, cudaStream_t st) {
-    static size_t configured = 0;
+    static size_t configured[64] = {0};
     const size_t smem = fwd_tc_smem(p.sk);
-    if (int rc = prepare_kernel(attn_fwd_tc_kernel, smem, &configured)) return rc;
+    if (int rc = prepare_kernel(attn_fwd_tc_kernel, smem, configured)) return rc;
     const int skp = (p.sk + 15) & ~15;
     const int tmem_cols = skp <= 64 ? 64 : 128;            // S (skp columns), then O (64 columns) in the same place
     MCAN_CHECK_CUDA(launch_kernel(attn_fwd_tc_kernel, dim3(p.batch * p.heads), dim3(kTcThreads), smem, st, p, tmem_cols, stage_mode() & 1));
@@ -633,9 +637,9 @@ int attn_tc_fwd_launch(const AttnParams& p, cudaStream_t st) {
 }
 
 int attn_tc_bwd_launch(const AttnParams& p, cudaStream_t st) {
-    static size_t configured = 0;
+    static size_t configured[64] = {0};
     const size_t smem = bwd_tc_smem(p.sq, p.sk);
-    if (int rc = prepare_kernel(attn_bwd_tc_kernel, smem, &configured)) return rc;
+    if (int rc = prepare_kernel(attn_bwd_tc_kernel, smem, configured)) return rc;
     MCAN_CHECK_CUDA(launch_kernel(attn_bwd_tc_kernel, dim3(p.batch * p.heads), dim3(kBwdThreads), smem, st, p, (stage_mode() >> 1) & 1));
     return 0;
 }
