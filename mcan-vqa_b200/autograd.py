@@ -57,7 +57,12 @@ class _Chain(torch.autograd.Function):
         ctx.act_needs = [t is not None and t.requires_grad for t in tensors[:n_act]]
         if runner.sparse_grads:
             ctx.set_materialize_grads(False)    # unused outputs arrive as None instead of zero tensors
-        outs = runner.forward(tensors[:n_act])
+        if not blocks.DRY_RUN:
+            for t in tensors[:n_act]:
+                if t is not None:
+                    ops.check_device(t, type(runner.module).__name__ + " input")
+        with ops.trusted():
+            outs = runner.forward(tensors[:n_act])
         for t in runner.non_differentiable:
             ctx.mark_non_differentiable(t)
         return outs
@@ -66,7 +71,8 @@ class _Chain(torch.autograd.Function):
     @once_differentiable
     def backward(ctx, *gouts):
         runner = ctx.runner
-        act_grads, grads = runner.backward(gouts, ctx.act_needs)
+        with ops.trusted():
+            act_grads, grads = runner.backward(gouts, ctx.act_needs)
         # a gradient in another dtype than its parameter (bf16 weight gradients produced directly in the all-reduce
         # buffer, blocks.WGRAD_BF16) is not handed to autograd: the data-parallel optimiser gets it from dp.GradSync
         pg = tuple(g if (g is None or g.dtype == p.dtype) else None for p, g in ((p, grads.get(p)) for p in runner.params))
@@ -114,7 +120,7 @@ class _MHAttRunner(_Runner):
     """MHAtt.forward(v, k, q, mask) -- mca.py:30-63; inputs that are the same tensor share one GEMM."""
 
     def __init__(self, module, same_vk, same_kq):
-        _Runner.__init__(self, module, list(module.parameters()))
+        _Runner.__init__(self, module, blocks.module_params(module))
         self.same_vk, self.same_kq = same_vk, same_kq
 
     def forward(self, acts):
@@ -172,7 +178,7 @@ class _MLPRunner(_Runner):
 
 
 def mlp(module, x):
-    return _run(_MLPRunner(module, list(module.parameters())), [x])
+    return _run(_MLPRunner(module, blocks.module_params(module)), [x])
 
 
 class _FCRunner(_Runner):
@@ -217,7 +223,7 @@ class _FCRunner(_Runner):
 
 
 def fc(module, x):
-    return _run(_FCRunner(module, list(module.parameters())), [x])
+    return _run(_FCRunner(module, blocks.module_params(module)), [x])
 
 
 # ------------------------------------------------------------------------------------------
@@ -239,7 +245,7 @@ class _SARunner(_Runner):
 
 
 def sa(module, x, x_mask):
-    return _run(_SARunner(module, list(module.parameters())), [x, x_mask])
+    return _run(_SARunner(module, blocks.module_params(module)), [x, x_mask])
 
 
 class _SGARunner(_Runner):
@@ -263,7 +269,7 @@ class _SGARunner(_Runner):
 
 
 def sga(module, x, y, x_mask, y_mask):
-    return _run(_SGARunner(module, list(module.parameters())), [x, y, x_mask, y_mask])
+    return _run(_SGARunner(module, blocks.module_params(module)), [x, y, x_mask, y_mask])
 
 
 # ------------------------------------------------------------------------------------------
@@ -295,7 +301,7 @@ class _MCAEDRunner(_Runner):
 
 
 def mca_ed(module, x, y, x_mask, y_mask):
-    return _run(_MCAEDRunner(module, list(module.parameters())), [x, y, x_mask, y_mask])
+    return _run(_MCAEDRunner(module, blocks.module_params(module)), [x, y, x_mask, y_mask])
 
 
 class _SAStackRunner(_Runner):
@@ -325,7 +331,7 @@ class _SAStackRunner(_Runner):
 
 
 def sa_stack(module, y, y_mask):
-    return _run(_SAStackRunner(module, list(module.parameters())), [y, y_mask])
+    return _run(_SAStackRunner(module, blocks.module_params(module)), [y, y_mask])
 
 
 # ------------------------------------------------------------------------------------------
@@ -347,7 +353,7 @@ class _AttFlatRunner(_Runner):
 
 
 def attflat(module, x, x_mask):
-    return _run(_AttFlatRunner(module, list(module.parameters())), [x, x_mask])
+    return _run(_AttFlatRunner(module, blocks.module_params(module)), [x, x_mask])
 
 
 # ------------------------------------------------------------------------------------------

@@ -322,6 +322,7 @@ class LinearParams(object):
         self._dirty = False
         self.managed = None     # optim.FusedAdamW that re-emits the operand copy with every parameter update
         self._lo_epoch = -1
+        self._scope_epoch = -1  # id of the refresh_scope that last refreshed this copy
 
     def shadow_items(self):
         """[(dst, master Parameter)] an optimiser has to keep in sync, or None when the copy cannot be
@@ -352,6 +353,9 @@ class LinearParams(object):
 
     def pending(self, force=False, need_lo=False):
         """(dst, src[, dst_lo]) copy items needed to bring the bf16 operand copy up to date ([] if current)."""
+        if (not force and _refresh_scope[0] > 0 and self._scope_epoch == _scope_epoch[0] and self.w is not None
+                and (not need_lo or self.w_lo is not None)):
+            return []       # the enclosing refresh_scope brought this copy up to date when it was entered
         self._ensure_storage()
         if need_lo and self.w_lo is None:
             self.w_lo = torch.zeros((self.n, self.w.stride(0)), dtype=_BF16, device=self.w.device)[:, :self.k]
@@ -445,6 +449,7 @@ class Bag(object):
 
 
 _refresh_scope = [0]     # > 0 while an enclosing module already refreshed every operand copy
+_scope_epoch = [0]       # counts outermost refresh_scopes; LinearParams._scope_epoch == this: refreshed by the current one
 
 
 def _force(rt_training):
@@ -495,7 +500,10 @@ class refresh_scope(object):
     def __enter__(self):
         if _refresh_scope[0] == 0:
             need_lo = (PRECISION == "fp32") and not torch.is_grad_enabled()
+            _scope_epoch[0] += 1
             refresh_params(self.lps, ALWAYS_RECAST and self.training, need_lo)
+            for lp in self.lps:
+                lp._scope_epoch = _scope_epoch[0]
         _refresh_scope[0] += 1
 
     def __exit__(self, *exc):
@@ -910,6 +918,23 @@ def _side_stream(dev):
     return st
 
 
+def module_params(m):
+    """list(m.parameters()), cached on the module: nn.Module.parameters() walks the whole module tree in Python
+    (2.5 ms for MCA_ED, paid several times per eager training step).  The cache holds the Parameter objects, which
+    survive .cuda() / .to() / load_state_dict(); a module whose parameters are REPLACED after the first forward
+    must call invalidate_module_params."""
+    cache = m.__dict__.get("_mcan_params")
+    if cache is None:
+        cache = list(m.parameters())
+        m.__dict__["_mcan_params"] = cache
+    return cache
+
+
+def invalidate_module_params(root):
+    for sub in root.modules():
+        sub.__dict__.pop("_mcan_params", None)
+
+
 def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
     """dx_out/dy_out: fp32 grads of the two outputs.  after_layer(bufs, grads, kind) is called with the flat
     gradient buffers and the {parameter: gradient} map of a layer ("dec" | "kv" | "enc") as soon as its
@@ -920,11 +945,12 @@ def mca_ed_bwd(rt, m, ctx, dx_out, dy_out, after_layer=None):
     B, Sx, Sy = ctx.B, ctx.Sx, ctx.Sy
     dev = dy_out.device
     grads = {}
-    total = sum(p.numel() for p in m.parameters()) + 8 * len(list(m.parameters())) + 64
+    params = module_params(m)
+    total = sum(p.numel() for p in params) + 8 * len(params) + 64
     # weight gradients of the SA / SGA layers (all 2-D parameters except the K/V projections batched across the
     # decoder layers) are written by grouped launches into an uninitialised arena; everything else starts from zero
     batched = set(id(w) for w, _ in ctx.lpkv.pairs) if L > 0 else set()
-    store = sum(p.numel() + 8 for p in m.parameters() if p.dim() == 2 and id(p) not in batched) if GROUP_WGRADS else 0
+    store = sum(p.numel() + 8 for p in params if p.dim() == 2 and id(p) not in batched) if GROUP_WGRADS else 0
     # split-K outputs of the question-side chain (2 per encoder layer + the batched K/V back-projection): one zero pool
     rows_x = B * Sx
     scratch = (2 * len(m.enc_list) + 1) * ((rows_x * H + 3) // 4 * 4) if (SPLITK_MIN_K > 0 and rows_x <= SPLITK_MAX_ROWS) else 0

@@ -6,6 +6,7 @@ synchronise.  Tensors must be CUDA tensors; 2-D operands may be row-strided view
 (stride(1) == 1).  Nothing here falls back to PyTorch math.
 """
 import ctypes
+import threading
 
 import torch
 
@@ -15,7 +16,20 @@ _BF16 = torch.bfloat16
 _F32 = torch.float32
 
 
+# The eager route (the unchanged core/exec.py) pays these helpers ~1500 times per training step: torch.cuda.current_stream()
+# and torch.cuda.current_device() go through several layers of Python (lazy-init checks, device-index parsing, a Stream
+# object) -- the two C entry points behind them are used directly (tools/host_profile_gpu.py: 14.6 -> see DESIGN.md §8).
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+_raw_device = getattr(torch._C, "_cuda_getDevice", None)
+
+
+def _current_device():
+    return _raw_device() if _raw_device is not None else torch.cuda.current_device()
+
+
 def _stream():
+    if _raw_stream is not None and _raw_device is not None:
+        return _raw_stream(_raw_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -23,20 +37,51 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
-def _req(t, dtype, name):
+# Argument validation.  Calls made from inside the overlay modules' launch chains (blocks.py via autograd._Chain) are
+# "trusted": every tensor there was allocated by the chain itself with the right dtype on the device of the module's
+# input, which check_device() validated at the chain's entry -- the ~900 per-tensor checks of a training step are skipped
+# (1.8 ms of host time on the eager route).  Direct calls of the functions below (tests, other users of the C ABI
+# wrappers) are always checked; the C ABI validates pointers, alignments and shapes in every case.
+_tls = threading.local()
+
+
+class trusted(object):
+    def __enter__(self):
+        _tls.depth = getattr(_tls, "depth", 0) + 1
+
+    def __exit__(self, *exc):
+        _tls.depth -= 1
+
+
+def check_device(t, name="input"):
+    """Entry check of a launch chain: CUDA tensor on the current device (kernels are enqueued on the current device's
+    current stream)."""
     if not t.is_cuda:
         raise capi.McanError("%s must be a CUDA tensor (the MCAN hot path has no CPU fallback)" % name)
-    if t.device.index != torch.cuda.current_device():
+    if t.device.index != _current_device():
+        raise capi.McanError("%s lives on %s but the current CUDA device is %d (one process per GPU: call "
+                             "torch.cuda.set_device first; nn.DataParallel is not supported)" %
+                             (name, t.device, _current_device()))
+
+
+def _req(t, dtype, name):
+    if getattr(_tls, "depth", 0):
+        return
+    if not t.is_cuda:
+        raise capi.McanError("%s must be a CUDA tensor (the MCAN hot path has no CPU fallback)" % name)
+    if t.device.index != _current_device():
         # kernels are enqueued on the CURRENT device's current stream (one process per GPU; nn.DataParallel
         # replicas on other devices are not supported -- use torch.distributed + dp.attach)
         raise capi.McanError("%s lives on %s but the current CUDA device is %d (one process per GPU: call "
                              "torch.cuda.set_device first; nn.DataParallel is not supported)" %
-                             (name, t.device, torch.cuda.current_device()))
+                             (name, t.device, _current_device()))
     if t.dtype != dtype:
         raise capi.McanError("%s must be %s, got %s" % (name, dtype, t.dtype))
 
 
 def _req2d(t, dtype, name):
+    if getattr(_tls, "depth", 0):
+        return
     _req(t, dtype, name)
     if t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
         raise capi.McanError("%s must be 2-D with unit inner stride" % name)
