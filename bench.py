@@ -529,6 +529,18 @@ def main():
     torch.cuda.synchronize()
     per_step = capi.launch_count - c0
     roof = gemm_roofline(probe, batch_dev, peaks)
+    # the eager route: the same kernels launched one by one from Python, as the reference's unchanged core/exec.py
+    # drives the overlay (no CUDA graph); host-bound, wall clock with a synchronize on both sides
+    eager_ms = None
+    if world == 1:
+        for _ in range(2):
+            probe._raw_step(*batch_dev)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            probe._raw_step(*batch_dev)
+        torch.cuda.synchronize()
+        eager_ms = (time.perf_counter() - t0) / 10 * 1e3
 
     # data parallel sanity: every replica applied the same summed gradients, so the parameters of all
     # ranks must still be bit-identical after ~100 optimiser steps (per-parameter checksums, max - min over ranks)
@@ -582,6 +594,10 @@ def main():
         }
         if divergence is not None:
             line["replica_checksum_divergence"] = divergence
+        if eager_ms is not None:
+            line["eager_route"] = {"ms_per_step": eager_ms, "value": BATCH / eager_ms * 1e3, "unit": "samples/s",
+                                   "note": "same kernels launched one by one from Python, no CUDA graph (the route the "
+                                           "unchanged core/exec.py takes); host-bound, 10 steps, wall clock"}
         if world == 1 and not args.skip_cpu:
             # the honest same-box bar: the unmodified reference, eager PyTorch on this GPU
             del trainer.graph

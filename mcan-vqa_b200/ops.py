@@ -175,6 +175,18 @@ def gemm_plan(m, n, k, *, accumulate=False, split_k=0, block_n=0, cta_group=0, s
     return dict(zip(keys, (int(v) for v in out)))
 
 
+_packers = {}
+
+
+def _gemm_packer():
+    pk = _packers.get("gemm")
+    if pk is None:
+        if capi.MAX_SEG != 3:
+            raise capi.McanError("ops.gemm marshals exactly 3 operand segments; capi.MAX_SEG is %d" % capi.MAX_SEG)
+        pk = _packers["gemm"] = capi.StructPacker(capi.GemmArgs)
+    return pk
+
+
 def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, seed=0, gate=None,
          gate_scale=1.0, resid=None, out_f32=None, out_bf16=None, out_lo=None, accumulate=False,
          split_k=0, block_n=0, cta_group=0, colsum=None):
@@ -197,52 +209,49 @@ def gemm(a, b, *, a_layout=0, b_layout=0, bias=None, relu=False, dropout_p=0.0, 
     n, kb = (b0.shape[0], b0.shape[1]) if b_layout == 0 else (b0.shape[1], b0.shape[0])
     if k != kb:
         raise capi.McanError("gemm: contraction mismatch %d vs %d" % (k, kb))
-    args = capi.GemmArgs()
-    for i, (ta, tb) in enumerate(zip(a_list, b_list)):
-        if ta.shape != a0.shape or tb.shape != b0.shape or ta.stride(0) != a0.stride(0) or tb.stride(0) != b0.stride(0):
-            raise capi.McanError("gemm: segments must share shape and leading dimension")
-        args.a[i] = ta.data_ptr()
-        args.b[i] = tb.data_ptr()
-    args.num_seg = len(a_list)
-    args.a_layout, args.b_layout = a_layout, b_layout
-    args.m, args.n, args.k = m, n, k
-    args.lda, args.ldb = a0.stride(0), b0.stride(0)
+    nseg = len(a_list)
+    if nseg == 1:
+        pa, pb = (a0.data_ptr(), 0, 0), (b0.data_ptr(), 0, 0)
+    else:
+        for ta, tb in zip(a_list, b_list):
+            if ta.shape != a0.shape or tb.shape != b0.shape or ta.stride(0) != a0.stride(0) or tb.stride(0) != b0.stride(0):
+                raise capi.McanError("gemm: segments must share shape and leading dimension")
+        pa = tuple(t.data_ptr() for t in a_list) + (0,) * (capi.MAX_SEG - nseg)
+        pb = tuple(t.data_ptr() for t in b_list) + (0,) * (capi.MAX_SEG - nseg)
+    p_bias = p_gate = p_resid = p_f32 = p_bf16 = p_lo = p_colsum = 0
+    ldg = ldr = ldo_f32 = ldo_bf16 = 0
     if bias is not None:
         _req(bias, _F32, "gemm bias")
-        args.bias = bias.data_ptr()
-    args.relu = 1 if relu else 0
-    args.dropout_p = float(dropout_p)
-    args.dropout_seed = int(seed) & 0xFFFFFFFF
-    args.dropout_seed_dev = _seed_ptr()
+        p_bias = bias.data_ptr()
     if gate is not None:
         _req2d(gate, _BF16, "gemm gate")
-        args.gate, args.ldg = gate.data_ptr(), gate.stride(0)
-    args.gate_scale = float(gate_scale)
+        p_gate, ldg = gate.data_ptr(), gate.stride(0)
     if resid is not None:
         _req2d(resid, _F32, "gemm resid")
-        args.resid, args.ldr = resid.data_ptr(), resid.stride(0)
+        p_resid, ldr = resid.data_ptr(), resid.stride(0)
     if out_f32 is not None:
         _req2d(out_f32, _F32, "gemm out_f32")
-        args.out_f32, args.ldo_f32 = out_f32.data_ptr(), out_f32.stride(0)
+        p_f32, ldo_f32 = out_f32.data_ptr(), out_f32.stride(0)
     if out_bf16 is not None:
         _req2d(out_bf16, _BF16, "gemm out_bf16")
-        args.out_bf16, args.ldo_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
+        p_bf16, ldo_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
     if out_lo is not None:
         _req2d(out_lo, _BF16, "gemm out_lo")
         if out_bf16 is None or out_lo.stride(0) != out_bf16.stride(0):
             raise capi.McanError("gemm: out_lo needs out_bf16 with the same leading dimension")
-        args.out_bf16_lo = out_lo.data_ptr()
+        p_lo = out_lo.data_ptr()
     if colsum is not None:
         _req(colsum, _F32, "gemm colsum")
         if colsum.numel() != n or not colsum.is_contiguous():
             raise capi.McanError("gemm: colsum must be a contiguous fp32 vector of length N")
-        args.colsum = colsum.data_ptr()
-    args.accumulate = 1 if accumulate else 0
-    args.split_k = int(split_k)
-    args.block_n = int(block_n)
-    args.cta_group = int(cta_group)
-    args.stream = _stream()
-    capi.check(lib.mcan_gemm(ctypes.byref(args)), "mcan_gemm")
+        p_colsum = colsum.data_ptr()
+    # one pack_into in the field order of capi.GemmArgs (include/mcan_b200.h: mcan_gemm_args)
+    args = _gemm_packer().pack(
+        pa[0], pa[1], pa[2], pb[0], pb[1], pb[2], nseg, a_layout, b_layout, m, n, k, a0.stride(0), b0.stride(0),
+        p_bias, 1 if relu else 0, float(dropout_p), int(seed) & 0xFFFFFFFF, _seed_ptr() or 0,
+        p_gate, ldg, float(gate_scale), p_resid, ldr, p_f32, ldo_f32, p_bf16, p_lo, ldo_bf16, p_colsum,
+        1 if accumulate else 0, int(split_k), int(block_n), int(cta_group), _stream() or 0)
+    capi.check(lib.mcan_gemm(args), "mcan_gemm")
 
 
 def gemm_grouped(problems, split_k=0, accumulate=True):

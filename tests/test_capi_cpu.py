@@ -72,3 +72,40 @@ def test_no_cpu_fallback(lib):
         ops.layernorm_fwd(x, torch.ones(64), torch.zeros(64), 1e-6, y_f32=torch.empty_like(x))
     with pytest.raises(lib.McanError):
         ops.gemm(x.to(torch.bfloat16), x.to(torch.bfloat16), out_f32=torch.empty(4, 4))
+
+
+def test_struct_packer_matches_field_by_field_fill(lib):
+    """ops.gemm fills mcan_gemm_args with one struct.pack_into; the bytes must equal a ctypes field-by-field fill."""
+    import random
+    rnd = random.Random(7)
+    pk = lib.StructPacker(lib.GemmArgs)
+    assert pk.packer.size == ctypes.sizeof(lib.GemmArgs)
+    for _ in range(20):
+        args = lib.GemmArgs()
+        vals = []
+        for name, ctype in lib.GemmArgs._fields_:
+            if hasattr(ctype, "_length_"):
+                arr = getattr(args, name)
+                for i in range(ctype._length_):
+                    v = rnd.randrange(1, 1 << 47)
+                    arr[i] = v
+                    vals.append(v)
+            elif ctype is ctypes.c_float:
+                v = rnd.choice([0.0, 0.1, 1.0, 0.25])
+                setattr(args, name, v)
+                vals.append(v)
+            elif ctype is ctypes.c_void_p:
+                v = rnd.choice([0, rnd.randrange(1, 1 << 47)])
+                setattr(args, name, v or None)
+                vals.append(v)
+            elif ctype is ctypes.c_uint32:
+                v = rnd.randrange(0, 1 << 32)
+                setattr(args, name, v)
+                vals.append(v)
+            else:
+                v = rnd.randrange(0, 1 << 20)
+                setattr(args, name, v)
+                vals.append(v)
+        assert len(vals) == pk.count
+        ptr = pk.pack(*vals)
+        assert ctypes.string_at(ptr, pk.packer.size) == ctypes.string_at(ctypes.byref(args), ctypes.sizeof(args))
