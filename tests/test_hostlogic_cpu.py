@@ -209,3 +209,46 @@ def test_dry_run_whole_net_host_logic(monkeypatch, group, store, bf16_sink):
     assert len(out) == 8 and out[0].shape == (B, A) and out[2].dtype == torch.bool and out[5].shape == (B, 1, 1, 7)
     out[0].sum().backward()
     assert net.proj.weight.grad is not None
+
+
+def test_trusted_scope_skips_checks_only_inside_and_per_thread():
+    """ops.trusted(): the per-tensor argument checks are skipped inside the overlay's launch chains only -- a direct call
+    outside is still validated, also from another thread while one thread is inside a trusted scope."""
+    import threading
+    from mcan_vqa_b200 import capi, ops
+    x = torch.randn(4, 64)                                   # CPU tensor: must be rejected by a checked call
+    with pytest.raises(capi.McanError):
+        ops._req2d(x, torch.float32, "x")
+    seen = {}
+    with ops.trusted():
+        ops._req2d(x, torch.float32, "x")                    # skipped
+        with ops.trusted():
+            ops._req(x, torch.bfloat16, "x")                 # nested: still skipped
+
+        def other():
+            try:
+                ops._req2d(x, torch.float32, "x")
+                seen["other"] = "skipped"
+            except capi.McanError:
+                seen["other"] = "checked"
+        t = threading.Thread(target=other)
+        t.start()
+        t.join()
+    assert seen["other"] == "checked"
+    with pytest.raises(capi.McanError):
+        ops._req2d(x, torch.float32, "x")
+    with pytest.raises(capi.McanError):
+        ops.check_device(x)
+
+
+def test_module_params_cache():
+    from mcan_vqa_b200 import blocks
+    m = torch.nn.Sequential(torch.nn.Linear(4, 4), torch.nn.Linear(4, 2))
+    a = blocks.module_params(m)
+    assert [id(p) for p in a] == [id(p) for p in m.parameters()]
+    assert blocks.module_params(m) is a                      # no second tree walk
+    m.double()                                               # conversions keep the Parameter objects
+    assert all(p is q for p, q in zip(blocks.module_params(m), m.parameters()))
+    m[1] = torch.nn.Linear(4, 3)                             # replaced parameters: the owner invalidates
+    blocks.invalidate_module_params(m)
+    assert [id(p) for p in blocks.module_params(m)] == [id(p) for p in m.parameters()]
