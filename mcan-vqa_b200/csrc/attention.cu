@@ -5,8 +5,10 @@
 // (mca.py:76) and P.V (mca.py:78) run on warp-level tensor-core MMAs with the score tile held
 // in registers -- the [B,h,Sq,Sk] score tensor of the reference never exists in HBM, and the
 // head split / merge transposes (mca.py:33-59) become pointer arithmetic on the [rows, H]
-// activations.  The kernel is HBM/latency bound (1.4-2.7 % of the model's FLOPs), so it
-// uses mma.sync m16n8k16 on tiles that fit one warp rather than tcgen05.
+// activations.  These kernels use mma.sync m16n8k16 on tiles that fit one warp; they serve the small
+// problems (question side, question-guided attention with <= 32 keys), head dim 128, split precision and
+// the fused bias gradients.  The image self-attention (head dim 64, 49..128 queries, 33..128 keys: one
+// M = 128 UMMA tile per (batch, head)) is dispatched to the tcgen05 / TMEM kernels of attention_tc.cu.
 //
 // Backward recomputes P from Q,K and the dropout mask from the seed, then
 //   dV = Pd^T dO,  dPd = dO V^T,  dS = P o (m/(1-p) dPd - rowsum(Pd o dPd)), 0 where masked,
